@@ -1,0 +1,187 @@
+/*
+ * rcb200.h -- C ABI of the B200-native chunk-parallel range coder.
+ *
+ * Drop-in boundary for the encode/decode hot path of the reference crate
+ * diegodox/range_coder_rust (crate `range_coder` v0.1.0).  The reference is a
+ * Rust library with a per-symbol API and no FFI of its own; these are the entry
+ * points a Rust `extern "C"` block binds to replace the
+ * per-symbol loops of its callers.  Each entry point cites the reference
+ * interface it replaces (paths under /root/reference).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types.
+ *   - every function returns RCB_OK (0) or a negative rcb_error; nothing unwinds.
+ *   - pointers named d_* are device pointers on the ctx's device, 16-byte
+ *     aligned; h_* are host pointers.  Caller owns all buffers; the ctx owns
+ *     scratch (staging rows, lengths) and is not thread-safe (one ctx per GPU
+ *     per thread -- the reference's Encoder/Decoder are single-threaded owned
+ *     values too, src/encoder.rs:7-11, src/decoder.rs:6-12).
+ *   - work is issued on the ctx's CUDA stream.  Entry points that return a
+ *     host result synchronise that stream; the *_async forms do not.
+ *   - a "chunk" is one independent reference `Encoder` run: chunk i covers
+ *     symbols [i*chunk_syms, min(n_syms,(i+1)*chunk_syms)) and its bytes
+ *     stream[offsets[i] .. offsets[i+1]) are exactly what
+ *     `Encoder::new(); encode(..)*; finish()` (src/encoder.rs:13-46) returns
+ *     for those symbols under that chunk's model.
+ */
+#ifndef RCB200_H
+#define RCB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RCB_VERSION 100 /* 0.1.0, tracks the reference crate version (Cargo.toml:3) */
+
+typedef enum rcb_error {
+    RCB_OK = 0,
+    RCB_ERR_INVALID_ARGUMENT = -1,
+    RCB_ERR_CUDA = -2,             /* a CUDA runtime call failed; see rcb_last_cuda_error */
+    RCB_ERR_ZERO_TOTAL = -3,       /* total_freq == 0: divide-by-zero panic, src/range_coder.rs:39 */
+    RCB_ERR_ZERO_FREQ_SYMBOL = -4, /* c_freq == 0 for a coded symbol: the reference never returns
+                                      (range == 0 keeps loop 1 alive, src/range_coder.rs:83-85) */
+    RCB_ERR_LOWER_OVERFLOW = -5,   /* RangeCoderError::LowerBoundOverflow, src/error.rs:6-10 */
+    RCB_ERR_UPPER_OVERFLOW = -6,   /* RangeCoderError::UpperBoundOverflow, src/error.rs:12 */
+    RCB_ERR_SYMBOL_OUT_OF_RANGE = -7, /* index >= alphabet: Vec::get().unwrap() panic,
+                                         examples/sample_impl.rs:19 */
+    RCB_ERR_OUT_CAPACITY = -8,     /* caller's output buffer too small */
+    RCB_ERR_TRUNCATED_STREAM = -9, /* Decoder ran out of bytes: pop_front().unwrap(),
+                                      src/decoder.rs:33 */
+    RCB_ERR_INVALID_MODEL = -10,   /* table has cum_freq > total_freq (outside the path) */
+    RCB_ERR_UNSUPPORTED = -11,
+    RCB_ERR_NO_DEVICE = -12        /* no CUDA device: there is no CPU fallback */
+} rcb_error;
+
+/* per-chunk status words written to d_status (0 = ok) */
+enum {
+    RCB_ST_OK = 0,
+    RCB_ST_ZERO_FREQ = 1,
+    RCB_ST_LOWER_OVERFLOW = 2,
+    RCB_ST_UPPER_OVERFLOW = 3,
+    RCB_ST_SYMBOL_RANGE = 4,
+    RCB_ST_OUT_CAPACITY = 5,
+    RCB_ST_TRUNCATED = 6
+};
+
+/* model flags reported by rcb_model_info */
+enum {
+    RCB_MODEL_POW2 = 1,       /* total_freq is a power of two: range/total is a shift */
+    RCB_MODEL_CONSISTENT = 2, /* cum+c <= total for every symbol: overflow errors unreachable */
+    RCB_MODEL_REGULAR = 4     /* cum[i+1] == cum[i]+c[i]: table-driven decode lookup is sound */
+};
+
+typedef struct rcb_ctx rcb_ctx;
+typedef struct rcb_model rcb_model;
+
+const char *rcb_strerror(int err);
+int rcb_version(void);
+/* last cudaError_t seen by this ctx (0 = cudaSuccess) and its string */
+int rcb_last_cuda_error(const rcb_ctx *ctx, const char **msg);
+
+/* ---- context --------------------------------------------------------------
+ * Replaces nothing in the reference (it has no runtime); owns the stream and
+ * scratch.  `stream` is a cudaStream_t (NULL = a private non-blocking stream). */
+int rcb_ctx_create(int device, void *stream, rcb_ctx **out);
+int rcb_ctx_destroy(rcb_ctx *ctx);
+int rcb_ctx_set_stream(rcb_ctx *ctx, void *stream);
+int rcb_ctx_synchronize(rcb_ctx *ctx);
+/* tuning knobs (0 = default): threads per block of the coder kernels */
+int rcb_ctx_set_block_threads(rcb_ctx *ctx, int encode_threads, int decode_threads);
+/* kernels launched by this ctx so far (bench.py's gpu_launches) */
+uint64_t rcb_ctx_launch_count(const rcb_ctx *ctx);
+/* Per-kernel CUDA-event timing on the launching stream (off by default).
+ * rcb_ctx_get_timings synchronises and fills ms[0..n): [0] encode kernel,
+ * [1] length scan, [2] gather (compaction), [3] decode kernel, [4] decode
+ * status summary of the most recent encode / decode issued with timing on. */
+int rcb_ctx_enable_timing(rcb_ctx *ctx, int on);
+int rcb_ctx_get_timings(rcb_ctx *ctx, float *ms, int n);
+
+/* ---- frequency model ------------------------------------------------------
+ * Dense snapshot of a `PModel` (src/pmodel.rs:4-13): c_freq(i), cum_freq(i)
+ * for i < K and total_freq().  PModel has no alphabet-size method, so K is
+ * explicit.  n_models == 1: one static model shared by all chunks;
+ * n_models == n_chunks: one model per chunk. */
+int rcb_model_create(rcb_ctx *ctx, uint32_t K, uint64_t n_models, rcb_model **out);
+int rcb_model_destroy(rcb_model *m);
+
+/* FreqTable::add_alphabet_freq in a loop (examples/sample_impl.rs:58-60,78-80).
+ * chunk_syms == 0: one histogram of all n_syms into d_counts = uint64[K].
+ * chunk_syms  > 0: one histogram per chunk into d_counts = uint32[n_chunks][K].
+ * Symbols are u8 (sym_bytes 1) or u16 little-endian (sym_bytes 2); a symbol
+ * >= K is not counted and makes the call return RCB_ERR_SYMBOL_OUT_OF_RANGE. */
+int rcb_histogram(rcb_ctx *ctx, const void *d_syms, uint64_t n_syms, int sym_bytes,
+                  uint32_t K, uint64_t chunk_syms, void *d_counts);
+
+/* FreqTable::calc_cum (examples/sample_impl.rs:61-69): c = counts, cum =
+ * exclusive prefix sum, total = sum.  count_bytes is 8 (uint64[n_models][K]) or
+ * 4 (uint32[n_models][K]).  When a u64 sum exceeds 2^32-1 (total_freq is u32,
+ * src/pmodel.rs:10) the counts are first shifted right by the smallest sh with
+ * (sum>>sh)+K <= 2^32-1, non-zero counts staying >= 1 (build-defined
+ * extension; identical in the oracle).  Synchronises. */
+int rcb_model_from_counts(rcb_ctx *ctx, rcb_model *m, const void *d_counts, int count_bytes);
+
+/* Snapshot of arbitrary PModel tables from host memory:
+ * h_c, h_cum: uint32[n_models][K]; h_total: uint32[n_models].  Synchronises. */
+int rcb_model_from_tables(rcb_ctx *ctx, rcb_model *m, const uint32_t *h_c,
+                          const uint32_t *h_cum, const uint32_t *h_total);
+
+/* Read model `index` back (any pointer may be NULL). */
+int rcb_model_get_tables(rcb_ctx *ctx, const rcb_model *m, uint64_t index, uint32_t *h_c,
+                         uint32_t *h_cum, uint32_t *h_total, uint32_t *h_flags);
+
+/* ---- encode: replaces the caller's loop over Encoder::encode + finish ------
+ * (examples/sample_impl.rs:92-98 -> src/encoder.rs:24-46 ->
+ * src/range_coder.rs:53-135).  Output: d_out[0 .. d_offsets[n_chunks]) and
+ * d_offsets = uint64[n_chunks+1]; d_status = uint32[n_chunks] (may be NULL).
+ * h_out_bytes receives d_offsets[n_chunks].  Returns the first chunk error
+ * mapped to rcb_error, or RCB_ERR_OUT_CAPACITY if out_cap is too small (then
+ * *h_out_bytes is the size needed). */
+int rcb_encode_chunks(rcb_ctx *ctx, const void *d_syms, uint64_t n_syms, int sym_bytes,
+                      uint64_t chunk_syms, const rcb_model *m, uint8_t *d_out,
+                      uint64_t out_cap, uint64_t *d_offsets, uint32_t *d_status,
+                      uint64_t *h_out_bytes);
+/* same, no synchronisation and no host result (errors stay in d_status);
+ * call rcb_encode_result later to fetch them. */
+int rcb_encode_chunks_async(rcb_ctx *ctx, const void *d_syms, uint64_t n_syms, int sym_bytes,
+                            uint64_t chunk_syms, const rcb_model *m, uint8_t *d_out,
+                            uint64_t out_cap, uint64_t *d_offsets, uint32_t *d_status);
+int rcb_encode_result(rcb_ctx *ctx, uint64_t *h_out_bytes);
+/* an out_cap that always suffices for this model / shape */
+uint64_t rcb_encode_bound(rcb_ctx *ctx, const rcb_model *m, uint64_t n_syms, int sym_bytes,
+                          uint64_t chunk_syms);
+
+/* ---- decode: replaces Decoder::new + the loop over Decoder::decode ---------
+ * (examples/sample_impl.rs:110-120 -> src/decoder.rs:14-54, with
+ * examples/sample_impl.rs:27-45 as the built-in find_index).  The symbol count
+ * is out-of-band exactly like in the reference. d_stream must be readable up
+ * to the next multiple of 16 bytes past d_offsets[n_chunks]. */
+int rcb_decode_chunks(rcb_ctx *ctx, const uint8_t *d_stream, const uint64_t *d_offsets,
+                      uint64_t n_syms, int sym_bytes, uint64_t chunk_syms,
+                      const rcb_model *m, void *d_syms_out, uint32_t *d_status);
+int rcb_decode_chunks_async(rcb_ctx *ctx, const uint8_t *d_stream, const uint64_t *d_offsets,
+                            uint64_t n_syms, int sym_bytes, uint64_t chunk_syms,
+                            const rcb_model *m, void *d_syms_out, uint32_t *d_status);
+int rcb_decode_result(rcb_ctx *ctx);
+
+/* ---- host-buffer convenience (H2D, encode/decode, D2H inside the call) -----
+ * What a Rust `gpu::encode_chunks(&pmodel, K, &symbols, chunk_syms)` binds. */
+int rcb_encode_host(rcb_ctx *ctx, const void *h_syms, uint64_t n_syms, int sym_bytes,
+                    uint64_t chunk_syms, const rcb_model *m, uint8_t *h_out, uint64_t out_cap,
+                    uint64_t *h_offsets, uint64_t *h_out_bytes);
+int rcb_decode_host(rcb_ctx *ctx, const uint8_t *h_stream, const uint64_t *h_offsets,
+                    uint64_t n_syms, int sym_bytes, uint64_t chunk_syms, const rcb_model *m,
+                    void *h_syms_out);
+
+/* ---- synthetic data (benchmark inputs; not in the reference)
+ * symbol j = #{ i < K-1 : thr[t][i] <= mix64(seed + j*GOLDEN) >> 32 },
+ * t = (j / chunk_syms) % n_tables; h_thr = uint32[n_tables][K-1]. */
+int rcb_generate(rcb_ctx *ctx, void *d_out, uint64_t first, uint64_t n, int sym_bytes,
+                 uint32_t K, uint64_t seed, const uint32_t *h_thr, uint32_t n_tables,
+                 uint64_t chunk_syms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RCB200_H */

@@ -1,0 +1,265 @@
+"""Thin Python front end over the C ABI: torch supplies device memory and
+streams (plumbing); every byte of coding work happens in librcb200.so.
+
+Names follow the reference's domain: symbols, chunks, frequency tables
+(`c_freq`, `cum_freq`, `total_freq` -- src/pmodel.rs:4-13), code streams.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import RcbError
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+class Model:
+    """Dense snapshot of a PModel (src/pmodel.rs:4-13): one table shared by all
+    chunks (n_models == 1) or one per chunk."""
+
+    def __init__(self, ctx, K, n_models=1):
+        self.ctx = ctx
+        self.K = int(K)
+        self.n_models = int(n_models)
+        h = ctypes.c_void_p()
+        ctx._check(ctx.lib.rcb_model_create(ctx.h, self.K, self.n_models, ctypes.byref(h)), "rcb_model_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.rcb_model_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def tables(self, index=0):
+        """(c[K], cum[K], total, flags) of model `index`, copied to the host."""
+        c = np.zeros(self.K, dtype=np.uint32)
+        cum = np.zeros(self.K, dtype=np.uint32)
+        total = ctypes.c_uint32()
+        flags = ctypes.c_uint32()
+        self.ctx._check(
+            self.ctx.lib.rcb_model_get_tables(self.ctx.h, self.h, index, _np_ptr(c), _np_ptr(cum),
+                                              ctypes.byref(total), ctypes.byref(flags)),
+            "rcb_model_get_tables")
+        return c, cum, total.value, flags.value
+
+
+class Context:
+    """One context per GPU (include/rcb200.h); issues work on the torch stream
+    that is current when it is created (or on `stream`)."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RcbError(_lib.RCB_ERR_NO_DEVICE, "Context")
+        self.device = torch.device("cuda", device)
+        with torch.cuda.device(self.device):
+            s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        self.stream = s
+        h = ctypes.c_void_p()
+        rc = self.lib.rcb_ctx_create(device, ctypes.c_void_p(s.cuda_stream), ctypes.byref(h))
+        if rc:
+            raise RcbError(rc, "rcb_ctx_create")
+        self.h = h
+
+    # ------------------------------------------------------------ plumbing
+    def _check(self, rc, where):
+        if rc:
+            detail = ""
+            if rc == _lib.RCB_ERR_CUDA:
+                msg = ctypes.c_char_p()
+                self.lib.rcb_last_cuda_error(self.h, ctypes.byref(msg))
+                detail = (msg.value or b"").decode()
+            raise RcbError(rc, where, detail)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rcb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        self._check(self.lib.rcb_ctx_synchronize(self.h), "rcb_ctx_synchronize")
+
+    def set_block_threads(self, encode_threads=0, decode_threads=0):
+        self._check(self.lib.rcb_ctx_set_block_threads(self.h, encode_threads, decode_threads),
+                    "rcb_ctx_set_block_threads")
+
+    def enable_timing(self, on=True):
+        self._check(self.lib.rcb_ctx_enable_timing(self.h, 1 if on else 0), "rcb_ctx_enable_timing")
+
+    def timings(self):
+        """ms of (encode kernel, length scan, gather, decode kernel, status summary)."""
+        ms = (ctypes.c_float * 5)()
+        self._check(self.lib.rcb_ctx_get_timings(self.h, ms, 5), "rcb_ctx_get_timings")
+        return dict(zip(("encode_kernel", "scan", "gather", "decode_kernel", "summary"), [float(x) for x in ms]))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.rcb_ctx_launch_count(self.h))
+
+    @staticmethod
+    def _sym_bytes(t):
+        if t.dtype == torch.uint8:
+            return 1
+        if t.dtype in (torch.int16, torch.uint16):
+            return 2
+        raise TypeError("symbols must be uint8 or (u)int16 tensors")
+
+    # --------------------------------------------------------------- model
+    def histogram(self, syms, K, chunk_syms=0):
+        """FreqTable::add_alphabet_freq loop (examples/sample_impl.rs:58-60,78-80).
+        chunk_syms == 0 -> int64[K]; else int32[n_chunks][K] (bit patterns of u64/u32)."""
+        n = syms.numel()
+        sb = self._sym_bytes(syms)
+        if chunk_syms == 0:
+            counts = torch.empty(K, dtype=torch.int64, device=self.device)
+        else:
+            n_chunks = (n + chunk_syms - 1) // chunk_syms
+            counts = torch.empty((n_chunks, K), dtype=torch.int32, device=self.device)
+        self._check(self.lib.rcb_histogram(self.h, _ptr(syms), n, sb, K, chunk_syms, _ptr(counts)),
+                    "rcb_histogram")
+        return counts
+
+    def model_from_counts(self, counts, K=None):
+        """FreqTable::calc_cum (examples/sample_impl.rs:61-69) on device counts."""
+        if counts.dim() == 1:
+            n_models, k = 1, counts.shape[0]
+        else:
+            n_models, k = counts.shape
+        K = int(K or k)
+        assert k == K
+        cb = 8 if counts.dtype == torch.int64 else 4
+        assert counts.dtype in (torch.int64, torch.int32)
+        m = Model(self, K, n_models)
+        self._check(self.lib.rcb_model_from_counts(self.h, m.h, _ptr(counts.contiguous()), cb),
+                    "rcb_model_from_counts")
+        return m
+
+    def model_from_tables(self, c, cum, total):
+        """Snapshot of PModel tables given as host arrays: c/cum [K] or [n_models][K]."""
+        c = np.ascontiguousarray(c, dtype=np.uint32)
+        cum = np.ascontiguousarray(cum, dtype=np.uint32)
+        if c.ndim == 1:
+            n_models, K = 1, c.shape[0]
+        else:
+            n_models, K = c.shape
+        total = np.ascontiguousarray(np.atleast_1d(total), dtype=np.uint32)
+        assert cum.shape == c.shape and total.shape[0] == n_models
+        m = Model(self, K, n_models)
+        self._check(self.lib.rcb_model_from_tables(self.h, m.h, _np_ptr(c), _np_ptr(cum), _np_ptr(total)),
+                    "rcb_model_from_tables")
+        return m
+
+    # -------------------------------------------------------- encode/decode
+    def encode_bound(self, model, n_syms, sym_bytes, chunk_syms):
+        return int(self.lib.rcb_encode_bound(self.h, model.h, n_syms, sym_bytes, chunk_syms))
+
+    def encode_chunks(self, syms, chunk_syms, model, out=None, offsets=None, status=None, sync=True):
+        """Every chunk through Encoder::encode ... finish (src/encoder.rs:24-46).
+        Returns (stream uint8[cap], offsets int64[n_chunks+1], n_bytes or None)."""
+        n = syms.numel()
+        sb = self._sym_bytes(syms)
+        n_chunks = (n + chunk_syms - 1) // chunk_syms
+        if out is None:
+            out = torch.empty(self.encode_bound(model, n, sb, chunk_syms) + 16, dtype=torch.uint8,
+                              device=self.device)
+        if offsets is None:
+            offsets = torch.empty(n_chunks + 1, dtype=torch.int64, device=self.device)
+        if sync:
+            nbytes = ctypes.c_uint64()
+            rc = self.lib.rcb_encode_chunks(self.h, _ptr(syms), n, sb, chunk_syms, model.h, _ptr(out),
+                                            out.numel(), _ptr(offsets), _ptr(status), ctypes.byref(nbytes))
+            self._check(rc, "rcb_encode_chunks")
+            return out, offsets, int(nbytes.value)
+        rc = self.lib.rcb_encode_chunks_async(self.h, _ptr(syms), n, sb, chunk_syms, model.h, _ptr(out),
+                                              out.numel(), _ptr(offsets), _ptr(status))
+        self._check(rc, "rcb_encode_chunks_async")
+        return out, offsets, None
+
+    def encode_result(self):
+        nbytes = ctypes.c_uint64()
+        self._check(self.lib.rcb_encode_result(self.h, ctypes.byref(nbytes)), "rcb_encode_result")
+        return int(nbytes.value)
+
+    def decode_chunks(self, stream, offsets, n_syms, chunk_syms, model, sym_bytes=1, out=None, status=None,
+                      sync=True):
+        """Every chunk through Decoder::new + decode (src/decoder.rs:14-54)."""
+        if out is None:
+            dt = torch.uint8 if sym_bytes == 1 else torch.int16
+            out = torch.empty(n_syms, dtype=dt, device=self.device)
+        fn = self.lib.rcb_decode_chunks if sync else self.lib.rcb_decode_chunks_async
+        rc = fn(self.h, _ptr(stream), _ptr(offsets), n_syms, sym_bytes, chunk_syms, model.h, _ptr(out),
+                _ptr(status))
+        self._check(rc, "rcb_decode_chunks")
+        return out
+
+    def decode_result(self):
+        self._check(self.lib.rcb_decode_result(self.h), "rcb_decode_result")
+
+    # ------------------------------------------------- host-buffer entry points
+    def encode_host(self, syms_np, chunk_syms, model, out_np=None):
+        syms_np = np.ascontiguousarray(syms_np)
+        sb = syms_np.dtype.itemsize
+        n = syms_np.size
+        n_chunks = (n + chunk_syms - 1) // chunk_syms
+        if out_np is None:
+            out_np = np.empty(self.encode_bound(model, n, sb, chunk_syms) + 16, dtype=np.uint8)
+        offsets = np.zeros(n_chunks + 1, dtype=np.uint64)
+        nbytes = ctypes.c_uint64()
+        rc = self.lib.rcb_encode_host(self.h, _np_ptr(syms_np), n, sb, chunk_syms, model.h, _np_ptr(out_np),
+                                      out_np.size, _np_ptr(offsets), ctypes.byref(nbytes))
+        self._check(rc, "rcb_encode_host")
+        return out_np, offsets, int(nbytes.value)
+
+    def decode_host(self, stream_np, offsets_np, n_syms, chunk_syms, model, sym_bytes=1, out_np=None):
+        stream_np = np.ascontiguousarray(stream_np, dtype=np.uint8)
+        offsets_np = np.ascontiguousarray(offsets_np, dtype=np.uint64)
+        if out_np is None:
+            out_np = np.empty(n_syms, dtype=np.uint8 if sym_bytes == 1 else np.uint16)
+        rc = self.lib.rcb_decode_host(self.h, _np_ptr(stream_np), _np_ptr(offsets_np), n_syms, sym_bytes,
+                                      chunk_syms, model.h, _np_ptr(out_np))
+        self._check(rc, "rcb_decode_host")
+        return out_np
+
+    # ------------------------------------------------------- synthetic data
+    def generate(self, n, K, seed, thresholds, sym_bytes=1, chunk_syms=0, first=0, out=None):
+        """Counter-based synthetic symbols; thresholds uint32[n_tables][K-1]."""
+        thr = np.ascontiguousarray(thresholds, dtype=np.uint32)
+        if thr.ndim == 1:
+            thr = thr[None, :]
+        assert thr.shape[1] == K - 1
+        if out is None:
+            dt = torch.uint8 if sym_bytes == 1 else torch.int16
+            out = torch.empty(n, dtype=dt, device=self.device)
+        rc = self.lib.rcb_generate(self.h, _ptr(out), first, n, sym_bytes, K, seed, _np_ptr(thr), thr.shape[0],
+                                   chunk_syms)
+        self._check(rc, "rcb_generate")
+        return out
+
+
+def zipf_thresholds(K, s):
+    """floor(2^32 * CDF(i)) for i < K-1 of P(i) ~ (i+1)^-s, computed once on the
+    host in double; shared verbatim by the CPU and GPU generators."""
+    w = np.arange(1, K + 1, dtype=np.float64) ** (-float(s))
+    cdf = np.cumsum(w) / np.sum(w)
+    thr = np.floor(cdf[: K - 1] * 4294967296.0)
+    return np.minimum(thr, 4294967295.0).astype(np.uint32)

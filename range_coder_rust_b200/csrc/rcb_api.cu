@@ -1,0 +1,830 @@
+// rcb_api.cu -- C ABI (include/rcb200.h) over the sm_100a kernels.
+// There is no CPU implementation behind these entry points: without a CUDA
+// device every call fails with RCB_ERR_NO_DEVICE / RCB_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+
+#include "../../include/rcb200.h"
+#include "rcb_kernels.cuh"
+
+using namespace rcb;
+
+static_assert(sizeof(ModelHdr) == 48, "ModelHdr layout");
+static_assert(sizeof(LutEntry) == 16, "LutEntry layout");
+static_assert((int)RCB_ST_TRUNCATED == (int)ST_TRUNCATED, "status codes");
+static_assert((int)RCB_MODEL_REGULAR == (int)MODEL_REGULAR, "model flags");
+
+#define LUT_CAP 4096u       // buckets of the shared-model decode LUT (64 KiB of shared memory)
+#define MAX_K_SHARED 4096u  // table + LUT must fit 227 KiB of shared memory
+#define MAX_K 65536u
+
+struct rcb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int enc_threads = 128, dec_threads = 128;
+    int sm_count = 148;
+    uint8_t* staging = nullptr;
+    size_t staging_bytes = 0;
+    uint32_t* lens = nullptr;
+    uint32_t* status = nullptr;
+    size_t chunk_cap = 0;
+    unsigned long long* d_summary = nullptr;  // [0..3] encode, [4..7] decode
+    unsigned long long* h_summary = nullptr;  // pinned mirror
+    uint32_t* d_words = nullptr;              // [0] min c, [1] model bad bits, [2] hist oob, [3] max total
+    uint32_t* h_words = nullptr;              // pinned mirror
+    void* h2d = nullptr;                      // device scratch of the host-buffer entry points
+    size_t h2d_bytes = 0;
+    cudaError_t last_err = cudaSuccess;
+    uint64_t launches = 0;
+    uint64_t pending_pitch = 0, pending_out_cap = 0, pending_n_chunks = 0;
+    const uint64_t* pending_offsets = nullptr;
+    bool timing = false;
+    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ev_enc = false, ev_dec = false;
+};
+
+#define EV(c, i)                                                   \
+    do {                                                           \
+        if ((c)->timing) cudaEventRecord((c)->ev[i], (c)->stream); \
+    } while (0)
+
+struct rcb_model {
+    rcb_ctx* ctx = nullptr;
+    uint32_t K = 0;
+    uint64_t n_models = 0;
+    uint2* d_tab = nullptr;
+    uint32_t* d_total = nullptr;
+    ModelHdr* d_hdr = nullptr;
+    LutEntry* d_lut = nullptr;
+    ModelHdr h_hdr0;       // header of model 0 (the shared model)
+    uint32_t min_c = 0;    // smallest non-zero c over all models
+    uint32_t max_total = 0;
+    uint32_t bad_bits = 0; // 4: some model inconsistent, 8: some model irregular
+    bool ready = false;
+};
+
+#define CK(ctx, call)                                  \
+    do {                                               \
+        cudaError_t e__ = (call);                      \
+        if (e__ != cudaSuccess) {                      \
+            (ctx)->last_err = e__;                     \
+            return RCB_ERR_CUDA;                       \
+        }                                              \
+    } while (0)
+
+#define CK_LAUNCH(ctx)                                 \
+    do {                                               \
+        (ctx)->launches++;                             \
+        cudaError_t e__ = cudaGetLastError();          \
+        if (e__ != cudaSuccess) {                      \
+            (ctx)->last_err = e__;                     \
+            return RCB_ERR_CUDA;                       \
+        }                                              \
+    } while (0)
+
+extern "C" const char* rcb_strerror(int err) {
+    switch (err) {
+        case RCB_OK: return "ok";
+        case RCB_ERR_INVALID_ARGUMENT: return "invalid argument";
+        case RCB_ERR_CUDA: return "CUDA error";
+        case RCB_ERR_ZERO_TOTAL: return "total_freq is zero (reference: divide-by-zero panic)";
+        case RCB_ERR_ZERO_FREQ_SYMBOL: return "coded symbol has c_freq == 0 (reference: never returns)";
+        case RCB_ERR_LOWER_OVERFLOW: return "RangeCoderError::LowerBoundOverflow";
+        case RCB_ERR_UPPER_OVERFLOW: return "RangeCoderError::UpperBoundOverflow";
+        case RCB_ERR_SYMBOL_OUT_OF_RANGE: return "symbol index >= alphabet size";
+        case RCB_ERR_OUT_CAPACITY: return "output buffer too small";
+        case RCB_ERR_TRUNCATED_STREAM: return "code stream truncated (reference: pop_front panic)";
+        case RCB_ERR_INVALID_MODEL: return "invalid model table (cum_freq > total_freq)";
+        case RCB_ERR_UNSUPPORTED: return "unsupported configuration";
+        case RCB_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+        default: return "unknown error";
+    }
+}
+
+extern "C" int rcb_version(void) { return RCB_VERSION; }
+
+extern "C" int rcb_last_cuda_error(const rcb_ctx* ctx, const char** msg) {
+    if (!ctx) return 0;
+    if (msg) *msg = cudaGetErrorString(ctx->last_err);
+    return (int)ctx->last_err;
+}
+
+static int status_to_error(uint32_t st) {
+    switch (st) {
+        case ST_OK: return RCB_OK;
+        case ST_ZERO_FREQ: return RCB_ERR_ZERO_FREQ_SYMBOL;
+        case ST_LOWER_OVERFLOW: return RCB_ERR_LOWER_OVERFLOW;
+        case ST_UPPER_OVERFLOW: return RCB_ERR_UPPER_OVERFLOW;
+        case ST_SYMBOL_RANGE: return RCB_ERR_SYMBOL_OUT_OF_RANGE;
+        case ST_OUT_CAPACITY: return RCB_ERR_OUT_CAPACITY;
+        case ST_TRUNCATED: return RCB_ERR_TRUNCATED_STREAM;
+        default: return RCB_ERR_INVALID_ARGUMENT;
+    }
+}
+
+// ------------------------------------------------------------------ context
+extern "C" int rcb_ctx_create(int device, void* stream, rcb_ctx** out) {
+    if (!out) return RCB_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return RCB_ERR_NO_DEVICE;
+    if (device < 0 || device >= n) return RCB_ERR_INVALID_ARGUMENT;
+    rcb_ctx* c = new (std::nothrow) rcb_ctx();
+    if (!c) return RCB_ERR_INVALID_ARGUMENT;
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        delete c;
+        return RCB_ERR_CUDA;
+    }
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete c;
+            return RCB_ERR_CUDA;
+        }
+        c->own_stream = true;
+    }
+    bool ok = cudaMalloc(&c->d_summary, 8 * sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMallocHost(&c->h_summary, 8 * sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMalloc(&c->d_words, 8 * sizeof(uint32_t)) == cudaSuccess &&
+              cudaMallocHost(&c->h_words, 8 * sizeof(uint32_t)) == cudaSuccess;
+    if (!ok) {
+        rcb_ctx_destroy(c);
+        return RCB_ERR_CUDA;
+    }
+    *out = c;
+    return RCB_OK;
+}
+
+extern "C" int rcb_ctx_destroy(rcb_ctx* c) {
+    if (!c) return RCB_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->staging);
+    cudaFree(c->lens);
+    cudaFree(c->status);
+    cudaFree(c->d_summary);
+    cudaFreeHost(c->h_summary);
+    cudaFree(c->d_words);
+    cudaFreeHost(c->h_words);
+    cudaFree(c->h2d);
+    for (int i = 0; i < 7; i++)
+        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return RCB_OK;
+}
+
+extern "C" int rcb_ctx_set_stream(rcb_ctx* c, void* stream) {
+    if (!c) return RCB_ERR_INVALID_ARGUMENT;
+    if (c->own_stream && c->stream) {
+        cudaStreamSynchronize(c->stream);
+        cudaStreamDestroy(c->stream);
+        c->own_stream = false;
+    }
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        CK(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    return RCB_OK;
+}
+
+extern "C" int rcb_ctx_synchronize(rcb_ctx* c) {
+    if (!c) return RCB_ERR_INVALID_ARGUMENT;
+    CK(c, cudaStreamSynchronize(c->stream));
+    return RCB_OK;
+}
+
+extern "C" int rcb_ctx_set_block_threads(rcb_ctx* c, int enc, int dec) {
+    if (!c) return RCB_ERR_INVALID_ARGUMENT;
+    auto okv = [](int v) { return v == 0 || (v >= 32 && v <= 256 && v % 32 == 0); };
+    if (!okv(enc) || !okv(dec)) return RCB_ERR_INVALID_ARGUMENT;
+    c->enc_threads = enc ? enc : 128;
+    c->dec_threads = dec ? dec : 128;
+    return RCB_OK;
+}
+
+extern "C" uint64_t rcb_ctx_launch_count(const rcb_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int rcb_ctx_enable_timing(rcb_ctx* c, int on) {
+    if (!c) return RCB_ERR_INVALID_ARGUMENT;
+    CK(c, cudaSetDevice(c->device));
+    if (on && !c->ev[0])
+        for (int i = 0; i < 7; i++) CK(c, cudaEventCreate(&c->ev[i]));
+    c->timing = on != 0;
+    c->ev_enc = c->ev_dec = false;
+    return RCB_OK;
+}
+
+extern "C" int rcb_ctx_get_timings(rcb_ctx* c, float* ms, int n) {
+    if (!c || !ms || n < 0) return RCB_ERR_INVALID_ARGUMENT;
+    CK(c, cudaStreamSynchronize(c->stream));
+    float v[5] = {0, 0, 0, 0, 0};
+    if (c->ev_enc) {
+        CK(c, cudaEventElapsedTime(&v[0], c->ev[0], c->ev[1]));
+        CK(c, cudaEventElapsedTime(&v[1], c->ev[1], c->ev[2]));
+        CK(c, cudaEventElapsedTime(&v[2], c->ev[2], c->ev[3]));
+    }
+    if (c->ev_dec) {
+        CK(c, cudaEventElapsedTime(&v[3], c->ev[4], c->ev[5]));
+        CK(c, cudaEventElapsedTime(&v[4], c->ev[5], c->ev[6]));
+    }
+    for (int i = 0; i < n && i < 5; i++) ms[i] = v[i];
+    return RCB_OK;
+}
+
+static int ensure_chunks(rcb_ctx* c, uint64_t n_chunks) {
+    if (n_chunks <= c->chunk_cap) return RCB_OK;
+    CK(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->lens);
+    cudaFree(c->status);
+    c->lens = nullptr;
+    c->status = nullptr;
+    c->chunk_cap = 0;
+    CK(c, cudaMalloc(&c->lens, n_chunks * sizeof(uint32_t)));
+    CK(c, cudaMalloc(&c->status, n_chunks * sizeof(uint32_t)));
+    c->chunk_cap = n_chunks;
+    return RCB_OK;
+}
+
+static int ensure_staging(rcb_ctx* c, size_t bytes) {
+    if (bytes <= c->staging_bytes) return RCB_OK;
+    CK(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->staging);
+    c->staging = nullptr;
+    c->staging_bytes = 0;
+    CK(c, cudaMalloc(&c->staging, bytes));
+    c->staging_bytes = bytes;
+    return RCB_OK;
+}
+
+static int ensure_h2d(rcb_ctx* c, size_t bytes) {
+    if (bytes <= c->h2d_bytes) return RCB_OK;
+    CK(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->h2d);
+    c->h2d = nullptr;
+    c->h2d_bytes = 0;
+    CK(c, cudaMalloc(&c->h2d, bytes));
+    c->h2d_bytes = bytes;
+    return RCB_OK;
+}
+
+// -------------------------------------------------------------------- model
+extern "C" int rcb_model_create(rcb_ctx* c, uint32_t K, uint64_t n_models, rcb_model** out) {
+    if (!c || !out || K == 0 || K > MAX_K || n_models == 0) return RCB_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (n_models == 1 && K > MAX_K_SHARED) return RCB_ERR_UNSUPPORTED;
+    CK(c, cudaSetDevice(c->device));
+    rcb_model* m = new (std::nothrow) rcb_model();
+    if (!m) return RCB_ERR_INVALID_ARGUMENT;
+    m->ctx = c;
+    m->K = K;
+    m->n_models = n_models;
+    bool ok = cudaMalloc(&m->d_tab, n_models * K * sizeof(uint2)) == cudaSuccess &&
+              cudaMalloc(&m->d_total, n_models * sizeof(uint32_t)) == cudaSuccess &&
+              cudaMalloc(&m->d_hdr, n_models * sizeof(ModelHdr)) == cudaSuccess;
+    if (ok && n_models == 1) ok = cudaMalloc(&m->d_lut, LUT_CAP * sizeof(LutEntry)) == cudaSuccess;
+    if (!ok) {
+        c->last_err = cudaGetLastError();
+        rcb_model_destroy(m);
+        return RCB_ERR_CUDA;
+    }
+    *out = m;
+    return RCB_OK;
+}
+
+extern "C" int rcb_model_destroy(rcb_model* m) {
+    if (!m) return RCB_OK;
+    if (m->ctx) {
+        cudaSetDevice(m->ctx->device);
+        cudaStreamSynchronize(m->ctx->stream);
+    }
+    cudaFree(m->d_tab);
+    cudaFree(m->d_total);
+    cudaFree(m->d_hdr);
+    cudaFree(m->d_lut);
+    delete m;
+    return RCB_OK;
+}
+
+template <typename SYM>
+static int launch_hist(rcb_ctx* c, const void* d_syms, uint64_t n, uint32_t K, uint64_t chunk_syms,
+                       void* d_counts) {
+    const int threads = K <= 4096 ? 256 : 64;  // private copy of the K bins per warp
+    const size_t smem = (size_t)(threads / 32) * K * sizeof(uint32_t);
+    if (chunk_syms == 0) {
+        CK(c, cudaMemsetAsync(d_counts, 0, (size_t)K * sizeof(unsigned long long), c->stream));
+        auto kern = hist_global_kernel<SYM>;
+        CK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        uint64_t nvec = n / (16 / sizeof(SYM));
+        uint64_t want = (nvec + threads * 8 - 1) / (threads * 8);
+        uint64_t maxb = (uint64_t)c->sm_count * 8;
+        int blocks = (int)(want < 1 ? 1 : (want > maxb ? maxb : want));
+        kern<<<blocks, threads, smem, c->stream>>>((const SYM*)d_syms, n, K,
+                                                    (unsigned long long*)d_counts, c->d_words + 2);
+        CK_LAUNCH(c);
+    } else {
+        uint64_t n_chunks = (n + chunk_syms - 1) / chunk_syms;
+        if (n_chunks == 0) return RCB_OK;
+        if (n_chunks > 0x7FFFFFFFull) return RCB_ERR_UNSUPPORTED;
+        auto kern = hist_chunks_kernel<SYM>;
+        CK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)n_chunks, threads, smem, c->stream>>>((const SYM*)d_syms, n, chunk_syms, K,
+                                                                (uint32_t*)d_counts, c->d_words + 2);
+        CK_LAUNCH(c);
+    }
+    return RCB_OK;
+}
+
+extern "C" int rcb_histogram(rcb_ctx* c, const void* d_syms, uint64_t n_syms, int sym_bytes, uint32_t K,
+                             uint64_t chunk_syms, void* d_counts) {
+    if (!c || !d_counts || (n_syms && !d_syms) || K == 0 || K > MAX_K) return RCB_ERR_INVALID_ARGUMENT;
+    if (sym_bytes != 1 && sym_bytes != 2) return RCB_ERR_UNSUPPORTED;
+    if (K > 16384) return RCB_ERR_UNSUPPORTED;  // per-warp private bins must fit shared memory
+    if (reinterpret_cast<uintptr_t>(d_syms) & 15u) return RCB_ERR_INVALID_ARGUMENT;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaMemsetAsync(c->d_words + 2, 0, sizeof(uint32_t), c->stream));
+    int r = sym_bytes == 1 ? launch_hist<uint8_t>(c, d_syms, n_syms, K, chunk_syms, d_counts)
+                           : launch_hist<uint16_t>(c, d_syms, n_syms, K, chunk_syms, d_counts);
+    if (r) return r;
+    CK(c, cudaMemcpyAsync(c->h_words + 2, c->d_words + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                          c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return c->h_words[2] ? RCB_ERR_SYMBOL_OUT_OF_RANGE : RCB_OK;
+}
+
+static int finalize_model(rcb_ctx* c, rcb_model* m) {
+    // words: [0] min c (atomicMin), [1] bad bits, [2] histogram flag (untouched), [3] max total
+    c->h_words[4] = 0xFFFFFFFFu;
+    c->h_words[5] = 0u;
+    c->h_words[7] = 0u;
+    CK(c, cudaMemcpyAsync(c->d_words, c->h_words + 4, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(c->d_words + 3, c->h_words + 7, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    if (m->n_models > 0x7FFFFFFFull) return RCB_ERR_UNSUPPORTED;
+    finalize_models_kernel<<<(unsigned)m->n_models, 256, 0, c->stream>>>(
+        m->d_tab, m->d_total, m->K, m->d_hdr, m->n_models == 1 ? m->d_lut : nullptr, LUT_CAP, c->d_words);
+    CK_LAUNCH(c);
+    CK(c, cudaMemcpyAsync(c->h_words, c->d_words, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(&m->h_hdr0, m->d_hdr, sizeof(ModelHdr), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    m->min_c = c->h_words[0];
+    uint32_t bad = c->h_words[1];
+    m->ready = false;
+    if (bad & 2u) return RCB_ERR_ZERO_TOTAL;
+    if (bad & 1u) return RCB_ERR_INVALID_MODEL;
+    // per-model flags are in the headers; aggregate what the launch dispatch needs
+    m->bad_bits = bad & (4u | 8u);
+    m->max_total = c->h_words[3];
+    m->ready = true;
+    return RCB_OK;
+}
+
+extern "C" int rcb_model_from_counts(rcb_ctx* c, rcb_model* m, const void* d_counts, int count_bytes) {
+    if (!c || !m || !d_counts || m->ctx != c) return RCB_ERR_INVALID_ARGUMENT;
+    if (count_bytes != 4 && count_bytes != 8) return RCB_ERR_INVALID_ARGUMENT;
+    if (m->n_models > 0x7FFFFFFFull) return RCB_ERR_UNSUPPORTED;
+    CK(c, cudaSetDevice(c->device));
+    if (count_bytes == 8)
+        counts_to_tables_kernel<unsigned long long><<<(unsigned)m->n_models, 256, 0, c->stream>>>(
+            (const unsigned long long*)d_counts, m->K, m->d_tab, m->d_total);
+    else
+        counts_to_tables_kernel<uint32_t><<<(unsigned)m->n_models, 256, 0, c->stream>>>(
+            (const uint32_t*)d_counts, m->K, m->d_tab, m->d_total);
+    CK_LAUNCH(c);
+    return finalize_model(c, m);
+}
+
+extern "C" int rcb_model_from_tables(rcb_ctx* c, rcb_model* m, const uint32_t* h_c, const uint32_t* h_cum,
+                                     const uint32_t* h_total) {
+    if (!c || !m || !h_c || !h_cum || !h_total || m->ctx != c) return RCB_ERR_INVALID_ARGUMENT;
+    CK(c, cudaSetDevice(c->device));
+    const size_t n = (size_t)m->n_models * m->K;
+    uint2* tmp = (uint2*)malloc(n * sizeof(uint2));
+    if (!tmp) return RCB_ERR_INVALID_ARGUMENT;
+    for (size_t i = 0; i < n; i++) tmp[i] = make_uint2(h_cum[i], h_c[i]);
+    cudaError_t e = cudaMemcpyAsync(m->d_tab, tmp, n * sizeof(uint2), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(m->d_total, h_total, m->n_models * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                            c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    free(tmp);
+    if (e != cudaSuccess) {
+        c->last_err = e;
+        return RCB_ERR_CUDA;
+    }
+    return finalize_model(c, m);
+}
+
+extern "C" int rcb_model_get_tables(rcb_ctx* c, const rcb_model* m, uint64_t index, uint32_t* h_c,
+                                    uint32_t* h_cum, uint32_t* h_total, uint32_t* h_flags) {
+    if (!c || !m || index >= m->n_models) return RCB_ERR_INVALID_ARGUMENT;
+    CK(c, cudaSetDevice(c->device));
+    uint2* tmp = (uint2*)malloc((size_t)m->K * sizeof(uint2));
+    if (!tmp) return RCB_ERR_INVALID_ARGUMENT;
+    ModelHdr h;
+    cudaError_t e = cudaMemcpyAsync(tmp, m->d_tab + index * m->K, (size_t)m->K * sizeof(uint2),
+                                    cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(&h, m->d_hdr + index, sizeof(ModelHdr), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+        free(tmp);
+        c->last_err = e;
+        return RCB_ERR_CUDA;
+    }
+    for (uint32_t i = 0; i < m->K; i++) {
+        if (h_cum) h_cum[i] = tmp[i].x;
+        if (h_c) h_c[i] = tmp[i].y;
+    }
+    free(tmp);
+    if (h_total) *h_total = h.div.total;
+    if (h_flags) *h_flags = h.flags;
+    return RCB_OK;
+}
+
+// ------------------------------------------------------------------- encode
+static uint64_t staging_pitch(const rcb_model* m, uint64_t chunk_syms) {
+    // bits per symbol <= log2(total / min c) (+ ~2^-15 from the truncating division);
+    // loop-2 range truncation adds < 0.1 %: 1/128 margin + 64 bytes, and the sync entry
+    // point retries with the exact need if a row still overflows.
+    double total = (double)m->max_total, minc = (double)(m->min_c ? m->min_c : 1);
+    double bits = log2(total / minc);
+    if (bits < 0.0) bits = 0.0;
+    double bytes = (double)chunk_syms * bits / 8.0;
+    uint64_t p = (uint64_t)(bytes * (1.0 + 1.0 / 128.0)) + 64 + 8;
+    return (p + 15) & ~15ull;
+}
+
+extern "C" uint64_t rcb_encode_bound(rcb_ctx* c, const rcb_model* m, uint64_t n_syms, int sym_bytes,
+                                     uint64_t chunk_syms) {
+    (void)sym_bytes;
+    if (!c || !m || !m->ready || chunk_syms == 0) return 0;
+    uint64_t n_chunks = (n_syms + chunk_syms - 1) / chunk_syms;
+    return n_chunks * staging_pitch(m, chunk_syms) + 16;
+}
+
+template <typename SYM>
+static void launch_encode_variant(rcb_ctx* c, const rcb_model* m, const EncodeArgs& a, int threads,
+                                  unsigned blocks) {
+    const bool shared = m->n_models == 1;
+    const bool pow2 = shared && (m->h_hdr0.flags & MODEL_POW2);
+    const bool checked = (m->bad_bits & 4u) != 0;
+    const bool rangechk = (uint64_t)m->K < (1ull << (8 * sizeof(SYM)));
+    const size_t smem = shared ? (size_t)m->K * sizeof(uint2) : 0;
+#define RCB_ENC(SH, P2, CH, RC)                                                                        \
+    do {                                                                                               \
+        auto kern = encode_kernel<SYM, SH, P2, CH, RC>;                                                \
+        if (smem > 48 * 1024)                                                                          \
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+        kern<<<blocks, threads, smem, c->stream>>>(a);                                                 \
+    } while (0)
+#define RCB_ENC_RC(SH, P2, CH)               \
+    do {                                     \
+        if (rangechk) RCB_ENC(SH, P2, CH, true); \
+        else RCB_ENC(SH, P2, CH, false);     \
+    } while (0)
+#define RCB_ENC_CH(SH, P2)                   \
+    do {                                     \
+        if (checked) RCB_ENC_RC(SH, P2, true); \
+        else RCB_ENC_RC(SH, P2, false);      \
+    } while (0)
+    if (shared) {
+        if (pow2) RCB_ENC_CH(true, true);
+        else RCB_ENC_CH(true, false);
+    } else {
+        RCB_ENC_CH(false, false);
+    }
+#undef RCB_ENC_CH
+#undef RCB_ENC_RC
+#undef RCB_ENC
+}
+
+static int encode_launch(rcb_ctx* c, const void* d_syms, uint64_t n_syms, int sym_bytes, uint64_t chunk_syms,
+                         const rcb_model* m, uint8_t* d_out, uint64_t out_cap, uint64_t* d_offsets,
+                         uint32_t* d_status, uint64_t pitch_override) {
+    if (!c || !m || !m->ready || m->ctx != c || !d_offsets || chunk_syms == 0) return RCB_ERR_INVALID_ARGUMENT;
+    if (n_syms && !d_syms) return RCB_ERR_INVALID_ARGUMENT;
+    if (sym_bytes != 1 && sym_bytes != 2) return RCB_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(d_syms) & 15u) || (reinterpret_cast<uintptr_t>(d_out) & 15u) ||
+        (reinterpret_cast<uintptr_t>(d_offsets) & 7u))
+        return RCB_ERR_INVALID_ARGUMENT;
+    if (chunk_syms > 0x40000000ull) return RCB_ERR_UNSUPPORTED;  // code length is tracked in 32 bits
+    const uint64_t n_chunks = (n_syms + chunk_syms - 1) / chunk_syms;
+    if (m->n_models != 1 && m->n_models != n_chunks) return RCB_ERR_INVALID_ARGUMENT;
+    if (n_chunks > 0x7FFFFFFFull) return RCB_ERR_UNSUPPORTED;
+    CK(c, cudaSetDevice(c->device));
+    if (n_chunks == 0) {
+        CK(c, cudaMemsetAsync(d_offsets, 0, sizeof(uint64_t), c->stream));
+        CK(c, cudaMemsetAsync(c->d_summary, 0, 4 * sizeof(unsigned long long), c->stream));
+        c->pending_out_cap = out_cap;
+        c->pending_offsets = d_offsets;
+        c->pending_n_chunks = 0;
+        return RCB_OK;
+    }
+    int r = ensure_chunks(c, n_chunks);
+    if (r) return r;
+    uint64_t pitch = pitch_override ? pitch_override : staging_pitch(m, chunk_syms);
+    if (pitch > 0xFFFFFFF0ull) return RCB_ERR_UNSUPPORTED;
+    r = ensure_staging(c, (size_t)(n_chunks * pitch + 64));
+    if (r) return r;
+    c->pending_pitch = pitch;
+    c->pending_out_cap = out_cap;
+    c->pending_offsets = d_offsets;
+    c->pending_n_chunks = n_chunks;
+
+    EncodeArgs a;
+    a.syms = d_syms;
+    a.n_syms = n_syms;
+    a.chunk_syms = chunk_syms;
+    a.n_chunks = n_chunks;
+    a.tabs = m->d_tab;
+    a.hdrs = m->d_hdr;
+    a.K = m->K;
+    a.per_chunk = m->n_models != 1;
+    a.staging = c->staging;
+    a.pitch = pitch;
+    a.lens = c->lens;
+    a.status = d_status ? d_status : c->status;
+    const int threads = c->enc_threads;
+    const unsigned blocks = (unsigned)((n_chunks + threads - 1) / threads);
+    EV(c, 0);
+    if (sym_bytes == 1)
+        launch_encode_variant<uint8_t>(c, m, a, threads, blocks);
+    else
+        launch_encode_variant<uint16_t>(c, m, a, threads, blocks);
+    CK_LAUNCH(c);
+    EV(c, 1);
+    scan_lengths_kernel<<<1, 1024, 0, c->stream>>>(c->lens, a.status, n_chunks, d_offsets, c->d_summary);
+    CK_LAUNCH(c);
+    EV(c, 2);
+    gather_kernel<<<(unsigned)n_chunks, 256, 0, c->stream>>>(c->staging, pitch, c->lens, d_offsets, d_out,
+                                                            out_cap);
+    CK_LAUNCH(c);
+    EV(c, 3);
+    c->ev_enc = c->timing;
+    return RCB_OK;
+}
+
+extern "C" int rcb_encode_chunks_async(rcb_ctx* c, const void* d_syms, uint64_t n_syms, int sym_bytes,
+                                       uint64_t chunk_syms, const rcb_model* m, uint8_t* d_out,
+                                       uint64_t out_cap, uint64_t* d_offsets, uint32_t* d_status) {
+    return encode_launch(c, d_syms, n_syms, sym_bytes, chunk_syms, m, d_out, out_cap, d_offsets, d_status, 0);
+}
+
+// Fetch the summary of the last encode on this ctx.  Sets *need_pitch when a staging row overflowed.
+static int encode_result(rcb_ctx* c, uint64_t* total_bytes, uint64_t* need_pitch) {
+    const uint64_t* d_offsets = c->pending_offsets;
+    const uint64_t n_chunks = c->pending_n_chunks;
+    unsigned long long total = 0;
+    CK(c, cudaMemcpyAsync(c->h_summary, c->d_summary, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                          c->stream));
+    if (d_offsets)
+        CK(c, cudaMemcpyAsync(c->h_summary + 4, d_offsets + n_chunks, sizeof(unsigned long long),
+                              cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (d_offsets) total = c->h_summary[4];
+    if (total_bytes) *total_bytes = total;
+    if (need_pitch) *need_pitch = 0;
+    if (c->h_summary[0]) {
+        uint32_t st = (uint32_t)c->h_summary[2];
+        if (st == ST_OUT_CAPACITY && need_pitch) *need_pitch = ((c->h_summary[3] + 15) & ~15ull) + 16;
+        return status_to_error(st);
+    }
+    if (d_offsets && total > c->pending_out_cap) return RCB_ERR_OUT_CAPACITY;
+    return RCB_OK;
+}
+
+extern "C" int rcb_encode_chunks(rcb_ctx* c, const void* d_syms, uint64_t n_syms, int sym_bytes,
+                                 uint64_t chunk_syms, const rcb_model* m, uint8_t* d_out, uint64_t out_cap,
+                                 uint64_t* d_offsets, uint32_t* d_status, uint64_t* h_out_bytes) {
+    int r = encode_launch(c, d_syms, n_syms, sym_bytes, chunk_syms, m, d_out, out_cap, d_offsets, d_status, 0);
+    if (r) return r;
+    uint64_t need = 0;
+    r = encode_result(c, h_out_bytes, &need);
+    if (r == RCB_ERR_OUT_CAPACITY && need) {
+        // a staging row was too small for this data: rerun once with the exact need
+        r = encode_launch(c, d_syms, n_syms, sym_bytes, chunk_syms, m, d_out, out_cap, d_offsets, d_status, need);
+        if (r) return r;
+        r = encode_result(c, h_out_bytes, nullptr);
+    }
+    return r;
+}
+
+extern "C" int rcb_encode_result(rcb_ctx* c, uint64_t* h_out_bytes) {
+    if (!c || !c->pending_offsets) return RCB_ERR_INVALID_ARGUMENT;
+    return encode_result(c, h_out_bytes, nullptr);
+}
+
+// ------------------------------------------------------------------- decode
+template <typename SYM>
+static void launch_decode_variant(rcb_ctx* c, const rcb_model* m, const DecodeArgs& a, int threads,
+                                  unsigned blocks) {
+    const bool shared = m->n_models == 1;
+    const bool pow2 = shared && (m->h_hdr0.flags & MODEL_POW2);
+    const bool checked = (m->bad_bits & 4u) != 0;
+    size_t smem = 0;
+    if (shared) {
+        uint32_t nb = (m->h_hdr0.flags & MODEL_REGULAR) ? m->h_hdr0.nb : 0u;
+        smem = (size_t)nb * sizeof(LutEntry) + (size_t)m->K * sizeof(uint2);
+    }
+#define RCB_DEC(SH, P2, CH)                                                                            \
+    do {                                                                                               \
+        auto kern = decode_kernel<SYM, SH, P2, CH>;                                                    \
+        if (smem > 48 * 1024)                                                                          \
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+        kern<<<blocks, threads, smem, c->stream>>>(a);                                                 \
+    } while (0)
+#define RCB_DEC_CH(SH, P2)                 \
+    do {                                   \
+        if (checked) RCB_DEC(SH, P2, true); \
+        else RCB_DEC(SH, P2, false);       \
+    } while (0)
+    if (shared) {
+        if (pow2) RCB_DEC_CH(true, true);
+        else RCB_DEC_CH(true, false);
+    } else {
+        RCB_DEC_CH(false, false);
+    }
+#undef RCB_DEC_CH
+#undef RCB_DEC
+}
+
+extern "C" int rcb_decode_chunks_async(rcb_ctx* c, const uint8_t* d_stream, const uint64_t* d_offsets,
+                                       uint64_t n_syms, int sym_bytes, uint64_t chunk_syms,
+                                       const rcb_model* m, void* d_syms_out, uint32_t* d_status) {
+    if (!c || !m || !m->ready || m->ctx != c || !d_offsets || chunk_syms == 0) return RCB_ERR_INVALID_ARGUMENT;
+    if (n_syms && (!d_stream || !d_syms_out)) return RCB_ERR_INVALID_ARGUMENT;
+    if (sym_bytes != 1 && sym_bytes != 2) return RCB_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(d_stream) & 15u) || (reinterpret_cast<uintptr_t>(d_syms_out) & 15u) ||
+        (reinterpret_cast<uintptr_t>(d_offsets) & 7u))
+        return RCB_ERR_INVALID_ARGUMENT;
+    const uint64_t n_chunks = (n_syms + chunk_syms - 1) / chunk_syms;
+    if (m->n_models != 1 && m->n_models != n_chunks) return RCB_ERR_INVALID_ARGUMENT;
+    if (n_chunks > 0x7FFFFFFFull) return RCB_ERR_UNSUPPORTED;
+    CK(c, cudaSetDevice(c->device));
+    if (n_chunks == 0) {
+        CK(c, cudaMemsetAsync(c->d_summary + 4, 0, 4 * sizeof(unsigned long long), c->stream));
+        return RCB_OK;
+    }
+    int r = ensure_chunks(c, n_chunks);
+    if (r) return r;
+    DecodeArgs a;
+    a.stream = d_stream;
+    a.offsets = d_offsets;
+    a.n_syms = n_syms;
+    a.chunk_syms = chunk_syms;
+    a.n_chunks = n_chunks;
+    a.tabs = m->d_tab;
+    a.hdrs = m->d_hdr;
+    a.lut = m->d_lut;
+    a.K = m->K;
+    a.per_chunk = m->n_models != 1;
+    a.out = d_syms_out;
+    a.status = d_status ? d_status : c->status;
+    const int threads = c->dec_threads;
+    const unsigned blocks = (unsigned)((n_chunks + threads - 1) / threads);
+    EV(c, 4);
+    if (sym_bytes == 1)
+        launch_decode_variant<uint8_t>(c, m, a, threads, blocks);
+    else
+        launch_decode_variant<uint16_t>(c, m, a, threads, blocks);
+    CK_LAUNCH(c);
+    EV(c, 5);
+    status_summary_kernel<<<1, 1024, 0, c->stream>>>(a.status, n_chunks, c->d_summary + 4);
+    CK_LAUNCH(c);
+    EV(c, 6);
+    c->ev_dec = c->timing;
+    return RCB_OK;
+}
+
+extern "C" int rcb_decode_result(rcb_ctx* c) {
+    if (!c) return RCB_ERR_INVALID_ARGUMENT;
+    CK(c, cudaMemcpyAsync(c->h_summary + 4, c->d_summary + 4, 4 * sizeof(unsigned long long),
+                          cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (c->h_summary[4]) return status_to_error((uint32_t)c->h_summary[6]);
+    return RCB_OK;
+}
+
+extern "C" int rcb_decode_chunks(rcb_ctx* c, const uint8_t* d_stream, const uint64_t* d_offsets,
+                                 uint64_t n_syms, int sym_bytes, uint64_t chunk_syms, const rcb_model* m,
+                                 void* d_syms_out, uint32_t* d_status) {
+    int r = rcb_decode_chunks_async(c, d_stream, d_offsets, n_syms, sym_bytes, chunk_syms, m, d_syms_out,
+                                    d_status);
+    if (r) return r;
+    return rcb_decode_result(c);
+}
+
+// ------------------------------------------------------- host-buffer wrappers
+extern "C" int rcb_encode_host(rcb_ctx* c, const void* h_syms, uint64_t n_syms, int sym_bytes,
+                               uint64_t chunk_syms, const rcb_model* m, uint8_t* h_out, uint64_t out_cap,
+                               uint64_t* h_offsets, uint64_t* h_out_bytes) {
+    if (!c || !m || !m->ready || chunk_syms == 0 || !h_offsets || !h_out_bytes) return RCB_ERR_INVALID_ARGUMENT;
+    if (sym_bytes != 1 && sym_bytes != 2) return RCB_ERR_UNSUPPORTED;
+    if (n_syms && !h_syms) return RCB_ERR_INVALID_ARGUMENT;
+    const uint64_t n_chunks = (n_syms + chunk_syms - 1) / chunk_syms;
+    const uint64_t in_bytes = (n_syms * sym_bytes + 15) & ~15ull;
+    const uint64_t bound = rcb_encode_bound(c, m, n_syms, sym_bytes, chunk_syms) + 16;
+    const uint64_t off_bytes = ((n_chunks + 1) * sizeof(uint64_t) + 15) & ~15ull;
+    CK(c, cudaSetDevice(c->device));
+    int r = ensure_h2d(c, in_bytes + bound + off_bytes + 64);
+    if (r) return r;
+    uint8_t* d_in = (uint8_t*)c->h2d;
+    uint8_t* d_out = d_in + in_bytes;
+    uint64_t* d_off = (uint64_t*)(d_out + ((bound + 15) & ~15ull));
+    if (n_syms)
+        CK(c, cudaMemcpyAsync(d_in, h_syms, n_syms * sym_bytes, cudaMemcpyHostToDevice, c->stream));
+    uint64_t total = 0;
+    r = rcb_encode_chunks(c, d_in, n_syms, sym_bytes, chunk_syms, m, d_out, bound, d_off, nullptr, &total);
+    *h_out_bytes = total;
+    if (r) return r;
+    if (total > out_cap) return RCB_ERR_OUT_CAPACITY;
+    CK(c, cudaMemcpyAsync(h_offsets, d_off, (n_chunks + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                          c->stream));
+    if (total) CK(c, cudaMemcpyAsync(h_out, d_out, total, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return RCB_OK;
+}
+
+extern "C" int rcb_decode_host(rcb_ctx* c, const uint8_t* h_stream, const uint64_t* h_offsets,
+                               uint64_t n_syms, int sym_bytes, uint64_t chunk_syms, const rcb_model* m,
+                               void* h_syms_out) {
+    if (!c || !m || !m->ready || chunk_syms == 0 || !h_offsets) return RCB_ERR_INVALID_ARGUMENT;
+    if (sym_bytes != 1 && sym_bytes != 2) return RCB_ERR_UNSUPPORTED;
+    if (n_syms && (!h_stream || !h_syms_out)) return RCB_ERR_INVALID_ARGUMENT;
+    const uint64_t n_chunks = (n_syms + chunk_syms - 1) / chunk_syms;
+    const uint64_t total = h_offsets[n_chunks];
+    const uint64_t st_bytes = (total + 31) & ~15ull;
+    const uint64_t off_bytes = ((n_chunks + 1) * sizeof(uint64_t) + 15) & ~15ull;
+    const uint64_t out_bytes = (n_syms * sym_bytes + 15) & ~15ull;
+    CK(c, cudaSetDevice(c->device));
+    int r = ensure_h2d(c, st_bytes + off_bytes + out_bytes + 64);
+    if (r) return r;
+    uint8_t* d_st = (uint8_t*)c->h2d;
+    uint64_t* d_off = (uint64_t*)(d_st + st_bytes);
+    uint8_t* d_out = (uint8_t*)d_off + off_bytes;
+    if (total) CK(c, cudaMemcpyAsync(d_st, h_stream, total, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(d_off, h_offsets, (n_chunks + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice,
+                          c->stream));
+    r = rcb_decode_chunks(c, d_st, d_off, n_syms, sym_bytes, chunk_syms, m, d_out, nullptr);
+    if (r) return r;
+    if (n_syms)
+        CK(c, cudaMemcpyAsync(h_syms_out, d_out, n_syms * sym_bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return RCB_OK;
+}
+
+// ----------------------------------------------------------- synthetic data
+extern "C" int rcb_generate(rcb_ctx* c, void* d_out, uint64_t first, uint64_t n, int sym_bytes, uint32_t K,
+                            uint64_t seed, const uint32_t* h_thr, uint32_t n_tables, uint64_t chunk_syms) {
+    if (!c || !d_out || !h_thr || K < 1 || K > MAX_K || n_tables == 0) return RCB_ERR_INVALID_ARGUMENT;
+    if (sym_bytes != 1 && sym_bytes != 2) return RCB_ERR_UNSUPPORTED;
+    if (sym_bytes == 1 && K > 256) return RCB_ERR_INVALID_ARGUMENT;
+    if (n_tables > 1 && chunk_syms == 0) return RCB_ERR_INVALID_ARGUMENT;
+    const size_t thr_bytes = (size_t)n_tables * (K - 1) * sizeof(uint32_t);
+    if (thr_bytes > 200 * 1024) return RCB_ERR_UNSUPPORTED;
+    if (n == 0) return RCB_OK;
+    CK(c, cudaSetDevice(c->device));
+    uint32_t* d_thr = nullptr;
+    CK(c, cudaMalloc(&d_thr, thr_bytes ? thr_bytes : 4));
+    cudaError_t e = cudaMemcpyAsync(d_thr, h_thr, thr_bytes, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        const int threads = 256;
+        uint64_t groups = (n + (16 / sym_bytes) - 1) / (16 / sym_bytes);
+        uint64_t want = (groups + threads - 1) / threads;
+        uint64_t maxb = (uint64_t)c->sm_count * 16;
+        unsigned blocks = (unsigned)(want > maxb ? maxb : want);
+        if (sym_bytes == 1) {
+            auto kern = generate_kernel<uint8_t>;
+            if (thr_bytes > 48 * 1024)
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thr_bytes);
+            kern<<<blocks, threads, thr_bytes, c->stream>>>((uint8_t*)d_out, first, n, K, seed, d_thr, n_tables,
+                                                             chunk_syms ? chunk_syms : 1);
+        } else {
+            auto kern = generate_kernel<uint16_t>;
+            if (thr_bytes > 48 * 1024)
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thr_bytes);
+            kern<<<blocks, threads, thr_bytes, c->stream>>>((uint16_t*)d_out, first, n, K, seed, d_thr, n_tables,
+                                                              chunk_syms ? chunk_syms : 1);
+        }
+        c->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_thr);
+    if (e != cudaSuccess) {
+        c->last_err = e;
+        return RCB_ERR_CUDA;
+    }
+    return RCB_OK;
+}

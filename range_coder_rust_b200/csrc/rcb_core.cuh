@@ -1,0 +1,389 @@
+// rcb_core.cuh -- per-symbol range-coder arithmetic shared by every kernel.
+//
+// Semantics restated from the reference crate (paths under /root/reference):
+//   src/range_coder.rs:53-92   param_update  (range, lower, loop 1, loop 2)
+//   src/range_coder.rs:95-100  left_shift
+//   src/range_coder.rs:110-116 no_carry_expansion      ("loop 1")
+//   src/range_coder.rs:126-135 range_reduction_expansion ("loop 2")
+//   src/encoder.rs:40-46       finish (8 bytes of lower_bound, MSB first)
+//   src/decoder.rs:31-54       shift_left_buffer / decode
+//   examples/sample_impl.rs:27-45 find_index (rfreq + binary search)
+//
+// Design (not a port): the byte loops are replaced by a closed form on the hot
+// path (n1 = clz(lower ^ upper) / 8 whole bytes at once) with the literal loops
+// kept as a rare slow path, range/total is a shift or a multiply-high
+// reciprocal, and the decoder never divides: it classifies `data - lower` in
+// the product domain (cum * rpt <= d  <=>  cum <= d / rpt for integers).
+//
+// Everything here is __host__ __device__ so the same code can be compiled by
+// g++ into a test-only harness (tests/hostcore) and compared with the oracle
+// without a GPU.  The product never runs the host instantiation.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define RCB_HD __host__ __device__ __forceinline__
+#define RCB_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define RCB_HD inline
+#define RCB_HD_NOINLINE
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define RCB_LIKELY(x) (__builtin_expect(!!(x), 1))
+#define RCB_UNLIKELY(x) (__builtin_expect(!!(x), 0))
+#else
+#define RCB_LIKELY(x) (__builtin_expect(!!(x), 1))
+#define RCB_UNLIKELY(x) (__builtin_expect(!!(x), 0))
+#endif
+
+namespace rcb {
+
+constexpr uint64_t TOP8 = 1ull << 56;   // src/range_coder.rs:23
+constexpr uint64_t TOP16 = 1ull << 48;  // src/range_coder.rs:24
+
+// per-chunk status word (0 = ok); values mirror include/rcb200.h
+enum : uint32_t {
+    ST_OK = 0,
+    ST_ZERO_FREQ = 1,        // range became 0: the reference never returns (range_coder.rs:83-85)
+    ST_LOWER_OVERFLOW = 2,   // range_coder.rs:68-81
+    ST_UPPER_OVERFLOW = 3,   // range_coder.rs:111,138-146
+    ST_SYMBOL_RANGE = 4,     // symbol >= K (sample_impl.rs:19 would panic)
+    ST_OUT_CAPACITY = 5,     // staging row too small; the reported length is the needed size
+    ST_TRUNCATED = 6         // decoder.rs:33 pop_front on an empty buffer
+};
+
+RCB_HD uint64_t umul64hi(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umul64hi(a, b);
+#else
+    return (uint64_t)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+
+RCB_HD uint32_t clz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__clz((int)x);
+#else
+    return x ? (uint32_t)__builtin_clz(x) : 32u;
+#endif
+}
+
+// top `sh` bits (sh in 0..31) of x moved to the bottom; 0 when sh == 0
+RCB_HD uint32_t top_bits(uint32_t x, uint32_t sh) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(x, 0u, sh);
+#else
+    return sh ? (x >> (32u - sh)) : 0u;
+#endif
+}
+
+RCB_HD uint32_t bswap32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(x, 0u, 0x0123);
+#else
+    return __builtin_bswap32(x);
+#endif
+}
+
+// ---------------------------------------------------------------------------
+// range / total_freq  (src/range_coder.rs:38-40), bit-exact without a divide.
+//   power-of-two total : shift.
+//   otherwise          : q = mulhi(range, floor(2^64/total)) is floor(range/total)
+//                        or one less; one compare fixes it (error < 1 because
+//                        range < 2^64 and 2^64 - magic*total < total).
+// ---------------------------------------------------------------------------
+struct DivParams {
+    uint64_t magic;   // floor(2^64 / total), only used when !pow2
+    uint32_t total;
+    uint32_t shift;   // log2(total) when total is a power of two
+};
+
+template <bool POW2>
+RCB_HD uint64_t range_par_total(uint64_t range, const DivParams& p) {
+    if (POW2) return range >> p.shift;
+    uint64_t q = umul64hi(range, p.magic);
+    uint64_t rem = range - q * (uint64_t)p.total;
+    return q + (rem >= (uint64_t)p.total ? 1u : 0u);
+}
+
+// host-side helper: fill DivParams for a total (total >= 1)
+inline bool make_div_params(uint32_t total, DivParams* p, bool* pow2) {
+    if (total == 0) return false;
+    p->total = total;
+    *pow2 = (total & (total - 1)) == 0;
+    p->shift = 0;
+    p->magic = 0;
+    if (*pow2) {
+        uint32_t s = 0;
+        while ((1u << s) != total) s++;
+        p->shift = s;
+    } else {
+        p->magic = (uint64_t)((((unsigned __int128)1) << 64) / total);
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------
+// Renormalisation after range/lower have been updated for a symbol.
+// Sink::put(lower_hi32, sh) receives the top sh/8 bytes (sh in {0,8,16,24}) of
+// lower_bound; Sink::put_byte(b) one byte (slow path).  Order of bytes equals
+// the reference's emission order (src/encoder.rs:35).
+//
+// Fast path: loop 1 emits n1 = clz(lower ^ (lower+range)) / 8 bytes (equal top
+// bytes imply range < 2^56 after each shift, so the shifted sum never wraps),
+// and loop 2 does not fire when range << 8*n1 >= 2^48.  Anything else (n1 >= 4,
+// loop 2, range == 0, overflow) takes the literal loops below.
+// ---------------------------------------------------------------------------
+template <bool CHECKED, class Sink>
+RCB_HD void renorm_slow(uint64_t& lo, uint64_t& rg, Sink& sink, uint32_t& err) {
+    if (rg == 0) {  // reference: infinite loop (zero-frequency symbol)
+        if (!err) err = ST_ZERO_FREQ;
+        lo = 0;
+        rg = ~0ull;
+        return;
+    }
+    // loop 1: src/range_coder.rs:83-85,110-116
+    for (;;) {
+        uint64_t up = lo + rg;
+        if (CHECKED && up < lo) {  // upper_bound().unwrap() panics
+            if (!err) err = ST_UPPER_OVERFLOW;
+            lo = 0;
+            rg = ~0ull;
+            return;
+        }
+        if ((lo ^ up) >= TOP8) break;
+        sink.put_byte((uint32_t)(lo >> 56));
+        rg <<= 8;
+        lo <<= 8;
+    }
+    // loop 2: src/range_coder.rs:87-89,126-135 (entered only after loop 1 stopped)
+    while (rg < TOP16) {
+        rg = ~lo & (TOP16 - 1);
+        sink.put_byte((uint32_t)(lo >> 56));
+        rg <<= 8;
+        lo <<= 8;
+    }
+}
+
+template <bool CHECKED, class Sink>
+RCB_HD void renorm(uint64_t& lo, uint64_t& rg, Sink& sink, uint32_t& err) {
+    uint64_t up = lo + rg;
+    uint32_t xh = (uint32_t)((lo ^ up) >> 32);
+    uint32_t sh = clz32(xh) & 24u;  // 8 * n1 for n1 in 0..3 (xh == 0 -> 32 & 24 == 0, caught below)
+    uint64_t rg2 = rg << sh;
+    bool fast = (xh != 0) && (rg2 >= TOP16);
+    if (CHECKED) fast = fast && (up >= lo);
+    if (RCB_LIKELY(fast)) {
+        sink.put((uint32_t)(lo >> 32), sh);
+        lo <<= sh;
+        rg = rg2;
+    } else {
+        renorm_slow<CHECKED>(lo, rg, sink, err);
+    }
+}
+
+// One symbol through param_update (src/range_coder.rs:53-92).
+template <bool POW2, bool CHECKED, class Sink>
+RCB_HD void update_symbol(uint64_t& lo, uint64_t& rg, uint32_t cum, uint32_t c,
+                          const DivParams& p, Sink& sink, uint32_t& err) {
+    uint64_t rpt = range_par_total<POW2>(rg, p);  // :62
+    uint64_t add = rpt * (uint64_t)cum;           // :70
+    rg = rpt * (uint64_t)c;                       // :65
+    uint64_t nlo = lo + add;
+    if (CHECKED && nlo < lo) {                    // :74-80
+        if (!err) err = ST_LOWER_OVERFLOW;
+        nlo = 0;
+        rg = ~0ull;
+    }
+    lo = nlo;
+    renorm<CHECKED>(lo, rg, sink, err);
+}
+
+// ---------------------------------------------------------------------------
+// Encoder byte sink: big-endian bit accumulator, flushed as 32-bit words.
+// Store::word(pos, w) writes 4 bytes at byte offset pos (pos % 4 == 0),
+// Store::byte(pos, b) one byte (tail only).
+// ---------------------------------------------------------------------------
+template <class Store>
+struct EncSink {
+    uint64_t acc = 0;   // pending bytes, most recent in the low bits
+    uint32_t nb = 0;    // pending bits (multiple of 8, < 32 between symbols)
+    uint32_t pos = 0;   // bytes already stored
+    uint32_t cap;       // capacity of the row in bytes
+    uint32_t overflow = 0;
+    Store st;
+
+    RCB_HD EncSink(Store s, uint32_t cap_) : cap(cap_), st(s) {}
+
+    RCB_HD void flush_word() {
+        uint32_t w = (uint32_t)(acc >> (nb - 32u));
+        if (RCB_LIKELY(pos + 4u <= cap))
+            st.word(pos, bswap32(w));
+        else
+            overflow = 1;
+        pos += 4u;
+        nb -= 32u;
+    }
+    RCB_HD void put(uint32_t lo_hi, uint32_t sh) {
+        acc = (acc << sh) | (uint64_t)top_bits(lo_hi, sh);
+        nb += sh;
+        if (nb >= 32u) flush_word();
+    }
+    RCB_HD void put_byte(uint32_t b) {
+        acc = (acc << 8) | (uint64_t)(b & 0xFFu);
+        nb += 8u;
+        if (nb >= 32u) flush_word();
+    }
+    // src/encoder.rs:40-46: 8 x left_shift, then drain the accumulator.
+    RCB_HD uint32_t finish(uint64_t lo) {
+        for (int i = 0; i < 8; i++) {
+            put_byte((uint32_t)(lo >> 56));
+            lo <<= 8;
+        }
+        while (nb) {
+            uint32_t b = (uint32_t)(acc >> (nb - 8u)) & 0xFFu;
+            if (pos < cap)
+                st.byte(pos, b);
+            else
+                overflow = 1;
+            pos += 1u;
+            nb -= 8u;
+        }
+        return pos;  // code length (the needed capacity when overflow is set)
+    }
+};
+
+// ---------------------------------------------------------------------------
+// Decoder input window (src/decoder.rs:9,31-35): `data` is aligned with
+// lower_bound; `w` holds the following bytes left-aligned, refilled 32 bits at
+// a time by Fetch::next_be32() (big-endian word, zeros past the end).
+// ---------------------------------------------------------------------------
+template <class Fetch>
+struct DecSink {
+    uint64_t data = 0;
+    uint64_t w = 0;      // upcoming bytes, next byte in the top 8 bits
+    uint32_t cnt = 0;    // valid bits in w
+    uint32_t used = 0;   // bytes shifted into data so far
+    Fetch f;
+
+    RCB_HD explicit DecSink(Fetch fetch) : f(fetch) {}
+
+    RCB_HD void refill() {
+        // cnt < 32 here
+        w |= (uint64_t)f.next_be32() << (32u - cnt);
+        cnt += 32u;
+    }
+    // Decoder::new: data = first 8 bytes big-endian (decoder.rs:21)
+    RCB_HD void prime(uint32_t skip_bytes) {
+        // first fetched word may contain skip_bytes leading bytes before the chunk
+        uint32_t first = f.next_be32();
+        w = (uint64_t)first << (32u + 8u * skip_bytes);
+        cnt = 32u - 8u * skip_bytes;
+        for (int i = 0; i < 8; i++) put_byte(0);
+    }
+    RCB_HD void put(uint32_t /*lo_hi*/, uint32_t sh) {
+        data = (data << sh) | (uint64_t)top_bits((uint32_t)(w >> 32), sh);
+        w <<= sh;
+        cnt -= sh;
+        used += sh >> 3;
+        if (cnt < 32u) refill();
+    }
+    RCB_HD void put_byte(uint32_t /*b*/) {
+        if (cnt < 8u) refill();
+        data = (data << 8) | (w >> 56);
+        w <<= 8;
+        cnt -= 8u;
+        used += 1u;
+        if (cnt < 32u) refill();
+    }
+};
+
+// ---------------------------------------------------------------------------
+// Symbol lookup (examples/sample_impl.rs:27-45) in the product domain.
+// Reference: rfreq = d / rpt; binary search for the smallest `left` with
+// cum[left+1] > rfreq.  cum[i] <= d / rpt  <=>  cum[i] * rpt <= d, and
+// cum[i] * rpt <= total * rpt <= range cannot wrap for a validated table.
+// CumAt(i) returns cum[i] for 1 <= i <= K-1.
+// ---------------------------------------------------------------------------
+template <class CumAt>
+RCB_HD uint32_t find_index_exact(uint64_t d, uint64_t rpt, uint32_t K, CumAt cum_at) {
+    uint32_t left = 0, right = K - 1;
+    while (left < right) {
+        uint32_t mid = (left + right) >> 1;
+        uint64_t prod = rpt * (uint64_t)cum_at(mid + 1);
+        if (prod <= d)
+            left = mid + 1;
+        else
+            right = mid;
+    }
+    return left;
+}
+
+
+// ---------------------------------------------------------------------------
+// Table-driven lookup for a REGULAR table (cum[i+1] == cum[i] + c[i]).
+// The rfreq axis [0,total) is cut into nb buckets of width 2^wshift.  Entry b
+// describes the symbol A whose interval contains b<<wshift and the next
+// non-zero symbol B:  [cumA,cumB) -> A, [cumB,cumC) -> B.
+// The bucket is chosen from a float estimate of d/rpt ~= d*total/range biased
+// low (rpt = floor(range/total) only makes the true quotient larger), then the
+// choice is verified exactly in the product domain; any miss (estimate off,
+// more than one boundary in the bucket, clamp-to-K-1 case, garbage stream)
+// falls back to find_index_exact, so the result never depends on float error.
+// ---------------------------------------------------------------------------
+struct LutEntry {
+    uint32_t cumA, cumB, cumC;
+    uint32_t syms;  // A | B << 16
+};
+
+struct ModelHdr {
+    DivParams div;       // 16 bytes
+    uint32_t flags;      // RCB_MODEL_* (include/rcb200.h)
+    uint32_t min_c;      // smallest non-zero c_freq (staging bound)
+    uint32_t nb;         // LUT buckets (shared model only, else 0)
+    uint32_t wshift;     // log2(bucket width)
+    float lut_scale;     // total / 2^wshift
+    uint32_t K;
+    uint32_t pad0, pad1;
+};
+
+enum : uint32_t { MODEL_POW2 = 1, MODEL_CONSISTENT = 2, MODEL_REGULAR = 4 };
+
+RCB_HD float u64_to_float(uint64_t x) {
+    return (float)(uint32_t)(x >> 32) * 4294967296.0f + (float)(uint32_t)x;
+}
+
+RCB_HD float fast_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+
+RCB_HD uint32_t lut_bucket(uint64_t d, uint64_t rg, float scale, float max_bucket) {
+    float bf = u64_to_float(d) * fast_rcp(u64_to_float(rg)) * scale - (1.0f / 128.0f);
+    bf = bf < 0.0f ? 0.0f : bf;
+    bf = bf > max_bucket ? max_bucket : bf;
+    return (uint32_t)bf;
+}
+
+// Returns true when the entry resolves the symbol; then sym, P = rpt*cum[sym]
+// and rgn = rpt*c[sym] are set.
+RCB_HD bool lut_resolve(const LutEntry& e, uint64_t d, uint64_t rpt, uint32_t& sym,
+                        uint64_t& P, uint64_t& rgn) {
+    uint64_t PA = rpt * (uint64_t)e.cumA;
+    uint64_t PB = rpt * (uint64_t)e.cumB;
+    uint64_t PC = rpt * (uint64_t)e.cumC;
+    bool takeB = d >= PB;
+    P = takeB ? PB : PA;
+    uint64_t PN = takeB ? PC : PB;
+    sym = takeB ? (e.syms >> 16) : (e.syms & 0xFFFFu);
+    rgn = PN - P;
+    return (d - P) < rgn;  // P <= d < PN (unsigned wrap makes d < P fail)
+}
+
+}  // namespace rcb

@@ -1,0 +1,751 @@
+// rcb_kernels.cuh -- sm_100a kernels of the chunk-parallel range coder.
+//
+//   K1 hist_global_kernel / hist_chunks_kernel   examples/sample_impl.rs:58-60,78-80
+//   K2 counts_to_tables_kernel / finalize_models_kernel  examples/sample_impl.rs:61-69
+//   K3 encode_kernel                              src/encoder.rs:24-46, src/range_coder.rs:53-135
+//   K4 scan_lengths_kernel + gather_kernel        (no reference analogue: one VecDeque there)
+//   K5 decode_kernel                              src/decoder.rs:14-54, examples/sample_impl.rs:27-45
+//   generate_kernel                               synthetic benchmark inputs
+//
+// Layout in HBM
+//   symbols   [n_chunks][chunk_syms] u8 / u16-LE, dense, chunk i at i*chunk_syms
+//   tables    [n_models][K] uint2 {cum, c}; headers [n_models] ModelHdr; LUT [nb] (shared model)
+//   staging   [n_chunks][pitch] bytes, pitch % 16 == 0 (ctx scratch)
+//   lengths   [n_chunks] u32; offsets [n_chunks+1] u64; stream dense bytes
+// One coder state (lower_bound, range) per lane; lane l of a block owns chunk
+// blockIdx.x * blockDim.x + l from its first to its last symbol.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rcb_core.cuh"
+
+namespace rcb {
+
+// ------------------------------------------------------------------ helpers
+__device__ __forceinline__ uint4 ldg_stream_v4(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, uint32_t lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= (uint32_t)o) v += t;
+    }
+    return v;
+}
+
+__device__ __forceinline__ unsigned long long warp_incl_scan64(unsigned long long v, uint32_t lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= (uint32_t)o) v += t;
+    }
+    return v;
+}
+
+// =============================================================== K1 histogram
+// Global histogram.  Each warp owns a private copy of the K bins in shared
+// memory (bins of one copy are K consecutive words), merged into the u64
+// global table with one atomic per non-zero bin per block.
+template <typename SYM>
+__global__ void __launch_bounds__(256) hist_global_kernel(const SYM* __restrict__ syms, uint64_t n,
+                                                          uint32_t K, unsigned long long* counts,
+                                                          uint32_t* bad) {
+    extern __shared__ uint32_t s_hist[];  // [warps][K]
+    const uint32_t warps = blockDim.x >> 5, warp = threadIdx.x >> 5;
+    for (uint32_t i = threadIdx.x; i < warps * K; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    uint32_t* h = s_hist + warp * K;
+    constexpr uint32_t PER = 16 / sizeof(SYM);
+    const uint64_t nvec = n / PER;
+    const uint4* v = reinterpret_cast<const uint4*>(syms);
+    uint32_t oob = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 q = ldg_stream_v4(v + i);
+        uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (sizeof(SYM) == 1) {
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    uint32_t s = (w[j] >> (8 * b)) & 0xFFu;
+                    if (s < K) atomicAdd(&h[s], 1u); else oob = 1;
+                }
+            } else {
+#pragma unroll
+                for (int b = 0; b < 2; b++) {
+                    uint32_t s = (w[j] >> (16 * b)) & 0xFFFFu;
+                    if (s < K) atomicAdd(&h[s], 1u); else oob = 1;
+                }
+            }
+        }
+    }
+    // tail symbols (n not a multiple of the vector width)
+    if (blockIdx.x == 0) {
+        for (uint64_t i = nvec * PER + threadIdx.x; i < n; i += blockDim.x) {
+            uint32_t s = syms[i];
+            if (s < K) atomicAdd(&h[s], 1u); else oob = 1;
+        }
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < K; b += blockDim.x) {
+        unsigned long long t = 0;
+        for (uint32_t w = 0; w < warps; w++) t += s_hist[w * K + b];
+        if (t) atomicAdd(&counts[b], t);
+    }
+    if (oob) atomicOr(bad, 1u);
+}
+
+// One block per chunk: u32 counts[n_chunks][K].
+template <typename SYM>
+__global__ void __launch_bounds__(256) hist_chunks_kernel(const SYM* __restrict__ syms, uint64_t n,
+                                                          uint64_t chunk_syms, uint32_t K,
+                                                          uint32_t* counts, uint32_t* bad) {
+    extern __shared__ uint32_t s_hist[];  // [warps][K]
+    const uint32_t warps = blockDim.x >> 5, warp = threadIdx.x >> 5;
+    const uint64_t chunk = blockIdx.x;
+    const uint64_t first = chunk * chunk_syms;
+    const uint64_t cnt = (n - first < chunk_syms) ? (n - first) : chunk_syms;
+    for (uint32_t i = threadIdx.x; i < warps * K; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    uint32_t* h = s_hist + warp * K;
+    const SYM* p = syms + first;
+    uint32_t oob = 0;
+    constexpr uint32_t PER = 16 / sizeof(SYM);
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(p) & 15u) == 0);
+    uint64_t done = 0;
+    if (vec_ok) {
+        const uint64_t nvec = cnt / PER;
+        const uint4* v = reinterpret_cast<const uint4*>(p);
+        for (uint64_t i = threadIdx.x; i < nvec; i += blockDim.x) {
+            uint4 q = ldg_stream_v4(v + i);
+            uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (sizeof(SYM) == 1) {
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        uint32_t s = (w[j] >> (8 * b)) & 0xFFu;
+                        if (s < K) atomicAdd(&h[s], 1u); else oob = 1;
+                    }
+                } else {
+#pragma unroll
+                    for (int b = 0; b < 2; b++) {
+                        uint32_t s = (w[j] >> (16 * b)) & 0xFFFFu;
+                        if (s < K) atomicAdd(&h[s], 1u); else oob = 1;
+                    }
+                }
+            }
+        }
+        done = nvec * PER;
+    }
+    for (uint64_t i = done + threadIdx.x; i < cnt; i += blockDim.x) {
+        uint32_t s = p[i];
+        if (s < K) atomicAdd(&h[s], 1u); else oob = 1;
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < K; b += blockDim.x) {
+        uint32_t t = 0;
+        for (uint32_t w = 0; w < warps; w++) t += s_hist[w * K + b];
+        counts[chunk * K + b] = t;
+    }
+    if (oob) atomicOr(bad, 1u);
+}
+
+// ============================================================ K2 model build
+// counts -> {cum, c} tables.  One block (256 threads) per model:
+//   c   = normalise(counts)            (identity unless a u64 sum > 2^32-1)
+//   cum = exclusive prefix sum of c    (warp-shuffle scan + carry across tiles)
+//   total = sum c
+template <typename CNT>
+__global__ void __launch_bounds__(256) counts_to_tables_kernel(const CNT* __restrict__ counts,
+                                                               uint32_t K, uint2* tabs,
+                                                               uint32_t* totals) {
+    __shared__ unsigned long long s_warp[8];
+    __shared__ unsigned long long s_carry;
+    __shared__ uint32_t s_shift;
+    const uint64_t model = blockIdx.x;
+    const CNT* cnt = counts + model * K;
+    uint2* tab = tabs + model * K;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // pass 1: sum (u64) to decide the normalisation shift
+    unsigned long long part = 0;
+    for (uint32_t i = threadIdx.x; i < K; i += blockDim.x) part += (unsigned long long)cnt[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+    if (lane == 0) s_warp[warp] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long sum = 0;
+        for (uint32_t w = 0; w < (blockDim.x >> 5); w++) sum += s_warp[w];
+        uint32_t sh = 0;
+        if (sum > 0xFFFFFFFFull)
+            while ((sum >> sh) + K > 0xFFFFFFFFull) sh++;
+        s_shift = sh;
+        s_carry = 0;
+    }
+    __syncthreads();
+    const uint32_t sh = s_shift;
+
+    // pass 2: tiles of blockDim.x symbols, exclusive scan with running carry
+    for (uint32_t base = 0; base < K; base += blockDim.x) {
+        uint32_t i = base + threadIdx.x;
+        unsigned long long raw = i < K ? (unsigned long long)cnt[i] : 0ull;
+        uint32_t c = 0;
+        if (raw) {
+            unsigned long long s = raw >> sh;
+            c = (uint32_t)(s ? s : 1ull);
+        }
+        uint32_t incl = warp_incl_scan(c, lane);
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t woff = 0;
+        for (uint32_t w = 0; w < warp; w++) woff += (uint32_t)s_warp[w];
+        uint32_t carry = (uint32_t)s_carry;
+        uint32_t cum = carry + woff + incl - c;  // u32 wrapping like release-mode Rust
+        if (i < K) tab[i] = make_uint2(cum, c);
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = (unsigned long long)(cum + c);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) totals[model] = (uint32_t)s_carry;
+}
+
+// Validate a table, derive its header (reciprocal, flags, staging bound) and,
+// for the shared model, the decode LUT.  One block per model.
+__global__ void __launch_bounds__(256) finalize_models_kernel(const uint2* __restrict__ tabs,
+                                                              const uint32_t* __restrict__ totals,
+                                                              uint32_t K, ModelHdr* hdrs,
+                                                              LutEntry* lut, uint32_t lut_cap,
+                                                              uint32_t* summary /*[0]=min c, [1]=bad bits, [3]=max total*/) {
+    __shared__ uint32_t s_flags_bad;  // bit0 inconsistent, bit1 irregular, bit2 cum>total
+    __shared__ uint32_t s_minc;
+    const uint64_t model = blockIdx.x;
+    const uint2* tab = tabs + model * K;
+    const uint32_t total = totals[model];
+    if (threadIdx.x == 0) {
+        s_flags_bad = 0;
+        s_minc = 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    uint32_t bad = 0, minc = 0xFFFFFFFFu;
+    for (uint32_t i = threadIdx.x; i < K; i += blockDim.x) {
+        uint2 e = tab[i];
+        unsigned long long end = (unsigned long long)e.x + e.y;
+        if (end > total) bad |= 1u;
+        if (e.x > total) bad |= 4u;
+        if (i + 1 < K) {
+            if ((unsigned long long)tab[i + 1].x != end) bad |= 2u;
+        }
+        if (e.y && e.y < minc) minc = e.y;
+    }
+    if (bad) atomicOr(&s_flags_bad, bad);
+    atomicMin(&s_minc, minc);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ModelHdr h;
+        h.div.total = total;
+        h.div.shift = 0;
+        h.div.magic = 0;
+        uint32_t flags = 0;
+        if (total && (total & (total - 1)) == 0) {
+            flags |= MODEL_POW2;
+            h.div.shift = 31u - (uint32_t)__clz((int)total);
+        } else if (total) {
+            h.div.magic = 0xFFFFFFFFFFFFFFFFull / total;  // == floor(2^64/total): total does not divide 2^64
+        }
+        if (!(s_flags_bad & 1u)) flags |= MODEL_CONSISTENT;
+        if (!(s_flags_bad & 3u)) flags |= MODEL_REGULAR;
+        h.flags = flags;
+        h.min_c = s_minc;
+        h.K = K;
+        // LUT geometry (used only when lut != nullptr)
+        uint32_t bits = total > 1 ? 32u - (uint32_t)__clz((int)(total - 1)) : 0u;  // ceil(log2 total)
+        uint32_t lg_cap = 31u - (uint32_t)__clz((int)lut_cap);
+        h.wshift = bits > lg_cap ? bits - lg_cap : 0u;
+        h.nb = total ? (uint32_t)((((unsigned long long)total - 1) >> h.wshift) + 1) : 0u;
+        h.lut_scale = (float)total / (float)(1ull << h.wshift);
+        h.pad0 = h.pad1 = 0;
+        hdrs[model] = h;
+        if (s_flags_bad & 4u) atomicOr(&summary[1], 1u);
+        if (total == 0) atomicOr(&summary[1], 2u);
+        if (s_flags_bad & 1u) atomicOr(&summary[1], 4u);   // some model inconsistent
+        if (s_flags_bad & 3u) atomicOr(&summary[1], 8u);   // some model irregular
+        atomicMin(&summary[0], s_minc);
+        atomicMax(&summary[3], total);
+    }
+    if (lut == nullptr || total == 0) return;
+    __syncthreads();
+    // LUT (shared model only; blockIdx.x == 0).  Built only for REGULAR tables.
+    const ModelHdr& H = hdrs[model];
+    if (!(H.flags & MODEL_REGULAR)) return;
+    for (uint32_t b = threadIdx.x; b < H.nb; b += blockDim.x) {
+        unsigned long long v0 = (unsigned long long)b << H.wshift;  // < total
+        // A = number of i in [1,K-1] with cum[i] <= v0  (the reference's search result)
+        uint32_t left = 0, right = K - 1;
+        while (left < right) {
+            uint32_t mid = (left + right) >> 1;
+            if ((unsigned long long)tab[mid + 1].x <= v0) left = mid + 1; else right = mid;
+        }
+        uint32_t A = left;
+        uint2 ea = tab[A];
+        uint32_t cumA = ea.x, cumB = ea.x + ea.y;
+        uint32_t B = A + 1;
+        while (B < K && tab[B].y == 0) B++;
+        uint32_t cumC = cumB;
+        if (B < K) cumC = cumB + tab[B].y;
+        LutEntry e;
+        e.cumA = cumA;
+        e.cumB = cumB;
+        e.cumC = cumC;
+        e.syms = A | ((B & 0xFFFFu) << 16);
+        lut[b] = e;
+    }
+}
+
+// ================================================================= K3 encode
+struct EncodeArgs {
+    const void* syms;
+    uint64_t n_syms;
+    uint64_t chunk_syms;
+    uint64_t n_chunks;
+    const uint2* tabs;      // [n_models][K]
+    const ModelHdr* hdrs;   // [n_models]
+    uint32_t K;
+    uint32_t per_chunk;     // 1: model index = chunk
+    uint8_t* staging;       // [n_chunks][pitch]
+    uint64_t pitch;
+    uint32_t* lens;         // [n_chunks]
+    uint32_t* status;       // [n_chunks]
+};
+
+struct RowStore {
+    uint8_t* row;
+    __device__ __forceinline__ void word(uint32_t pos, uint32_t w) const {
+        *reinterpret_cast<uint32_t*>(row + pos) = w;
+    }
+    __device__ __forceinline__ void byte(uint32_t pos, uint32_t b) const { row[pos] = (uint8_t)b; }
+};
+
+// SHARED: one table for all chunks, staged in shared memory.
+// !SHARED: one table per chunk, read through L1/L2 from global memory.
+template <typename SYM, bool SHARED, bool POW2, bool CHECKED, bool RANGECHK>
+__global__ void __launch_bounds__(256) encode_kernel(EncodeArgs a) {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    uint2* s_tab = reinterpret_cast<uint2*>(s_raw);
+    __shared__ ModelHdr s_hdr;
+    if (SHARED) {
+        for (uint32_t i = threadIdx.x; i < a.K; i += blockDim.x) s_tab[i] = a.tabs[i];
+        if (threadIdx.x == 0) s_hdr = a.hdrs[0];
+        __syncthreads();
+    }
+    const uint64_t chunk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (chunk >= a.n_chunks) return;
+    const uint64_t first = chunk * a.chunk_syms;
+    const uint64_t cnt = (a.n_syms - first < a.chunk_syms) ? (a.n_syms - first) : a.chunk_syms;
+    const SYM* src = reinterpret_cast<const SYM*>(a.syms) + first;
+
+    const uint2* tab = SHARED ? s_tab : a.tabs + chunk * a.K;
+    DivParams div;
+    bool pow2 = POW2;
+    if (SHARED) {
+        div = s_hdr.div;
+    } else {
+        ModelHdr h = a.hdrs[chunk];
+        div = h.div;
+        pow2 = (h.flags & MODEL_POW2) != 0;
+    }
+    const uint32_t K = a.K;
+
+    uint64_t lo = 0, rg = ~0ull;  // src/range_coder.rs:13-20
+    uint32_t err = 0;
+    RowStore rs{a.staging + chunk * a.pitch};
+    EncSink<RowStore> sink(rs, (uint32_t)a.pitch);
+
+    auto step = [&](uint32_t s) {
+        if (RANGECHK && s >= K) {
+            if (!err) err = ST_SYMBOL_RANGE;
+            s = 0;
+        }
+        uint2 e = tab[s];
+        if (SHARED) {
+            update_symbol<POW2, CHECKED>(lo, rg, e.x, e.y, div, sink, err);
+        } else {
+            if (pow2)
+                update_symbol<true, CHECKED>(lo, rg, e.x, e.y, div, sink, err);
+            else
+                update_symbol<false, CHECKED>(lo, rg, e.x, e.y, div, sink, err);
+        }
+    };
+
+    constexpr uint32_t PER = 16 / sizeof(SYM);
+    uint64_t done = 0;
+    if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+        const uint4* v = reinterpret_cast<const uint4*>(src);
+        const uint64_t nvec = cnt / PER;
+        uint4 cur = nvec ? ldg_stream_v4(v) : make_uint4(0, 0, 0, 0);
+        for (uint64_t i = 0; i < nvec; i++) {
+            // one vector of lookahead hides the global-load latency behind 16 symbols of work
+            uint4 nxt = (i + 1 < nvec) ? ldg_stream_v4(v + i + 1) : make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+            for (int j = 0; j < 4; j++) {
+                const uint32_t w = cur.x;
+                cur.x = cur.y;
+                cur.y = cur.z;
+                cur.z = cur.w;
+                if (sizeof(SYM) == 1) {
+#pragma unroll
+                    for (int b = 0; b < 4; b++) step((w >> (8 * b)) & 0xFFu);
+                } else {
+#pragma unroll
+                    for (int b = 0; b < 2; b++) step((w >> (16 * b)) & 0xFFFFu);
+                }
+            }
+            cur = nxt;
+        }
+        done = nvec * PER;
+    }
+#pragma unroll 1
+    for (uint64_t i = done; i < cnt; i++) step((uint32_t)src[i]);
+
+    uint32_t len = sink.finish(lo);  // src/encoder.rs:40-46
+    if (!err && sink.overflow) err = ST_OUT_CAPACITY;
+    a.lens[chunk] = len;
+    a.status[chunk] = err;
+}
+
+// ============================================================ K4 compaction
+// Exclusive scan of the chunk lengths into u64 offsets, plus an error summary:
+// summary[0] = number of chunks with status != 0, [1] = first such chunk,
+// [2] = its status, [3] = max length (needed pitch after ST_OUT_CAPACITY).
+__global__ void __launch_bounds__(1024) scan_lengths_kernel(const uint32_t* __restrict__ lens,
+                                                            const uint32_t* __restrict__ status,
+                                                            uint64_t n, uint64_t* offsets,
+                                                            unsigned long long* summary) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_bad[32];
+    __shared__ unsigned long long s_first[32];
+    __shared__ uint32_t s_maxlen[32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t per = (n + blockDim.x - 1) / blockDim.x;
+    const uint64_t lo = (uint64_t)threadIdx.x * per < n ? (uint64_t)threadIdx.x * per : n;
+    const uint64_t hi = lo + per < n ? lo + per : n;
+    unsigned long long sum = 0, bad = 0, firstbad = ~0ull;
+    uint32_t maxlen = 0;
+    for (uint64_t i = lo; i < hi; i++) {
+        uint32_t l = lens[i];
+        sum += l;
+        maxlen = l > maxlen ? l : maxlen;
+        if (status[i]) {
+            bad++;
+            if (firstbad == ~0ull) firstbad = i;
+        }
+    }
+    unsigned long long incl = warp_incl_scan64(sum, lane);
+    unsigned long long wbad = bad, wfirst = firstbad;
+    uint32_t wmax = maxlen;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        wbad += __shfl_down_sync(0xffffffffu, wbad, o);
+        unsigned long long f = __shfl_down_sync(0xffffffffu, wfirst, o);
+        wfirst = f < wfirst ? f : wfirst;
+        uint32_t m = __shfl_down_sync(0xffffffffu, wmax, o);
+        wmax = m > wmax ? m : wmax;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    if (lane == 0) {
+        s_bad[warp] = wbad;
+        s_first[warp] = wfirst;
+        s_maxlen[warp] = wmax;
+    }
+    __syncthreads();
+    unsigned long long woff = 0;
+    for (uint32_t w = 0; w < warp; w++) woff += s_warp[w];
+    unsigned long long run = woff + incl - sum;
+    for (uint64_t i = lo; i < hi; i++) {
+        offsets[i] = run;
+        run += lens[i];
+    }
+    if (threadIdx.x == blockDim.x - 1) offsets[n] = woff + incl;
+    if (threadIdx.x == 0) {
+        unsigned long long tb = 0, tf = ~0ull;
+        uint32_t tm = 0;
+        for (uint32_t w = 0; w < (blockDim.x >> 5); w++) {
+            tb += s_bad[w];
+            tf = s_first[w] < tf ? s_first[w] : tf;
+            tm = s_maxlen[w] > tm ? s_maxlen[w] : tm;
+        }
+        summary[0] = tb;
+        summary[1] = tf;
+        summary[2] = tb ? status[tf] : 0;
+        summary[3] = tm;
+    }
+}
+
+// 16-byte word at byte offset `off` (any alignment) of a 16-byte aligned row.
+__device__ __forceinline__ uint4 load_unaligned16(const uint8_t* row, uint64_t off) {
+    const uint4* p = reinterpret_cast<const uint4*>(row + (off & ~15ull));
+    uint4 a = p[0];
+    uint32_t sh = (uint32_t)(off & 15u);
+    if (sh == 0) return a;
+    uint4 b = p[1];
+    uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t q = sh >> 2, r = (sh & 3u) * 8u;
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint32_t x0 = 0, x1 = 0;
+        // q is uniform per block: the compiler resolves this into 4 predicated cases
+#pragma unroll
+        for (int qq = 0; qq < 4; qq++)
+            if ((uint32_t)qq == q) {
+                x0 = w[qq + k];
+                x1 = w[qq + k + 1];
+            }
+        o[k] = __funnelshift_r(x0, x1, r);
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// One block per chunk: staging row -> stream[offsets[chunk] ...).  The
+// destination is written with aligned 16-byte stores; the (constant per chunk)
+// source misalignment is absorbed by funnel shifts.
+__global__ void __launch_bounds__(256) gather_kernel(const uint8_t* __restrict__ staging, uint64_t pitch,
+                                                     const uint32_t* __restrict__ lens,
+                                                     const uint64_t* __restrict__ offsets,
+                                                     uint8_t* out, uint64_t out_cap) {
+    const uint64_t chunk = blockIdx.x;
+    const uint8_t* row = staging + chunk * pitch;
+    const uint64_t off = offsets[chunk];
+    uint64_t len = lens[chunk];
+    if (len > pitch) len = pitch;           // ST_OUT_CAPACITY rows hold only `pitch` bytes
+    if (off + len > out_cap) return;        // reported through h_out_bytes > out_cap
+    uint8_t* dst = out + off;
+    uint64_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u;
+    if (head > len) head = len;
+    for (uint64_t i = threadIdx.x; i < head; i += blockDim.x) dst[i] = row[i];
+    const uint64_t nvec = (len - head) >> 4;
+    uint4* dv = reinterpret_cast<uint4*>(dst + head);
+    for (uint64_t v = threadIdx.x; v < nvec; v += blockDim.x)
+        dv[v] = load_unaligned16(row, head + (v << 4));
+    const uint64_t tail0 = head + (nvec << 4);
+    for (uint64_t i = tail0 + threadIdx.x; i < len; i += blockDim.x) dst[i] = row[i];
+}
+
+// ================================================================= K5 decode
+struct DecodeArgs {
+    const uint8_t* stream;
+    const uint64_t* offsets;  // [n_chunks+1]
+    uint64_t n_syms;
+    uint64_t chunk_syms;
+    uint64_t n_chunks;
+    const uint2* tabs;
+    const ModelHdr* hdrs;
+    const LutEntry* lut;      // shared model only
+    uint32_t K;
+    uint32_t per_chunk;
+    void* out;
+    uint32_t* status;
+};
+
+// Sequential reader of one chunk's bytes: aligned 32-bit loads, one word of
+// lookahead in a register, zeros past `end`.
+struct GlobalFetch {
+    const uint32_t* p;
+    const uint32_t* end;
+    uint32_t nextw;
+    __device__ __forceinline__ void init(const uint8_t* start, const uint8_t* stream_end) {
+        p = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(start) & ~(uintptr_t)3);
+        end = reinterpret_cast<const uint32_t*>((reinterpret_cast<uintptr_t>(stream_end) + 3) & ~(uintptr_t)3);
+        nextw = p < end ? __ldg(p) : 0u;
+    }
+    __device__ __forceinline__ uint32_t next_be32() {
+        uint32_t r = bswap32(nextw);
+        p++;
+        nextw = p < end ? __ldg(p) : 0u;
+        return r;
+    }
+};
+
+template <typename SYM, bool SHARED, bool POW2, bool CHECKED>
+__global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    __shared__ ModelHdr s_hdr;
+    // shared layout: LutEntry[nb] | uint2[K]
+    LutEntry* s_lut = reinterpret_cast<LutEntry*>(s_raw);
+    uint2* s_tab = nullptr;
+    if (SHARED) {
+        if (threadIdx.x == 0) s_hdr = a.hdrs[0];
+        __syncthreads();
+        const uint32_t nb = (s_hdr.flags & MODEL_REGULAR) ? s_hdr.nb : 0u;
+        s_tab = reinterpret_cast<uint2*>(s_raw + (size_t)nb * sizeof(LutEntry));
+        const uint4* gl = reinterpret_cast<const uint4*>(a.lut);
+        uint4* sl = reinterpret_cast<uint4*>(s_lut);
+        for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) sl[i] = gl[i];
+        for (uint32_t i = threadIdx.x; i < a.K; i += blockDim.x) s_tab[i] = a.tabs[i];
+        __syncthreads();
+    }
+    const uint64_t chunk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (chunk >= a.n_chunks) return;
+    const uint64_t first = chunk * a.chunk_syms;
+    const uint64_t cnt = (a.n_syms - first < a.chunk_syms) ? (a.n_syms - first) : a.chunk_syms;
+    SYM* dst = reinterpret_cast<SYM*>(a.out) + first;
+
+    const uint2* tab = SHARED ? s_tab : a.tabs + chunk * a.K;
+    ModelHdr hdr = SHARED ? s_hdr : a.hdrs[chunk];
+    const DivParams div = hdr.div;
+    const bool pow2 = SHARED ? POW2 : ((hdr.flags & MODEL_POW2) != 0);
+    const bool use_lut = SHARED && (hdr.flags & MODEL_REGULAR);
+    const float lut_scale = hdr.lut_scale;
+    const float max_bucket = (float)(hdr.nb ? hdr.nb - 1 : 0);
+    const uint32_t K = a.K;
+
+    const uint64_t off0 = a.offsets[chunk], off1 = a.offsets[chunk + 1];
+    const uint8_t* start = a.stream + off0;
+    GlobalFetch gf;
+    gf.init(start, a.stream + a.offsets[a.n_chunks]);
+    DecSink<GlobalFetch> sink(gf);
+    sink.prime((uint32_t)(reinterpret_cast<uintptr_t>(start) & 3u));  // src/decoder.rs:14-23
+
+    uint64_t lo = 0, rg = ~0ull;
+    uint32_t err = 0;
+
+    auto step = [&]() -> uint32_t {
+        uint64_t rpt = pow2 ? range_par_total<true>(rg, div) : range_par_total<false>(rg, div);
+        uint64_t d = sink.data - lo;  // examples/sample_impl.rs:29
+        uint32_t sym;
+        uint64_t P, rgn;
+        bool ok = false;
+        if (use_lut) {
+            uint32_t b = lut_bucket(d, rg, lut_scale, max_bucket);
+            LutEntry e = s_lut[b];
+            ok = lut_resolve(e, d, rpt, sym, P, rgn);
+        }
+        if (!ok) {
+            sym = find_index_exact(d, rpt, K, [&](uint32_t i) { return tab[i].x; });
+            uint2 e = tab[sym];
+            P = rpt * (uint64_t)e.x;
+            rgn = rpt * (uint64_t)e.y;
+        }
+        // param_update with the symbol's (c, cum): src/decoder.rs:42-50
+        uint64_t nlo = lo + P;
+        if (CHECKED && nlo < lo) {
+            if (!err) err = ST_LOWER_OVERFLOW;
+            nlo = 0;
+            rgn = ~0ull;
+        }
+        lo = nlo;
+        rg = rgn;
+        renorm<CHECKED>(lo, rg, sink, err);  // consumes the same number of bytes (:52)
+        return sym;
+    };
+
+    constexpr uint32_t PER = 4 / sizeof(SYM);  // symbols per 32-bit store
+    uint64_t done = 0;
+    if ((reinterpret_cast<uintptr_t>(dst) & 3u) == 0) {
+        uint32_t* dw = reinterpret_cast<uint32_t*>(dst);
+        const uint64_t nw = cnt / PER;
+#pragma unroll 1
+        for (uint64_t i = 0; i < nw; i++) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (uint32_t b = 0; b < PER; b++) acc |= step() << (8 * sizeof(SYM) * b);
+            dw[i] = acc;
+        }
+        done = nw * PER;
+    }
+#pragma unroll 1
+    for (uint64_t i = done; i < cnt; i++) dst[i] = (SYM)step();
+
+    if (!err && (uint64_t)sink.used > off1 - off0) err = ST_TRUNCATED;  // src/decoder.rs:33
+    a.status[chunk] = err;
+}
+
+// Reduce a status array into the same 4-word summary scan_lengths_kernel writes.
+__global__ void __launch_bounds__(1024) status_summary_kernel(const uint32_t* __restrict__ status,
+                                                              uint64_t n, unsigned long long* summary) {
+    __shared__ unsigned long long s_bad[32];
+    __shared__ unsigned long long s_first[32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long bad = 0, firstbad = ~0ull;
+    for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        if (status[i]) {
+            bad++;
+            if (i < firstbad) firstbad = i;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        bad += __shfl_down_sync(0xffffffffu, bad, o);
+        unsigned long long f = __shfl_down_sync(0xffffffffu, firstbad, o);
+        firstbad = f < firstbad ? f : firstbad;
+    }
+    if (lane == 0) {
+        s_bad[warp] = bad;
+        s_first[warp] = firstbad;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long tb = 0, tf = ~0ull;
+        for (uint32_t w = 0; w < (blockDim.x >> 5); w++) {
+            tb += s_bad[w];
+            tf = s_first[w] < tf ? s_first[w] : tf;
+        }
+        summary[0] = tb;
+        summary[1] = tf;
+        summary[2] = tb ? status[tf] : 0;
+        summary[3] = 0;
+    }
+}
+
+// ============================================================ synthetic data
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+template <typename SYM>
+__global__ void __launch_bounds__(256) generate_kernel(SYM* out, uint64_t first, uint64_t n, uint32_t K,
+                                                       uint64_t seed, const uint32_t* __restrict__ thr,
+                                                       uint32_t n_tables, uint64_t chunk_syms) {
+    extern __shared__ uint32_t s_thr[];  // [n_tables][K-1]
+    const uint32_t nthr = K - 1;
+    for (uint32_t i = threadIdx.x; i < n_tables * nthr; i += blockDim.x) s_thr[i] = thr[i];
+    __syncthreads();
+    constexpr uint32_t PER = 16 / sizeof(SYM);
+    const uint64_t ngroups = (n + PER - 1) / PER;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups;
+         g += (uint64_t)gridDim.x * blockDim.x) {
+        __align__(16) SYM v[PER];
+#pragma unroll
+        for (uint32_t k = 0; k < PER; k++) {
+            uint64_t j = first + g * PER + k;
+            uint32_t r = (uint32_t)(mix64(seed + j * 0x9E3779B97F4A7C15ull) >> 32);
+            uint32_t t = n_tables > 1 ? (uint32_t)((j / chunk_syms) % n_tables) : 0u;
+            const uint32_t* th = s_thr + t * nthr;
+            uint32_t lo = 0, hi = nthr;
+            while (lo < hi) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (th[mid] <= r) lo = mid + 1; else hi = mid;
+            }
+            v[k] = (SYM)lo;
+        }
+        uint64_t base = g * PER;
+        if (base + PER <= n && (reinterpret_cast<uintptr_t>(out + base) & 15u) == 0) {
+            *reinterpret_cast<uint4*>(out + base) = *reinterpret_cast<uint4*>(v);
+        } else {
+            for (uint32_t k = 0; k < PER && base + k < n; k++) out[base + k] = v[k];
+        }
+    }
+}
+
+}  // namespace rcb

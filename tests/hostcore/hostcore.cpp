@@ -1,0 +1,191 @@
+// hostcore.cpp -- TEST INFRASTRUCTURE ONLY (never loaded by the package).
+//
+// Compiles the host instantiation of range_coder_rust_b200/csrc/rcb_core.cuh with
+// g++ so the closed-form renormalisation, the byte sinks, the reciprocal division
+// and the table-driven symbol lookup can be compared with the oracle on a machine
+// without a GPU.  The loops below mirror encode_kernel / decode_kernel lane by lane.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../range_coder_rust_b200/csrc/rcb_core.cuh"
+
+using namespace rcb;
+
+namespace {
+
+struct HostStore {
+    uint8_t* row;
+    void word(uint32_t pos, uint32_t w) const { memcpy(row + pos, &w, 4); }
+    void byte(uint32_t pos, uint32_t b) const { row[pos] = (uint8_t)b; }
+};
+
+struct HostFetch {
+    const uint8_t* base;  // aligned-down start
+    uint64_t pos;         // next word offset from base
+    const uint8_t* end;
+    uint32_t next_be32() {
+        uint32_t w = 0;
+        for (int i = 0; i < 4; i++) {
+            const uint8_t* p = base + pos + i;
+            uint32_t b = p < end ? *p : 0u;
+            w = (w << 8) | b;
+        }
+        pos += 4;
+        return w;
+    }
+};
+
+uint32_t load_sym(const uint8_t* syms, uint64_t i, int sb) {
+    if (sb == 1) return syms[i];
+    return (uint32_t)syms[2 * i] | ((uint32_t)syms[2 * i + 1] << 8);
+}
+void store_sym(uint8_t* out, uint64_t i, int sb, uint32_t v) {
+    if (sb == 1) {
+        out[i] = (uint8_t)v;
+    } else {
+        out[2 * i] = (uint8_t)v;
+        out[2 * i + 1] = (uint8_t)(v >> 8);
+    }
+}
+
+// mirrors finalize_models_kernel
+void build_header(uint32_t K, const uint32_t* c, const uint32_t* cum, uint32_t total, uint32_t lut_cap,
+                  ModelHdr& h, std::vector<LutEntry>& lut) {
+    bool pow2;
+    make_div_params(total, &h.div, &pow2);
+    uint32_t bad = 0;
+    for (uint32_t i = 0; i < K; i++) {
+        uint64_t end = (uint64_t)cum[i] + c[i];
+        if (end > total) bad |= 1;
+        if (i + 1 < K && (uint64_t)cum[i + 1] != end) bad |= 2;
+    }
+    h.flags = (pow2 ? MODEL_POW2 : 0) | ((bad & 1) ? 0 : MODEL_CONSISTENT) | ((bad & 3) ? 0 : MODEL_REGULAR);
+    uint32_t bits = 0;
+    while (bits < 32 && (1ull << bits) < total) bits++;
+    uint32_t lg_cap = 0;
+    while ((1u << (lg_cap + 1)) <= lut_cap) lg_cap++;
+    h.wshift = bits > lg_cap ? bits - lg_cap : 0;
+    h.nb = (uint32_t)((((uint64_t)total - 1) >> h.wshift) + 1);
+    h.lut_scale = (float)total / (float)(1ull << h.wshift);
+    h.K = K;
+    lut.clear();
+    if (!(h.flags & MODEL_REGULAR)) return;
+    lut.resize(h.nb);
+    for (uint32_t b = 0; b < h.nb; b++) {
+        uint64_t v0 = (uint64_t)b << h.wshift;
+        uint32_t left = 0, right = K - 1;
+        while (left < right) {
+            uint32_t mid = (left + right) >> 1;
+            if ((uint64_t)cum[mid + 1] <= v0) left = mid + 1; else right = mid;
+        }
+        uint32_t A = left, B = A + 1;
+        while (B < K && c[B] == 0) B++;
+        LutEntry e;
+        e.cumA = cum[A];
+        e.cumB = cum[A] + c[A];
+        e.cumC = e.cumB + (B < K ? c[B] : 0);
+        e.syms = A | ((B & 0xFFFFu) << 16);
+        lut[b] = e;
+    }
+}
+
+}  // namespace
+
+extern "C" int64_t hc_encode(const uint8_t* syms, uint64_t n, int sym_bytes, uint32_t K, const uint32_t* c,
+                             const uint32_t* cum, uint32_t total, uint8_t* out, uint32_t cap, int checked,
+                             uint32_t* status) {
+    DivParams div;
+    bool pow2;
+    if (!make_div_params(total, &div, &pow2)) return -1;
+    uint64_t lo = 0, rg = ~0ull;
+    uint32_t err = 0;
+    HostStore hs{out};
+    EncSink<HostStore> sink(hs, cap);
+    for (uint64_t i = 0; i < n; i++) {
+        uint32_t s = load_sym(syms, i, sym_bytes);
+        if (s >= K) {
+            if (!err) err = ST_SYMBOL_RANGE;
+            s = 0;
+        }
+        if (pow2) {
+            if (checked) update_symbol<true, true>(lo, rg, cum[s], c[s], div, sink, err);
+            else update_symbol<true, false>(lo, rg, cum[s], c[s], div, sink, err);
+        } else {
+            if (checked) update_symbol<false, true>(lo, rg, cum[s], c[s], div, sink, err);
+            else update_symbol<false, false>(lo, rg, cum[s], c[s], div, sink, err);
+        }
+    }
+    uint32_t len = sink.finish(lo);
+    if (!err && sink.overflow) err = ST_OUT_CAPACITY;
+    *status = err;
+    return (int64_t)len;
+}
+
+// stream/off0/off1: chunk bytes are stream[off0..off1); stream_len bounds the reads.
+extern "C" int64_t hc_decode(const uint8_t* stream, uint64_t off0, uint64_t off1, uint64_t stream_len,
+                             uint64_t n_syms, int sym_bytes, uint32_t K, const uint32_t* c, const uint32_t* cum,
+                             uint32_t total, uint8_t* out, int use_lut, int checked, uint32_t lut_cap,
+                             uint32_t* status, uint64_t* n_fallback) {
+    ModelHdr h;
+    std::vector<LutEntry> lut;
+    if (total == 0) return -1;
+    build_header(K, c, cum, total, lut_cap, h, lut);
+    const bool pow2 = (h.flags & MODEL_POW2) != 0;
+    const bool lut_ok = use_lut && (h.flags & MODEL_REGULAR);
+    const float max_bucket = (float)(h.nb ? h.nb - 1 : 0);
+    // emulate an unaligned chunk start inside an aligned buffer
+    uint64_t al = off0 & ~3ull;
+    HostFetch hf{stream + al, 0, stream + stream_len};
+    DecSink<HostFetch> sink(hf);
+    sink.prime((uint32_t)(off0 & 3u));
+    uint64_t lo = 0, rg = ~0ull, fallbacks = 0;
+    uint32_t err = 0;
+    for (uint64_t i = 0; i < n_syms; i++) {
+        uint64_t rpt = pow2 ? range_par_total<true>(rg, h.div) : range_par_total<false>(rg, h.div);
+        uint64_t d = sink.data - lo;
+        uint32_t sym = 0;
+        uint64_t P = 0, rgn = 0;
+        bool ok = false;
+        if (lut_ok) {
+            uint32_t b = lut_bucket(d, rg, h.lut_scale, max_bucket);
+            ok = lut_resolve(lut[b], d, rpt, sym, P, rgn);
+        }
+        if (!ok) {
+            fallbacks++;
+            sym = find_index_exact(d, rpt, K, [&](uint32_t j) { return cum[j]; });
+            P = rpt * (uint64_t)cum[sym];
+            rgn = rpt * (uint64_t)c[sym];
+        }
+        uint64_t nlo = lo + P;
+        if (checked && nlo < lo) {
+            if (!err) err = ST_LOWER_OVERFLOW;
+            nlo = 0;
+            rgn = ~0ull;
+        }
+        lo = nlo;
+        rg = rgn;
+        if (checked) renorm<true>(lo, rg, sink, err);
+        else renorm<false>(lo, rg, sink, err);
+        store_sym(out, i, sym_bytes, sym);
+    }
+    if (!err && (uint64_t)sink.used > off1 - off0) err = ST_TRUNCATED;
+    *status = err;
+    if (n_fallback) *n_fallback = fallbacks;
+    return (int64_t)sink.used;
+}
+
+// exhaustive check helper for the reciprocal: returns the number of mismatches
+extern "C" uint64_t hc_check_division(const uint64_t* ranges, uint64_t n, uint32_t total) {
+    DivParams div;
+    bool pow2;
+    if (!make_div_params(total, &div, &pow2)) return ~0ull;
+    uint64_t bad = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        uint64_t q = pow2 ? range_par_total<true>(ranges[i], div) : range_par_total<false>(ranges[i], div);
+        if (q != ranges[i] / total) bad++;
+    }
+    return bad;
+}

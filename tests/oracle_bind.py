@@ -1,0 +1,191 @@
+"""ctypes binding of the CPU oracle (oracle/librc_oracle.so) -- test infrastructure.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference
+legs use this module; the product package never imports it.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_LIB = os.path.join(ORACLE_DIR, "librc_oracle.so")
+
+_vp = ctypes.c_void_p
+_u64 = ctypes.c_uint64
+_u32 = ctypes.c_uint32
+_i64 = ctypes.c_int64
+_ci = ctypes.c_int
+
+RCO_ERR = {
+    -1: "LOWER_OVERFLOW", -2: "UPPER_OVERFLOW", -3: "ZERO_TOTAL", -4: "ZERO_FREQ",
+    -5: "CAPACITY", -6: "TRUNCATED", -7: "SYMBOL_RANGE",
+}
+
+
+def build_oracle(force=False):
+    src = [os.path.join(ORACLE_DIR, f) for f in ("rc_oracle.c", "rc_oracle.h", "Makefile")]
+    if force or not os.path.exists(ORACLE_LIB) or any(
+            os.path.getmtime(s) > os.path.getmtime(ORACLE_LIB) for s in src):
+        subprocess.run(["make", "-C", ORACLE_DIR, "-B"], check=True, capture_output=True)
+    return ORACLE_LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build_oracle()
+        L = ctypes.CDLL(ORACLE_LIB)
+        L.rco_encode.restype = _i64
+        L.rco_encode.argtypes = [_vp, _u64, _ci, _u32, _vp, _vp, _u32, _vp, _u64]
+        L.rco_decode.restype = _i64
+        L.rco_decode.argtypes = [_vp, _u64, _u64, _ci, _u32, _vp, _vp, _u32, _vp]
+        L.rco_histogram.restype = None
+        L.rco_histogram.argtypes = [_vp, _u64, _ci, _u32, _vp]
+        L.rco_calc_cum.restype = _u32
+        L.rco_calc_cum.argtypes = [_vp, _u32, _vp]
+        L.rco_normalise.restype = _ci
+        L.rco_normalise.argtypes = [_vp, _u32, _vp]
+        L.rco_encode_chunks.restype = _ci
+        L.rco_encode_chunks.argtypes = [_vp, _u64, _ci, _u64, _u32, _vp, _vp, _vp, _ci, _vp, _u64, _vp, _ci]
+        L.rco_decode_chunks.restype = _ci
+        L.rco_decode_chunks.argtypes = [_vp, _vp, _u64, _ci, _u64, _u32, _vp, _vp, _vp, _ci, _vp, _vp, _ci]
+        L.rco_generate.restype = None
+        L.rco_generate.argtypes = [_vp, _u64, _u64, _ci, _u32, _u64, _vp, _u32, _u64, _ci]
+        L.rco_hardware_threads.restype = _ci
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(_vp)
+
+
+def hardware_threads():
+    return int(lib().rco_hardware_threads())
+
+
+def histogram(syms, K):
+    syms = np.ascontiguousarray(syms)
+    counts = np.zeros(K, dtype=np.uint64)
+    lib().rco_histogram(_p(syms), syms.size, syms.dtype.itemsize, K, _p(counts))
+    return counts
+
+
+def normalise(counts):
+    counts = np.ascontiguousarray(counts, dtype=np.uint64)
+    c = np.zeros(counts.size, dtype=np.uint32)
+    sh = lib().rco_normalise(_p(counts), counts.size, _p(c))
+    return c, sh
+
+
+def calc_cum(c):
+    c = np.ascontiguousarray(c, dtype=np.uint32)
+    cum = np.zeros(c.size, dtype=np.uint32)
+    total = lib().rco_calc_cum(_p(c), c.size, _p(cum))
+    return cum, int(total)
+
+
+def model_from_symbols(syms, K):
+    """histogram -> (identity or shift) normalise -> calc_cum; returns (c, cum, total)."""
+    c, _ = normalise(histogram(syms, K))
+    cum, total = calc_cum(c)
+    return c, cum, total
+
+
+def encode(syms, c, cum, total, cap=None):
+    """Whole Encoder run; returns bytes, or raises ValueError(name) on an oracle error."""
+    syms = np.ascontiguousarray(syms)
+    c = np.ascontiguousarray(c, dtype=np.uint32)
+    cum = np.ascontiguousarray(cum, dtype=np.uint32)
+    if cap is None:
+        cap = 16 * syms.size + 64
+    out = np.zeros(cap, dtype=np.uint8)
+    n = lib().rco_encode(_p(syms), syms.size, syms.dtype.itemsize, c.size, _p(c), _p(cum), total, _p(out), cap)
+    if n < 0:
+        raise ValueError(RCO_ERR.get(n, str(n)))
+    return out[:n].tobytes()
+
+
+def decode(code, n_syms, c, cum, total, sym_bytes=1):
+    code = np.frombuffer(bytes(code), dtype=np.uint8) if not isinstance(code, np.ndarray) else code
+    code = np.ascontiguousarray(code, dtype=np.uint8)
+    c = np.ascontiguousarray(c, dtype=np.uint32)
+    cum = np.ascontiguousarray(cum, dtype=np.uint32)
+    out = np.zeros(n_syms, dtype=np.uint8 if sym_bytes == 1 else np.uint16)
+    used = lib().rco_decode(_p(code), code.size, n_syms, sym_bytes, c.size, _p(c), _p(cum), total, _p(out))
+    if used < 0:
+        raise ValueError(RCO_ERR.get(used, str(used)))
+    return out, int(used)
+
+
+def encode_chunks(syms, chunk_syms, c, cum, total, threads=None, pitch=None):
+    """Chunked multi-thread encode; returns (stream bytes array, offsets uint64[n_chunks+1])."""
+    syms = np.ascontiguousarray(syms)
+    c = np.ascontiguousarray(c, dtype=np.uint32)
+    cum = np.ascontiguousarray(cum, dtype=np.uint32)
+    total = np.ascontiguousarray(np.atleast_1d(total), dtype=np.uint32)
+    per_chunk = 1 if c.ndim == 2 else 0
+    K = c.shape[-1]
+    n = syms.size
+    n_chunks = (n + chunk_syms - 1) // chunk_syms
+    if pitch is None:
+        pitch = 4 * chunk_syms * syms.dtype.itemsize + 64
+    out = np.zeros(n_chunks * pitch, dtype=np.uint8)
+    lens = np.zeros(n_chunks, dtype=np.int64)
+    threads = threads or hardware_threads()
+    bad = lib().rco_encode_chunks(_p(syms), n, syms.dtype.itemsize, chunk_syms, K, _p(c), _p(cum), _p(total),
+                                  per_chunk, _p(out), pitch, _p(lens), threads)
+    if bad:
+        first = int(np.argmax(lens < 0))
+        raise ValueError(f"{bad} chunks failed; chunk {first}: {RCO_ERR.get(int(lens[first]), lens[first])}")
+    offsets = np.zeros(n_chunks + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum(lens)
+    stream = np.empty(int(offsets[-1]), dtype=np.uint8)
+    for i in range(n_chunks):
+        stream[int(offsets[i]):int(offsets[i + 1])] = out[i * pitch:i * pitch + int(lens[i])]
+    return stream, offsets
+
+
+def decode_chunks(stream, offsets, n_syms, chunk_syms, c, cum, total, sym_bytes=1, threads=None):
+    stream = np.ascontiguousarray(stream, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    c = np.ascontiguousarray(c, dtype=np.uint32)
+    cum = np.ascontiguousarray(cum, dtype=np.uint32)
+    total = np.ascontiguousarray(np.atleast_1d(total), dtype=np.uint32)
+    per_chunk = 1 if c.ndim == 2 else 0
+    K = c.shape[-1]
+    n_chunks = (n_syms + chunk_syms - 1) // chunk_syms
+    out = np.zeros(n_syms, dtype=np.uint8 if sym_bytes == 1 else np.uint16)
+    used = np.zeros(n_chunks, dtype=np.int64)
+    threads = threads or hardware_threads()
+    bad = lib().rco_decode_chunks(_p(stream), _p(offsets), n_syms, sym_bytes, chunk_syms, K, _p(c), _p(cum),
+                                  _p(total), per_chunk, _p(out), _p(used), threads)
+    if bad:
+        first = int(np.argmax(used < 0))
+        raise ValueError(f"{bad} chunks failed; chunk {first}: {RCO_ERR.get(int(used[first]), used[first])}")
+    return out, used
+
+
+def generate(n, K, seed, thresholds, sym_bytes=1, chunk_syms=0, first=0, threads=None):
+    thr = np.ascontiguousarray(thresholds, dtype=np.uint32)
+    if thr.ndim == 1:
+        thr = thr[None, :]
+    out = np.zeros(n, dtype=np.uint8 if sym_bytes == 1 else np.uint16)
+    lib().rco_generate(_p(out), first, n, sym_bytes, K, seed, _p(thr), thr.shape[0], chunk_syms or 1,
+                       threads or hardware_threads())
+    return out
+
+
+def zipf_thresholds(K, s):
+    """Same formula as range_coder_rust_b200.api.zipf_thresholds (kept separate on purpose:
+    the oracle side must not import the product)."""
+    w = np.arange(1, K + 1, dtype=np.float64) ** (-float(s))
+    cdf = np.cumsum(w) / np.sum(w)
+    thr = np.floor(cdf[: K - 1] * 4294967296.0)
+    return np.minimum(thr, 4294967295.0).astype(np.uint32)
