@@ -5,6 +5,7 @@ Names follow the reference's domain: symbols, chunks, frequency tables
 (`c_freq`, `cum_freq`, `total_freq` -- src/pmodel.rs:4-13), code streams.
 """
 import ctypes
+import weakref
 
 import numpy as np
 import torch
@@ -32,11 +33,13 @@ class Model:
         h = ctypes.c_void_p()
         ctx._check(ctx.lib.rcb_model_create(ctx.h, self.K, self.n_models, ctypes.byref(h)), "rcb_model_create")
         self.h = h
+        ctx._models.add(self)
 
     def close(self):
-        if getattr(self, "h", None):
+        # a model must be destroyed before its context (the C side keeps a ctx pointer)
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
             self.ctx.lib.rcb_model_destroy(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:
@@ -63,6 +66,8 @@ class Context:
 
     def __init__(self, device=0, stream=None):
         self.lib = _lib.load()
+        self.h = None
+        self._models = weakref.WeakSet()
         if not torch.cuda.is_available():
             raise RcbError(_lib.RCB_ERR_NO_DEVICE, "Context")
         self.device = torch.device("cuda", device)
@@ -87,6 +92,8 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
+            for m in list(self._models):
+                m.close()
             self.lib.rcb_ctx_destroy(self.h)
             self.h = None
 
@@ -125,22 +132,25 @@ class Context:
         raise TypeError("symbols must be uint8 or (u)int16 tensors")
 
     # --------------------------------------------------------------- model
-    def histogram(self, syms, K, chunk_syms=0):
+    def histogram(self, syms, K, chunk_syms=0, out=None):
         """FreqTable::add_alphabet_freq loop (examples/sample_impl.rs:58-60,78-80).
         chunk_syms == 0 -> int64[K]; else int32[n_chunks][K] (bit patterns of u64/u32)."""
         n = syms.numel()
         sb = self._sym_bytes(syms)
-        if chunk_syms == 0:
-            counts = torch.empty(K, dtype=torch.int64, device=self.device)
-        else:
-            n_chunks = (n + chunk_syms - 1) // chunk_syms
-            counts = torch.empty((n_chunks, K), dtype=torch.int32, device=self.device)
+        counts = out
+        if counts is None:
+            if chunk_syms == 0:
+                counts = torch.empty(K, dtype=torch.int64, device=self.device)
+            else:
+                n_chunks = (n + chunk_syms - 1) // chunk_syms
+                counts = torch.empty((n_chunks, K), dtype=torch.int32, device=self.device)
         self._check(self.lib.rcb_histogram(self.h, _ptr(syms), n, sb, K, chunk_syms, _ptr(counts)),
                     "rcb_histogram")
         return counts
 
-    def model_from_counts(self, counts, K=None):
-        """FreqTable::calc_cum (examples/sample_impl.rs:61-69) on device counts."""
+    def model_from_counts(self, counts, K=None, model=None):
+        """FreqTable::calc_cum (examples/sample_impl.rs:61-69) on device counts.
+        `model` rebuilds an existing Model of the same shape in place."""
         if counts.dim() == 1:
             n_models, k = 1, counts.shape[0]
         else:
@@ -149,7 +159,8 @@ class Context:
         assert k == K
         cb = 8 if counts.dtype == torch.int64 else 4
         assert counts.dtype in (torch.int64, torch.int32)
-        m = Model(self, K, n_models)
+        m = model if model is not None else Model(self, K, n_models)
+        assert m.K == K and m.n_models == n_models
         self._check(self.lib.rcb_model_from_counts(self.h, m.h, _ptr(counts.contiguous()), cb),
                     "rcb_model_from_counts")
         return m
