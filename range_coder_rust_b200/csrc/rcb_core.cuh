@@ -9,11 +9,14 @@
 //   src/decoder.rs:31-54       shift_left_buffer / decode
 //   examples/sample_impl.rs:27-45 find_index (rfreq + binary search)
 //
-// Design (not a port): the byte loops are replaced by a closed form on the hot
-// path (n1 = clz(lower ^ upper) / 8 whole bytes at once) with the literal loops
-// kept as a rare slow path, range/total is a shift or a multiply-high
-// reciprocal, and the decoder never divides: it classifies `data - lower` in
-// the product domain (cum * rpt <= d  <=>  cum <= d / rpt for integers).
+// Design (not a port): one coder state per GPU lane means the per-symbol
+// dependency chain IS the run time, so the hot path is written as straight-line
+// 32-bit code: the byte loops become a closed form (n1 = clz(lower ^ upper) / 8
+// whole bytes at once, literal loops kept as a rare slow path), range/total is
+// a shift or a multiply-high reciprocal, byte emission and input refill are
+// funnel shifts with predicated stores/loads instead of branches, and the
+// decoder never divides: it classifies `data - lower` in the product domain
+// (cum * rpt <= d  <=>  cum <= d / rpt for integers).
 //
 // Everything here is __host__ __device__ so the same code can be compiled by
 // g++ into a test-only harness (tests/hostcore) and compared with the oracle
@@ -23,19 +26,12 @@
 
 #if defined(__CUDACC__)
 #define RCB_HD __host__ __device__ __forceinline__
-#define RCB_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define RCB_HD inline
-#define RCB_HD_NOINLINE
 #endif
 
-#if defined(__CUDA_ARCH__)
 #define RCB_LIKELY(x) (__builtin_expect(!!(x), 1))
 #define RCB_UNLIKELY(x) (__builtin_expect(!!(x), 0))
-#else
-#define RCB_LIKELY(x) (__builtin_expect(!!(x), 1))
-#define RCB_UNLIKELY(x) (__builtin_expect(!!(x), 0))
-#endif
 
 namespace rcb {
 
@@ -69,12 +65,23 @@ RCB_HD uint32_t clz32(uint32_t x) {
 #endif
 }
 
-// top `sh` bits (sh in 0..31) of x moved to the bottom; 0 when sh == 0
-RCB_HD uint32_t top_bits(uint32_t x, uint32_t sh) {
+// high word of (hi:lo) << sh, sh in 0..31
+RCB_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t sh) {
 #if defined(__CUDA_ARCH__)
-    return __funnelshift_l(x, 0u, sh);
+    return __funnelshift_l(lo, hi, sh);
 #else
-    return sh ? (x >> (32u - sh)) : 0u;
+    sh &= 31u;
+    return sh ? ((hi << sh) | (lo >> (32u - sh))) : hi;
+#endif
+}
+
+// low word of (hi:lo) >> sh, sh in 0..31
+RCB_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    sh &= 31u;
+    return sh ? ((lo >> sh) | (hi << (32u - sh))) : lo;
 #endif
 }
 
@@ -201,101 +208,102 @@ RCB_HD void update_symbol(uint64_t& lo, uint64_t& rg, uint32_t cum, uint32_t c,
 }
 
 // ---------------------------------------------------------------------------
-// Encoder byte sink: big-endian bit accumulator, flushed as 32-bit words.
-// Store::word(pos, w) writes 4 bytes at byte offset pos (pos % 4 == 0),
-// Store::byte(pos, b) one byte (tail only).
+// Encoder byte sink.  `pend` holds the nb (< 32, multiple of 8) pending bits in
+// its low end (bits above nb are stale and never read).  New bytes enter with
+// one funnel shift; when 32 or more bits are pending the oldest 32 are stored
+// as one word.  Store::word(pos, w) writes 4 bytes at byte offset pos
+// (pos % 4 == 0, memory order = emission order), Store::byte(pos, b) one byte.
+// pos keeps counting past `cap`, so the final length is the needed capacity.
 // ---------------------------------------------------------------------------
 template <class Store>
 struct EncSink {
-    uint64_t acc = 0;   // pending bytes, most recent in the low bits
-    uint32_t nb = 0;    // pending bits (multiple of 8, < 32 between symbols)
-    uint32_t pos = 0;   // bytes already stored
-    uint32_t cap;       // capacity of the row in bytes
-    uint32_t overflow = 0;
+    uint32_t pend = 0;
+    uint32_t nb = 0;
+    uint32_t pos = 0;
+    uint32_t cap;
     Store st;
 
     RCB_HD EncSink(Store s, uint32_t cap_) : cap(cap_), st(s) {}
 
-    RCB_HD void flush_word() {
-        uint32_t w = (uint32_t)(acc >> (nb - 32u));
-        if (RCB_LIKELY(pos + 4u <= cap))
-            st.word(pos, bswap32(w));
-        else
-            overflow = 1;
-        pos += 4u;
-        nb -= 32u;
+    RCB_HD void push(uint32_t over, uint32_t merged, uint32_t sh) {
+        // (over:merged) is the 64-bit value (old pend << sh) | new bits
+        pend = merged;
+        nb += sh;
+        if (nb >= 32u) {
+            uint32_t w = funnel_r(merged, over, nb);  // bits [nb-32, nb); nb & 31 == nb - 32
+            if (pos + 4u <= cap) st.word(pos, bswap32(w));
+            pos += 4u;
+            nb -= 32u;
+        }
     }
     RCB_HD void put(uint32_t lo_hi, uint32_t sh) {
-        acc = (acc << sh) | (uint64_t)top_bits(lo_hi, sh);
-        nb += sh;
-        if (nb >= 32u) flush_word();
+        push(funnel_l(pend, 0u, sh), funnel_l(lo_hi, pend, sh), sh);
     }
-    RCB_HD void put_byte(uint32_t b) {
-        acc = (acc << 8) | (uint64_t)(b & 0xFFu);
-        nb += 8u;
-        if (nb >= 32u) flush_word();
-    }
-    // src/encoder.rs:40-46: 8 x left_shift, then drain the accumulator.
+    RCB_HD void put_byte(uint32_t b) { push(pend >> 24, (pend << 8) | (b & 0xFFu), 8u); }
+    // src/encoder.rs:40-46: 8 x left_shift, then drain the pending bytes.
     RCB_HD uint32_t finish(uint64_t lo) {
         for (int i = 0; i < 8; i++) {
             put_byte((uint32_t)(lo >> 56));
             lo <<= 8;
         }
         while (nb) {
-            uint32_t b = (uint32_t)(acc >> (nb - 8u)) & 0xFFu;
-            if (pos < cap)
-                st.byte(pos, b);
-            else
-                overflow = 1;
+            uint32_t b = (pend >> (nb - 8u)) & 0xFFu;
+            if (pos < cap) st.byte(pos, b);
             pos += 1u;
             nb -= 8u;
         }
-        return pos;  // code length (the needed capacity when overflow is set)
+        return pos;
     }
+    RCB_HD bool overflowed() const { return pos > cap; }
 };
 
 // ---------------------------------------------------------------------------
-// Decoder input window (src/decoder.rs:9,31-35): `data` is aligned with
-// lower_bound; `w` holds the following bytes left-aligned, refilled 32 bits at
-// a time by Fetch::next_be32() (big-endian word, zeros past the end).
+// Decoder input window (src/decoder.rs:9,31-35).  (dh:dl) is `data`, aligned
+// with lower_bound; (wh:wl) holds the following bytes left-aligned with `cnt`
+// valid bits, refilled 32 bits at a time from Fetch::next_be32() (a big-endian
+// word of the stream).  Invariant between symbols: cnt >= 32.
 // ---------------------------------------------------------------------------
 template <class Fetch>
 struct DecSink {
-    uint64_t data = 0;
-    uint64_t w = 0;      // upcoming bytes, next byte in the top 8 bits
-    uint32_t cnt = 0;    // valid bits in w
-    uint32_t used = 0;   // bytes shifted into data so far
+    uint32_t dh = 0, dl = 0;
+    uint32_t wh = 0, wl = 0;
+    uint32_t cnt = 0;
     Fetch f;
 
     RCB_HD explicit DecSink(Fetch fetch) : f(fetch) {}
 
+    RCB_HD uint64_t data() const { return ((uint64_t)dh << 32) | dl; }
+
     RCB_HD void refill() {
-        // cnt < 32 here
-        w |= (uint64_t)f.next_be32() << (32u - cnt);
-        cnt += 32u;
+        if (cnt < 32u) {  // then wl == 0
+            uint32_t be = f.next_be32();
+            wl = funnel_r(0u, be, cnt);  // low word of (be:0) >> cnt
+            wh |= be >> cnt;
+            cnt += 32u;
+        }
     }
-    // Decoder::new: data = first 8 bytes big-endian (decoder.rs:21)
+    // Decoder::new: data = first 8 bytes big-endian (decoder.rs:21).  The first
+    // fetched word holds skip_bytes bytes that precede the chunk.
     RCB_HD void prime(uint32_t skip_bytes) {
-        // first fetched word may contain skip_bytes leading bytes before the chunk
         uint32_t first = f.next_be32();
-        w = (uint64_t)first << (32u + 8u * skip_bytes);
+        wh = skip_bytes ? (first << (8u * skip_bytes)) : first;
+        wl = 0;
         cnt = 32u - 8u * skip_bytes;
+        refill();
         for (int i = 0; i < 8; i++) put_byte(0);
     }
     RCB_HD void put(uint32_t /*lo_hi*/, uint32_t sh) {
-        data = (data << sh) | (uint64_t)top_bits((uint32_t)(w >> 32), sh);
-        w <<= sh;
+        dh = funnel_l(dl, dh, sh);
+        dl = funnel_l(wh, dl, sh);
+        wh = funnel_l(wl, wh, sh);
+        wl <<= sh;
         cnt -= sh;
-        used += sh >> 3;
-        if (cnt < 32u) refill();
+        refill();
     }
-    RCB_HD void put_byte(uint32_t /*b*/) {
-        if (cnt < 8u) refill();
-        data = (data << 8) | (w >> 56);
-        w <<= 8;
-        cnt -= 8u;
-        used += 1u;
-        if (cnt < 32u) refill();
+    RCB_HD void put_byte(uint32_t /*b*/) { put(0u, 8u); }
+    // bytes shifted into data so far = fetched - skipped - still buffered
+    RCB_HD uint32_t used(uint32_t words_fetched, uint32_t skip_bytes) const {
+        return 4u * words_fetched - skip_bytes - (cnt >> 3);
     }
 };
 
@@ -320,17 +328,17 @@ RCB_HD uint32_t find_index_exact(uint64_t d, uint64_t rpt, uint32_t K, CumAt cum
     return left;
 }
 
-
 // ---------------------------------------------------------------------------
 // Table-driven lookup for a REGULAR table (cum[i+1] == cum[i] + c[i]).
 // The rfreq axis [0,total) is cut into nb buckets of width 2^wshift.  Entry b
 // describes the symbol A whose interval contains b<<wshift and the next
 // non-zero symbol B:  [cumA,cumB) -> A, [cumB,cumC) -> B.
-// The bucket is chosen from a float estimate of d/rpt ~= d*total/range biased
-// low (rpt = floor(range/total) only makes the true quotient larger), then the
-// choice is verified exactly in the product domain; any miss (estimate off,
-// more than one boundary in the bucket, clamp-to-K-1 case, garbage stream)
-// falls back to find_index_exact, so the result never depends on float error.
+// The bucket comes from a float estimate of d/rpt ~= d*total/range taken from
+// the high words only and biased low (range >= 2^48, so each high word carries
+// >= 16 significant bits: the estimate is off by < 1/4 bucket), then the choice
+// is verified exactly in the product domain; any miss (estimate off, more than
+// one boundary in the bucket, clamp-to-K-1 case, garbage stream) falls back to
+// find_index_exact, so the result never depends on float rounding.
 // ---------------------------------------------------------------------------
 struct LutEntry {
     uint32_t cumA, cumB, cumC;
@@ -350,10 +358,6 @@ struct ModelHdr {
 
 enum : uint32_t { MODEL_POW2 = 1, MODEL_CONSISTENT = 2, MODEL_REGULAR = 4 };
 
-RCB_HD float u64_to_float(uint64_t x) {
-    return (float)(uint32_t)(x >> 32) * 4294967296.0f + (float)(uint32_t)x;
-}
-
 RCB_HD float fast_rcp(float x) {
 #if defined(__CUDA_ARCH__)
     float r;
@@ -365,9 +369,11 @@ RCB_HD float fast_rcp(float x) {
 }
 
 RCB_HD uint32_t lut_bucket(uint64_t d, uint64_t rg, float scale, float max_bucket) {
-    float bf = u64_to_float(d) * fast_rcp(u64_to_float(rg)) * scale - (1.0f / 128.0f);
+    float fd = (float)(uint32_t)(d >> 32);
+    float fr = (float)(uint32_t)(rg >> 32);  // >= 2^16 for a live coder state
+    float bf = fd * (fast_rcp(fr) * scale) - (5.0f / 64.0f);
     bf = bf < 0.0f ? 0.0f : bf;
-    bf = bf > max_bucket ? max_bucket : bf;
+    bf = bf > max_bucket ? max_bucket : bf;  // also tames inf/NaN from a dead state
     return (uint32_t)bf;
 }
 

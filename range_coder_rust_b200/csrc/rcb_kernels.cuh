@@ -19,18 +19,12 @@
 #include <stdint.h>
 
 #include "rcb_core.cuh"
+#include "rcb_encode.cuh"
+#include "rcb_decode.cuh"
 
 namespace rcb {
 
 // ------------------------------------------------------------------ helpers
-__device__ __forceinline__ uint4 ldg_stream_v4(const uint4* p) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
-    return r;
-}
-
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, uint32_t lane) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -311,117 +305,6 @@ __global__ void __launch_bounds__(256) finalize_models_kernel(const uint2* __res
     }
 }
 
-// ================================================================= K3 encode
-struct EncodeArgs {
-    const void* syms;
-    uint64_t n_syms;
-    uint64_t chunk_syms;
-    uint64_t n_chunks;
-    const uint2* tabs;      // [n_models][K]
-    const ModelHdr* hdrs;   // [n_models]
-    uint32_t K;
-    uint32_t per_chunk;     // 1: model index = chunk
-    uint8_t* staging;       // [n_chunks][pitch]
-    uint64_t pitch;
-    uint32_t* lens;         // [n_chunks]
-    uint32_t* status;       // [n_chunks]
-};
-
-struct RowStore {
-    uint8_t* row;
-    __device__ __forceinline__ void word(uint32_t pos, uint32_t w) const {
-        *reinterpret_cast<uint32_t*>(row + pos) = w;
-    }
-    __device__ __forceinline__ void byte(uint32_t pos, uint32_t b) const { row[pos] = (uint8_t)b; }
-};
-
-// SHARED: one table for all chunks, staged in shared memory.
-// !SHARED: one table per chunk, read through L1/L2 from global memory.
-template <typename SYM, bool SHARED, bool POW2, bool CHECKED, bool RANGECHK>
-__global__ void __launch_bounds__(256) encode_kernel(EncodeArgs a) {
-    extern __shared__ __align__(16) uint8_t s_raw[];
-    uint2* s_tab = reinterpret_cast<uint2*>(s_raw);
-    __shared__ ModelHdr s_hdr;
-    if (SHARED) {
-        for (uint32_t i = threadIdx.x; i < a.K; i += blockDim.x) s_tab[i] = a.tabs[i];
-        if (threadIdx.x == 0) s_hdr = a.hdrs[0];
-        __syncthreads();
-    }
-    const uint64_t chunk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (chunk >= a.n_chunks) return;
-    const uint64_t first = chunk * a.chunk_syms;
-    const uint64_t cnt = (a.n_syms - first < a.chunk_syms) ? (a.n_syms - first) : a.chunk_syms;
-    const SYM* src = reinterpret_cast<const SYM*>(a.syms) + first;
-
-    const uint2* tab = SHARED ? s_tab : a.tabs + chunk * a.K;
-    DivParams div;
-    bool pow2 = POW2;
-    if (SHARED) {
-        div = s_hdr.div;
-    } else {
-        ModelHdr h = a.hdrs[chunk];
-        div = h.div;
-        pow2 = (h.flags & MODEL_POW2) != 0;
-    }
-    const uint32_t K = a.K;
-
-    uint64_t lo = 0, rg = ~0ull;  // src/range_coder.rs:13-20
-    uint32_t err = 0;
-    RowStore rs{a.staging + chunk * a.pitch};
-    EncSink<RowStore> sink(rs, (uint32_t)a.pitch);
-
-    auto step = [&](uint32_t s) {
-        if (RANGECHK && s >= K) {
-            if (!err) err = ST_SYMBOL_RANGE;
-            s = 0;
-        }
-        uint2 e = tab[s];
-        if (SHARED) {
-            update_symbol<POW2, CHECKED>(lo, rg, e.x, e.y, div, sink, err);
-        } else {
-            if (pow2)
-                update_symbol<true, CHECKED>(lo, rg, e.x, e.y, div, sink, err);
-            else
-                update_symbol<false, CHECKED>(lo, rg, e.x, e.y, div, sink, err);
-        }
-    };
-
-    constexpr uint32_t PER = 16 / sizeof(SYM);
-    uint64_t done = 0;
-    if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
-        const uint4* v = reinterpret_cast<const uint4*>(src);
-        const uint64_t nvec = cnt / PER;
-        uint4 cur = nvec ? ldg_stream_v4(v) : make_uint4(0, 0, 0, 0);
-        for (uint64_t i = 0; i < nvec; i++) {
-            // one vector of lookahead hides the global-load latency behind 16 symbols of work
-            uint4 nxt = (i + 1 < nvec) ? ldg_stream_v4(v + i + 1) : make_uint4(0, 0, 0, 0);
-#pragma unroll 1
-            for (int j = 0; j < 4; j++) {
-                const uint32_t w = cur.x;
-                cur.x = cur.y;
-                cur.y = cur.z;
-                cur.z = cur.w;
-                if (sizeof(SYM) == 1) {
-#pragma unroll
-                    for (int b = 0; b < 4; b++) step((w >> (8 * b)) & 0xFFu);
-                } else {
-#pragma unroll
-                    for (int b = 0; b < 2; b++) step((w >> (16 * b)) & 0xFFFFu);
-                }
-            }
-            cur = nxt;
-        }
-        done = nvec * PER;
-    }
-#pragma unroll 1
-    for (uint64_t i = done; i < cnt; i++) step((uint32_t)src[i]);
-
-    uint32_t len = sink.finish(lo);  // src/encoder.rs:40-46
-    if (!err && sink.overflow) err = ST_OUT_CAPACITY;
-    a.lens[chunk] = len;
-    a.status[chunk] = err;
-}
-
 // ============================================================ K4 compaction
 // Exclusive scan of the chunk lengths into u64 offsets, plus an error summary:
 // summary[0] = number of chunks with status != 0, [1] = first such chunk,
@@ -538,135 +421,6 @@ __global__ void __launch_bounds__(256) gather_kernel(const uint8_t* __restrict__
         dv[v] = load_unaligned16(row, head + (v << 4));
     const uint64_t tail0 = head + (nvec << 4);
     for (uint64_t i = tail0 + threadIdx.x; i < len; i += blockDim.x) dst[i] = row[i];
-}
-
-// ================================================================= K5 decode
-struct DecodeArgs {
-    const uint8_t* stream;
-    const uint64_t* offsets;  // [n_chunks+1]
-    uint64_t n_syms;
-    uint64_t chunk_syms;
-    uint64_t n_chunks;
-    const uint2* tabs;
-    const ModelHdr* hdrs;
-    const LutEntry* lut;      // shared model only
-    uint32_t K;
-    uint32_t per_chunk;
-    void* out;
-    uint32_t* status;
-};
-
-// Sequential reader of one chunk's bytes: aligned 32-bit loads, one word of
-// lookahead in a register, zeros past `end`.
-struct GlobalFetch {
-    const uint32_t* p;
-    const uint32_t* end;
-    uint32_t nextw;
-    __device__ __forceinline__ void init(const uint8_t* start, const uint8_t* stream_end) {
-        p = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(start) & ~(uintptr_t)3);
-        end = reinterpret_cast<const uint32_t*>((reinterpret_cast<uintptr_t>(stream_end) + 3) & ~(uintptr_t)3);
-        nextw = p < end ? __ldg(p) : 0u;
-    }
-    __device__ __forceinline__ uint32_t next_be32() {
-        uint32_t r = bswap32(nextw);
-        p++;
-        nextw = p < end ? __ldg(p) : 0u;
-        return r;
-    }
-};
-
-template <typename SYM, bool SHARED, bool POW2, bool CHECKED>
-__global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
-    extern __shared__ __align__(16) uint8_t s_raw[];
-    __shared__ ModelHdr s_hdr;
-    // shared layout: LutEntry[nb] | uint2[K]
-    LutEntry* s_lut = reinterpret_cast<LutEntry*>(s_raw);
-    uint2* s_tab = nullptr;
-    if (SHARED) {
-        if (threadIdx.x == 0) s_hdr = a.hdrs[0];
-        __syncthreads();
-        const uint32_t nb = (s_hdr.flags & MODEL_REGULAR) ? s_hdr.nb : 0u;
-        s_tab = reinterpret_cast<uint2*>(s_raw + (size_t)nb * sizeof(LutEntry));
-        const uint4* gl = reinterpret_cast<const uint4*>(a.lut);
-        uint4* sl = reinterpret_cast<uint4*>(s_lut);
-        for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) sl[i] = gl[i];
-        for (uint32_t i = threadIdx.x; i < a.K; i += blockDim.x) s_tab[i] = a.tabs[i];
-        __syncthreads();
-    }
-    const uint64_t chunk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (chunk >= a.n_chunks) return;
-    const uint64_t first = chunk * a.chunk_syms;
-    const uint64_t cnt = (a.n_syms - first < a.chunk_syms) ? (a.n_syms - first) : a.chunk_syms;
-    SYM* dst = reinterpret_cast<SYM*>(a.out) + first;
-
-    const uint2* tab = SHARED ? s_tab : a.tabs + chunk * a.K;
-    ModelHdr hdr = SHARED ? s_hdr : a.hdrs[chunk];
-    const DivParams div = hdr.div;
-    const bool pow2 = SHARED ? POW2 : ((hdr.flags & MODEL_POW2) != 0);
-    const bool use_lut = SHARED && (hdr.flags & MODEL_REGULAR);
-    const float lut_scale = hdr.lut_scale;
-    const float max_bucket = (float)(hdr.nb ? hdr.nb - 1 : 0);
-    const uint32_t K = a.K;
-
-    const uint64_t off0 = a.offsets[chunk], off1 = a.offsets[chunk + 1];
-    const uint8_t* start = a.stream + off0;
-    GlobalFetch gf;
-    gf.init(start, a.stream + a.offsets[a.n_chunks]);
-    DecSink<GlobalFetch> sink(gf);
-    sink.prime((uint32_t)(reinterpret_cast<uintptr_t>(start) & 3u));  // src/decoder.rs:14-23
-
-    uint64_t lo = 0, rg = ~0ull;
-    uint32_t err = 0;
-
-    auto step = [&]() -> uint32_t {
-        uint64_t rpt = pow2 ? range_par_total<true>(rg, div) : range_par_total<false>(rg, div);
-        uint64_t d = sink.data - lo;  // examples/sample_impl.rs:29
-        uint32_t sym;
-        uint64_t P, rgn;
-        bool ok = false;
-        if (use_lut) {
-            uint32_t b = lut_bucket(d, rg, lut_scale, max_bucket);
-            LutEntry e = s_lut[b];
-            ok = lut_resolve(e, d, rpt, sym, P, rgn);
-        }
-        if (!ok) {
-            sym = find_index_exact(d, rpt, K, [&](uint32_t i) { return tab[i].x; });
-            uint2 e = tab[sym];
-            P = rpt * (uint64_t)e.x;
-            rgn = rpt * (uint64_t)e.y;
-        }
-        // param_update with the symbol's (c, cum): src/decoder.rs:42-50
-        uint64_t nlo = lo + P;
-        if (CHECKED && nlo < lo) {
-            if (!err) err = ST_LOWER_OVERFLOW;
-            nlo = 0;
-            rgn = ~0ull;
-        }
-        lo = nlo;
-        rg = rgn;
-        renorm<CHECKED>(lo, rg, sink, err);  // consumes the same number of bytes (:52)
-        return sym;
-    };
-
-    constexpr uint32_t PER = 4 / sizeof(SYM);  // symbols per 32-bit store
-    uint64_t done = 0;
-    if ((reinterpret_cast<uintptr_t>(dst) & 3u) == 0) {
-        uint32_t* dw = reinterpret_cast<uint32_t*>(dst);
-        const uint64_t nw = cnt / PER;
-#pragma unroll 1
-        for (uint64_t i = 0; i < nw; i++) {
-            uint32_t acc = 0;
-#pragma unroll
-            for (uint32_t b = 0; b < PER; b++) acc |= step() << (8 * sizeof(SYM) * b);
-            dw[i] = acc;
-        }
-        done = nw * PER;
-    }
-#pragma unroll 1
-    for (uint64_t i = done; i < cnt; i++) dst[i] = (SYM)step();
-
-    if (!err && (uint64_t)sink.used > off1 - off0) err = ST_TRUNCATED;  // src/decoder.rs:33
-    a.status[chunk] = err;
 }
 
 // Reduce a status array into the same 4-word summary scan_lengths_kernel writes.

@@ -26,7 +26,9 @@ struct HostFetch {
     const uint8_t* base;  // aligned-down start
     uint64_t pos;         // next word offset from base
     const uint8_t* end;
+    uint32_t* calls;
     uint32_t next_be32() {
+        ++*calls;
         uint32_t w = 0;
         for (int i = 0; i < 4; i++) {
             const uint8_t* p = base + pos + i;
@@ -119,7 +121,7 @@ extern "C" int64_t hc_encode(const uint8_t* syms, uint64_t n, int sym_bytes, uin
         }
     }
     uint32_t len = sink.finish(lo);
-    if (!err && sink.overflow) err = ST_OUT_CAPACITY;
+    if (!err && sink.overflowed()) err = ST_OUT_CAPACITY;
     *status = err;
     return (int64_t)len;
 }
@@ -138,14 +140,16 @@ extern "C" int64_t hc_decode(const uint8_t* stream, uint64_t off0, uint64_t off1
     const float max_bucket = (float)(h.nb ? h.nb - 1 : 0);
     // emulate an unaligned chunk start inside an aligned buffer
     uint64_t al = off0 & ~3ull;
-    HostFetch hf{stream + al, 0, stream + stream_len};
+    uint32_t calls = 0;
+    const uint32_t skip = (uint32_t)(off0 & 3u);
+    HostFetch hf{stream + al, 0, stream + stream_len, &calls};
     DecSink<HostFetch> sink(hf);
-    sink.prime((uint32_t)(off0 & 3u));
+    sink.prime(skip);
     uint64_t lo = 0, rg = ~0ull, fallbacks = 0;
     uint32_t err = 0;
     for (uint64_t i = 0; i < n_syms; i++) {
         uint64_t rpt = pow2 ? range_par_total<true>(rg, h.div) : range_par_total<false>(rg, h.div);
-        uint64_t d = sink.data - lo;
+        uint64_t d = sink.data() - lo;
         uint32_t sym = 0;
         uint64_t P = 0, rgn = 0;
         bool ok = false;
@@ -171,10 +175,11 @@ extern "C" int64_t hc_decode(const uint8_t* stream, uint64_t off0, uint64_t off1
         else renorm<false>(lo, rg, sink, err);
         store_sym(out, i, sym_bytes, sym);
     }
-    if (!err && (uint64_t)sink.used > off1 - off0) err = ST_TRUNCATED;
+    const uint32_t used = sink.used(calls, skip);
+    if (!err && (uint64_t)used > off1 - off0) err = ST_TRUNCATED;
     *status = err;
     if (n_fallback) *n_fallback = fallbacks;
-    return (int64_t)sink.used;
+    return (int64_t)used;
 }
 
 // exhaustive check helper for the reciprocal: returns the number of mismatches
