@@ -82,7 +82,7 @@ int rcb_last_cuda_error(const rcb_ctx *ctx, const char **msg);
 
 /* ---- context --------------------------------------------------------------
  * Replaces nothing in the reference (it has no runtime); owns the stream and
- * scratch.  `stream` is a cudaStream_t (NULL = a private non-blocking stream). */
+ * scratch.  `stream` is a cudaStream_t (NULL = the default stream). */
 int rcb_ctx_create(int device, void *stream, rcb_ctx **out);
 int rcb_ctx_destroy(rcb_ctx *ctx);
 int rcb_ctx_set_stream(rcb_ctx *ctx, void *stream);

@@ -26,7 +26,6 @@ static_assert((int)RCB_MODEL_REGULAR == (int)MODEL_REGULAR, "model flags");
 struct rcb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    bool own_stream = false;
     int enc_threads = 128, dec_threads = 128;
     int sm_count = 148;
     uint8_t* staging = nullptr;
@@ -143,15 +142,7 @@ extern "C" int rcb_ctx_create(int device, void* stream, rcb_ctx** out) {
         return RCB_ERR_CUDA;
     }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
-    if (stream) {
-        c->stream = (cudaStream_t)stream;
-    } else {
-        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
-            delete c;
-            return RCB_ERR_CUDA;
-        }
-        c->own_stream = true;
-    }
+    c->stream = (cudaStream_t)stream;  // NULL = the default stream, as in the CUDA runtime
     bool ok = cudaMalloc(&c->d_summary, 8 * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMallocHost(&c->h_summary, 8 * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMalloc(&c->d_words, 8 * sizeof(uint32_t)) == cudaSuccess &&
@@ -167,7 +158,7 @@ extern "C" int rcb_ctx_create(int device, void* stream, rcb_ctx** out) {
 extern "C" int rcb_ctx_destroy(rcb_ctx* c) {
     if (!c) return RCB_OK;
     cudaSetDevice(c->device);
-    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->stream);
     cudaFree(c->staging);
     cudaFree(c->lens);
     cudaFree(c->status);
@@ -178,24 +169,14 @@ extern "C" int rcb_ctx_destroy(rcb_ctx* c) {
     cudaFree(c->h2d);
     for (int i = 0; i < 7; i++)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return RCB_OK;
 }
 
 extern "C" int rcb_ctx_set_stream(rcb_ctx* c, void* stream) {
     if (!c) return RCB_ERR_INVALID_ARGUMENT;
-    if (c->own_stream && c->stream) {
-        cudaStreamSynchronize(c->stream);
-        cudaStreamDestroy(c->stream);
-        c->own_stream = false;
-    }
-    if (stream) {
-        c->stream = (cudaStream_t)stream;
-    } else {
-        CK(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-        c->own_stream = true;
-    }
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->stream = (cudaStream_t)stream;
     return RCB_OK;
 }
 
@@ -481,30 +462,33 @@ static void launch_encode_variant(rcb_ctx* c, const rcb_model* m, const EncodeAr
     const bool checked = (m->bad_bits & 4u) != 0;
     const bool rangechk = (uint64_t)m->K < (1ull << (8 * sizeof(SYM)));
     const size_t smem = shared ? (size_t)m->K * sizeof(uint2) : 0;
-#define RCB_ENC(SH, P2, CH, RC)                                                                        \
+#define RCB_ENC(SH, P2, CH, RC, FU)                                                                    \
     do {                                                                                               \
-        auto kern = encode_kernel<SYM, SH, P2, CH, RC>;                                                \
+        auto kern = encode_kernel<SYM, SH, P2, CH, RC, FU>;                                            \
         if (smem > 48 * 1024)                                                                          \
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
         kern<<<blocks, threads, smem, c->stream>>>(a);                                                 \
     } while (0)
-#define RCB_ENC_RC(SH, P2, CH)               \
-    do {                                     \
-        if (rangechk) RCB_ENC(SH, P2, CH, true); \
-        else RCB_ENC(SH, P2, CH, false);     \
-    } while (0)
-#define RCB_ENC_CH(SH, P2)                   \
-    do {                                     \
-        if (checked) RCB_ENC_RC(SH, P2, true); \
-        else RCB_ENC_RC(SH, P2, false);      \
+#define RCB_ENC_RC(SH, P2, CH, FU)                   \
+    do {                                             \
+        if (rangechk) RCB_ENC(SH, P2, CH, true, FU); \
+        else RCB_ENC(SH, P2, CH, false, FU);         \
     } while (0)
     if (shared) {
-        if (pow2) RCB_ENC_CH(true, true);
-        else RCB_ENC_CH(true, false);
+        if (pow2) {
+            // FUSED: range/total and the renormalisation shift collapse into one shift
+            const bool fused = !checked && m->h_hdr0.div.shift >= 24;
+            if (fused) RCB_ENC_RC(true, true, false, true);
+            else if (checked) RCB_ENC_RC(true, true, true, false);
+            else RCB_ENC_RC(true, true, false, false);
+        } else {
+            if (checked) RCB_ENC_RC(true, false, true, false);
+            else RCB_ENC_RC(true, false, false, false);
+        }
     } else {
-        RCB_ENC_CH(false, false);
+        if (checked) RCB_ENC_RC(false, false, true, false);
+        else RCB_ENC_RC(false, false, false, false);
     }
-#undef RCB_ENC_CH
 #undef RCB_ENC_RC
 #undef RCB_ENC
 }
@@ -632,25 +616,30 @@ static void launch_decode_variant(rcb_ctx* c, const rcb_model* m, const DecodeAr
     const bool shared = m->n_models == 1;
     const bool pow2 = shared && (m->h_hdr0.flags & MODEL_POW2);
     const bool checked = (m->bad_bits & 4u) != 0;
+    const bool regular = shared && (m->h_hdr0.flags & MODEL_REGULAR);
+    // FUSED: range/total folded into the renormalisation shift, table-driven lookup (rcb_decode.cuh)
+    const bool fused = shared && pow2 && !checked && regular && m->h_hdr0.div.shift >= 24;
     size_t smem = 0;
     if (shared) {
-        uint32_t nb = (m->h_hdr0.flags & MODEL_REGULAR) ? m->h_hdr0.nb : 0u;
+        uint32_t nb = regular ? m->h_hdr0.nb : 0u;
+        if (fused) nb = LUT_CAP;
         smem = (size_t)nb * sizeof(LutEntry) + (size_t)m->K * sizeof(uint2);
     }
-#define RCB_DEC(SH, P2, CH)                                                                            \
+#define RCB_DEC(SH, P2, CH, FU)                                                                        \
     do {                                                                                               \
-        auto kern = decode_kernel<SYM, SH, P2, CH>;                                                    \
+        auto kern = decode_kernel<SYM, SH, P2, CH, FU>;                                                \
         if (smem > 48 * 1024)                                                                          \
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
         kern<<<blocks, threads, smem, c->stream>>>(a);                                                 \
     } while (0)
-#define RCB_DEC_CH(SH, P2)                 \
-    do {                                   \
-        if (checked) RCB_DEC(SH, P2, true); \
-        else RCB_DEC(SH, P2, false);       \
+#define RCB_DEC_CH(SH, P2)                         \
+    do {                                           \
+        if (checked) RCB_DEC(SH, P2, true, false); \
+        else RCB_DEC(SH, P2, false, false);        \
     } while (0)
     if (shared) {
-        if (pow2) RCB_DEC_CH(true, true);
+        if (fused) RCB_DEC(true, true, false, true);
+        else if (pow2) RCB_DEC_CH(true, true);
         else RCB_DEC_CH(true, false);
     } else {
         RCB_DEC_CH(false, false);

@@ -85,6 +85,26 @@ RCB_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {
 #endif
 }
 
+// 32-bit halves of a 64-bit value (explicit, so the compiler keeps 32-bit compares 32-bit)
+RCB_HD uint32_t hi32(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    uint32_t lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(x));
+    return hi;
+#else
+    return (uint32_t)(x >> 32);
+#endif
+}
+RCB_HD uint32_t lo32(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    uint32_t lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(x));
+    return lo;
+#else
+    return (uint32_t)x;
+#endif
+}
+
 RCB_HD uint32_t bswap32(uint32_t x) {
 #if defined(__CUDA_ARCH__)
     return __byte_perm(x, 0u, 0x0123);
@@ -211,11 +231,14 @@ RCB_HD void update_symbol(uint64_t& lo, uint64_t& rg, uint32_t cum, uint32_t c,
 // Encoder byte sink.  `pend` holds the nb (< 32, multiple of 8) pending bits in
 // its low end (bits above nb are stale and never read).  New bytes enter with
 // one funnel shift; when 32 or more bits are pending the oldest 32 are stored
-// as one word.  Store::word(pos, w) writes 4 bytes at byte offset pos
-// (pos % 4 == 0, memory order = emission order), Store::byte(pos, b) one byte.
+// as one word -- branch-free: the store is predicated and the counters are
+// updated with selects, so a symbol's emission is straight-line code.
+// Store::word_if(p, pos, w) writes 4 bytes at byte offset pos when p
+// (pos % 4 == 0, memory order = emission order); Store::byte(pos, b) one byte.
 // pos keeps counting past `cap`, so the final length is the needed capacity.
+// CHECK_CAP = false drops the capacity test (the caller guarantees room).
 // ---------------------------------------------------------------------------
-template <class Store>
+template <class Store, bool CHECK_CAP = true>
 struct EncSink {
     uint32_t pend = 0;
     uint32_t nb = 0;
@@ -228,13 +251,13 @@ struct EncSink {
     RCB_HD void push(uint32_t over, uint32_t merged, uint32_t sh) {
         // (over:merged) is the 64-bit value (old pend << sh) | new bits
         pend = merged;
-        nb += sh;
-        if (nb >= 32u) {
-            uint32_t w = funnel_r(merged, over, nb);  // bits [nb-32, nb); nb & 31 == nb - 32
-            if (pos + 4u <= cap) st.word(pos, bswap32(w));
-            pos += 4u;
-            nb -= 32u;
-        }
+        const uint32_t nb2 = nb + sh;
+        const bool fl = nb2 >= 32u;
+        const uint32_t w = funnel_r(merged, over, nb2);  // bits [nb2-32, nb2); nb2 & 31 == nb2 - 32
+        const bool room = CHECK_CAP ? (pos + 4u <= cap) : true;
+        st.word_if(fl && room, pos, bswap32(w));
+        pos += fl ? 4u : 0u;
+        nb = nb2 & 31u;
     }
     RCB_HD void put(uint32_t lo_hi, uint32_t sh) {
         push(funnel_l(pend, 0u, sh), funnel_l(lo_hi, pend, sh), sh);
@@ -258,10 +281,49 @@ struct EncSink {
 };
 
 // ---------------------------------------------------------------------------
+// Fused fast step for a power-of-two total 2^s with 24 <= s <= 31 and a
+// CONSISTENT table (no overflow is reachable, src/range_coder.rs:68-81,138-146).
+// The coder carries rpt = range >> s instead of range: after the update
+//   range' = rpt * c,  lower' = lower + rpt * cum,  upper' = lower + rpt * (cum + c)
+// loop 1 shifts both left by sh = 8 * n1 and the next symbol needs
+//   rpt_next = (range' << sh) >> s = range' >> (s - sh)          (range' << sh is exact)
+// so the renormalisation shift and the division collapse into one right shift.
+// n1 comes from three compares on the high word of lower' ^ upper' (find-leading-one
+// costs 19 cycles of latency on sm_100a, compare + select 9), and loop 2 does not
+// fire iff range' << sh >= 2^48 iff rpt_next >= 2^(48-s).
+// Returns false when the literal loops are needed (n1 >= 4 or loop 2); then the
+// caller renormalises (nlo, rgp) with renorm_slow.  hi/sh describe the bytes to
+// emit: the top sh/8 bytes of lower'.
+// ---------------------------------------------------------------------------
+struct FusedParams {
+    uint32_t s;      // log2(total)
+    uint32_t k0;     // s - 24: shift when n1 == 3
+    uint32_t thr;    // 2^(48 - s)
+};
+
+RCB_HD bool fused_step(uint64_t lo, uint64_t rpt, uint32_t cum, uint32_t c, const FusedParams& fp,
+                       uint64_t& nlo, uint64_t& rgp, uint64_t& nrpt, uint32_t& sh) {
+    nlo = lo + rpt * (uint64_t)cum;
+    const uint64_t up = lo + rpt * (uint64_t)(cum + c);
+    rgp = rpt * (uint64_t)c;
+    const uint32_t xh = hi32(nlo) ^ hi32(up);
+    const bool p1 = xh < (1u << 24), p2 = xh < (1u << 16), p3 = xh < (1u << 8);
+    const uint32_t k = p2 ? (p3 ? fp.k0 : fp.k0 + 8u) : (p1 ? fp.k0 + 16u : fp.k0 + 24u);
+    sh = (fp.k0 + 24u) - k;
+    nrpt = rgp >> k;
+    // loop 2 stays idle iff range' << sh >= 2^48 iff range' >= 2^(48-sh): a test on the high word
+    // of range' against 2^16 / 2^8 / 1 (exact for n1 <= 2; n1 == 3 and n1 >= 4, where the high
+    // word is 0, conservatively take the literal loops).  Ready as early as the shift amount.
+    const uint32_t need = p2 ? 1u : (p1 ? (1u << 8) : (1u << 16));
+    return hi32(rgp) >= need;
+}
+
+// ---------------------------------------------------------------------------
 // Decoder input window (src/decoder.rs:9,31-35).  (dh:dl) is `data`, aligned
 // with lower_bound; (wh:wl) holds the following bytes left-aligned with `cnt`
-// valid bits, refilled 32 bits at a time from Fetch::next_be32() (a big-endian
-// word of the stream).  Invariant between symbols: cnt >= 32.
+// valid bits, refilled 32 bits at a time from Fetch (peek_be32(): the next
+// big-endian word of the stream; advance_if(p): consume it when p).
+// Invariant between symbols: cnt >= 32.
 // ---------------------------------------------------------------------------
 template <class Fetch>
 struct DecSink {
@@ -275,17 +337,19 @@ struct DecSink {
     RCB_HD uint64_t data() const { return ((uint64_t)dh << 32) | dl; }
 
     RCB_HD void refill() {
-        if (cnt < 32u) {  // then wl == 0
-            uint32_t be = f.next_be32();
-            wl = funnel_r(0u, be, cnt);  // low word of (be:0) >> cnt
-            wh |= be >> cnt;
-            cnt += 32u;
-        }
+        // branch-free: when cnt < 32 (then wl == 0) append the next big-endian word
+        const bool need = cnt < 32u;
+        const uint32_t be = f.peek_be32();
+        wl = need ? funnel_r(0u, be, cnt) : wl;  // low word of (be:0) >> cnt
+        wh = need ? (wh | (be >> (cnt & 31u))) : wh;
+        cnt += need ? 32u : 0u;
+        f.advance_if(need);
     }
     // Decoder::new: data = first 8 bytes big-endian (decoder.rs:21).  The first
     // fetched word holds skip_bytes bytes that precede the chunk.
     RCB_HD void prime(uint32_t skip_bytes) {
-        uint32_t first = f.next_be32();
+        uint32_t first = f.peek_be32();
+        f.advance_if(true);
         wh = skip_bytes ? (first << (8u * skip_bytes)) : first;
         wl = 0;
         cnt = 32u - 8u * skip_bytes;
@@ -333,10 +397,12 @@ RCB_HD uint32_t find_index_exact(uint64_t d, uint64_t rpt, uint32_t K, CumAt cum
 // The rfreq axis [0,total) is cut into nb buckets of width 2^wshift.  Entry b
 // describes the symbol A whose interval contains b<<wshift and the next
 // non-zero symbol B:  [cumA,cumB) -> A, [cumB,cumC) -> B.
-// The bucket comes from a float estimate of d/rpt ~= d*total/range taken from
-// the high words only and biased low (range >= 2^48, so each high word carries
-// >= 16 significant bits: the estimate is off by < 1/4 bucket), then the choice
-// is verified exactly in the product domain; any miss (estimate off, more than
+// (Entry b is built for the point 1/8 bucket below b<<wshift, which absorbs the
+// error of the estimate.)  The bucket comes from a float estimate of
+// d/rpt ~= d*total/range taken from the high words only (range >= 2^48, so each
+// high word carries >= 16 significant bits: the estimate is within 1/16 bucket
+// above and 3/16 below the truth), then the choice is verified exactly in the
+// product domain; any miss (estimate off, more than
 // one boundary in the bucket, clamp-to-K-1 case, garbage stream) falls back to
 // find_index_exact, so the result never depends on float rounding.
 // ---------------------------------------------------------------------------
@@ -371,8 +437,7 @@ RCB_HD float fast_rcp(float x) {
 RCB_HD uint32_t lut_bucket(uint64_t d, uint64_t rg, float scale, float max_bucket) {
     float fd = (float)(uint32_t)(d >> 32);
     float fr = (float)(uint32_t)(rg >> 32);  // >= 2^16 for a live coder state
-    float bf = fd * (fast_rcp(fr) * scale) - (5.0f / 64.0f);
-    bf = bf < 0.0f ? 0.0f : bf;
+    float bf = fd * (fast_rcp(fr) * scale);  // >= 0; the LUT itself carries the safety margin
     bf = bf > max_bucket ? max_bucket : bf;  // also tames inf/NaN from a dead state
     return (uint32_t)bf;
 }
@@ -390,6 +455,61 @@ RCB_HD bool lut_resolve(const LutEntry& e, uint64_t d, uint64_t rpt, uint32_t& s
     sym = takeB ? (e.syms >> 16) : (e.syms & 0xFFFFu);
     rgn = PN - P;
     return (d - P) < rgn;  // P <= d < PN (unsigned wrap makes d < P fail)
+}
+
+
+// ---------------------------------------------------------------------------
+// Fused decode step (same preconditions as fused_step, plus a REGULAR table):
+// the candidates' new lower bounds lower + rpt * cum{A,B,C} come straight out of
+// multiply-adds, `data >= lower + rpt*cumB` picks the candidate, and
+// lower' <= data < upper' is the exact verification (d - P < rpt*c in disguise).
+// rinv16 = 16 * lut_scale / float(range >> 32) turns the high word of
+// data - lower into a byte offset into the 16-byte LUT entries.
+// ---------------------------------------------------------------------------
+RCB_HD uint32_t lut_offset16(uint32_t d_hi, float rinv16) {
+    float bf = (float)d_hi * rinv16;  // >= 0, in sixteenths of a bucket
+#if defined(__CUDA_ARCH__)
+    // round-toward-zero add of 2^23 leaves floor(bf) in the mantissa; no clamp: a huge estimate
+    // (garbage stream) lands on some in-bounds entry that fails verification (exact fallback)
+    return __float_as_uint(__fadd_rz(bf, 8388608.0f)) & 0xFFF0u;
+#else
+    if (!(bf < 65535.0f)) return 0xFFF0u;
+    return (uint32_t)bf & 0xFFF0u;
+#endif
+}
+
+RCB_HD float lut_rinv16(uint32_t rg_hi, float scale) {
+    return fast_rcp((float)rg_hi) * (16.0f * scale);
+}
+
+struct FusedDec {
+    uint64_t nlo, rgp, nrpt;
+    uint32_t sym, sh;
+    bool inside;  // symbol verified: lower' <= data < upper'
+    bool ok;      // ... and the fast renormalisation applies
+};
+
+RCB_HD FusedDec fused_decode_step(uint64_t lo, uint64_t rpt, uint64_t data, const LutEntry& e,
+                                  const FusedParams& fp) {
+    FusedDec r;
+    const uint64_t loA = lo + rpt * (uint64_t)e.cumA;
+    const uint64_t loB = lo + rpt * (uint64_t)e.cumB;
+    const uint64_t loC = lo + rpt * (uint64_t)e.cumC;
+    const bool takeB = data >= loB;
+    r.nlo = takeB ? loB : loA;
+    const uint64_t up = takeB ? loC : loB;
+    r.sym = takeB ? (e.syms >> 16) : (e.syms & 0xFFFFu);
+    const bool inside = (data >= r.nlo) & (data < up);
+    r.rgp = up - r.nlo;
+    const uint32_t xh = hi32(r.nlo) ^ hi32(up);
+    const bool p1 = xh < (1u << 24), p2 = xh < (1u << 16), p3 = xh < (1u << 8);
+    const uint32_t k = p2 ? (p3 ? fp.k0 : fp.k0 + 8u) : (p1 ? fp.k0 + 16u : fp.k0 + 24u);
+    r.sh = (fp.k0 + 24u) - k;
+    r.nrpt = r.rgp >> k;
+    const uint32_t need = p2 ? 1u : (p1 ? (1u << 8) : (1u << 16));  // see fused_step
+    r.inside = inside;
+    r.ok = inside & (hi32(r.rgp) >= need);
+    return r;
 }
 
 }  // namespace rcb

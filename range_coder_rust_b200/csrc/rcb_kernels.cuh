@@ -282,7 +282,10 @@ __global__ void __launch_bounds__(256) finalize_models_kernel(const uint2* __res
     const ModelHdr& H = hdrs[model];
     if (!(H.flags & MODEL_REGULAR)) return;
     for (uint32_t b = threadIdx.x; b < H.nb; b += blockDim.x) {
+        // the point this entry is built for: 1/8 bucket below the bucket start (estimate margin)
         unsigned long long v0 = (unsigned long long)b << H.wshift;  // < total
+        const unsigned long long margin = (1ull << H.wshift) >> 3;
+        v0 = v0 > margin ? v0 - margin : 0ull;
         // A = number of i in [1,K-1] with cum[i] <= v0  (the reference's search result)
         uint32_t left = 0, right = K - 1;
         while (left < right) {

@@ -18,7 +18,9 @@ namespace {
 
 struct HostStore {
     uint8_t* row;
-    void word(uint32_t pos, uint32_t w) const { memcpy(row + pos, &w, 4); }
+    void word_if(bool p, uint32_t pos, uint32_t w) const {
+        if (p) memcpy(row + pos, &w, 4);
+    }
     void byte(uint32_t pos, uint32_t b) const { row[pos] = (uint8_t)b; }
 };
 
@@ -27,16 +29,20 @@ struct HostFetch {
     uint64_t pos;         // next word offset from base
     const uint8_t* end;
     uint32_t* calls;
-    uint32_t next_be32() {
-        ++*calls;
+    uint32_t peek_be32() const {
         uint32_t w = 0;
         for (int i = 0; i < 4; i++) {
             const uint8_t* p = base + pos + i;
             uint32_t b = p < end ? *p : 0u;
             w = (w << 8) | b;
         }
-        pos += 4;
         return w;
+    }
+    void advance_if(bool p) {
+        if (p) {
+            ++*calls;
+            pos += 4;
+        }
     }
 };
 
@@ -78,6 +84,8 @@ void build_header(uint32_t K, const uint32_t* c, const uint32_t* cum, uint32_t t
     lut.resize(h.nb);
     for (uint32_t b = 0; b < h.nb; b++) {
         uint64_t v0 = (uint64_t)b << h.wshift;
+        const uint64_t margin = (1ull << h.wshift) >> 3;
+        v0 = v0 > margin ? v0 - margin : 0;
         uint32_t left = 0, right = K - 1;
         while (left < right) {
             uint32_t mid = (left + right) >> 1;
@@ -106,6 +114,37 @@ extern "C" int64_t hc_encode(const uint8_t* syms, uint64_t n, int sym_bytes, uin
     uint32_t err = 0;
     HostStore hs{out};
     EncSink<HostStore> sink(hs, cap);
+    // fused pow2 path (mirrors encode_kernel's FUSED instantiation), selected like the kernel does
+    bool consistent = true;
+    for (uint32_t i = 0; i < K; i++)
+        if ((uint64_t)cum[i] + c[i] > total) consistent = false;
+    if (pow2 && div.shift >= 24 && consistent && !checked) {
+        FusedParams fp{div.shift, div.shift - 24u, 1u << (48u - div.shift)};
+        uint64_t rpt = rg >> fp.s;
+        for (uint64_t i = 0; i < n; i++) {
+            uint32_t s = load_sym(syms, i, sym_bytes);
+            if (s >= K) {
+                if (!err) err = ST_SYMBOL_RANGE;
+                s = 0;
+            }
+            uint64_t nlo, rgp, nrpt;
+            uint32_t sh;
+            if (fused_step(lo, rpt, cum[s], c[s], fp, nlo, rgp, nrpt, sh)) {
+                sink.put((uint32_t)(nlo >> 32), sh);
+                lo = nlo << sh;
+                rpt = nrpt;
+            } else {
+                lo = nlo;
+                rg = rgp;
+                renorm_slow<false>(lo, rg, sink, err);
+                rpt = rg >> fp.s;
+            }
+        }
+        uint32_t len = sink.finish(lo);
+        if (!err && sink.overflowed()) err = ST_OUT_CAPACITY;
+        *status = err;
+        return (int64_t)len;
+    }
     for (uint64_t i = 0; i < n; i++) {
         uint32_t s = load_sym(syms, i, sym_bytes);
         if (s >= K) {
@@ -147,6 +186,44 @@ extern "C" int64_t hc_decode(const uint8_t* stream, uint64_t off0, uint64_t off1
     sink.prime(skip);
     uint64_t lo = 0, rg = ~0ull, fallbacks = 0;
     uint32_t err = 0;
+    // fused pow2 path (mirrors decode_kernel's FUSED instantiation)
+    if (lut_ok && pow2 && h.div.shift >= 24 && (h.flags & MODEL_CONSISTENT) && !checked && lut_cap == 4096) {
+        FusedParams fp{h.div.shift, h.div.shift - 24u, 1u << (48u - h.div.shift)};
+        std::vector<LutEntry> pad(4096);
+        for (uint32_t b = 0; b < 4096; b++) {
+            if (b < h.nb) pad[b] = lut[b];
+            else pad[b] = LutEntry{total, total, total, 0};
+        }
+        uint64_t rpt = rg >> fp.s;
+        float rinv16 = lut_rinv16(hi32(rg), h.lut_scale);
+        for (uint64_t i = 0; i < n_syms; i++) {
+            const uint64_t data = sink.data();
+            const uint32_t off = lut_offset16(hi32(data) - hi32(lo), rinv16);
+            FusedDec r = fused_decode_step(lo, rpt, data, pad[off >> 4], fp);
+            uint32_t sym;
+            if (r.ok) {
+                sym = r.sym;
+                sink.put(0, r.sh);
+                lo = r.nlo << r.sh;
+                rpt = r.nrpt;
+                rinv16 = lut_rinv16(hi32(r.rgp << r.sh), h.lut_scale);
+            } else {
+                fallbacks++;
+                sym = find_index_exact(data - lo, rpt, K, [&](uint32_t j) { return cum[j]; });
+                lo = lo + rpt * (uint64_t)cum[sym];
+                rg = rpt * (uint64_t)c[sym];
+                renorm<false>(lo, rg, sink, err);
+                rpt = rg >> fp.s;
+                rinv16 = lut_rinv16(hi32(rg), h.lut_scale);
+            }
+            store_sym(out, i, sym_bytes, sym);
+        }
+        const uint32_t used = sink.used(calls, skip);
+        if (!err && (uint64_t)used > off1 - off0) err = ST_TRUNCATED;
+        *status = err;
+        if (n_fallback) *n_fallback = fallbacks;
+        return (int64_t)used;
+    }
     for (uint64_t i = 0; i < n_syms; i++) {
         uint64_t rpt = pow2 ? range_par_total<true>(rg, h.div) : range_par_total<false>(rg, h.div);
         uint64_t d = sink.data() - lo;

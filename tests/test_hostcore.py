@@ -2,6 +2,7 @@
 host by tests/hostcore) against the oracle: closed-form renormalisation, byte
 sinks, reciprocal division, table-driven symbol lookup with exact fallback."""
 import ctypes
+import zlib
 
 import numpy as np
 import pytest
@@ -49,7 +50,7 @@ def random_model(rng, K, kind):
 @pytest.mark.parametrize("kind", ["pow2", "big", "gaps", "zipf"])
 @pytest.mark.parametrize("K", [2, 10, 256, 4096])
 def test_encode_decode_match_oracle(oracle, hostcore, K, kind):
-    rng = np.random.default_rng(hash((K, kind)) % (2 ** 32))
+    rng = np.random.default_rng(zlib.crc32(f"{K}-{kind}".encode()))
     c = random_model(rng, K, kind)
     cum, total = oracle.calc_cum(c)
     used_syms = np.flatnonzero(c)
@@ -72,6 +73,36 @@ def test_encode_decode_match_oracle(oracle, hostcore, K, kind):
             assert np.array_equal(dec, syms)
             if use_lut and K <= 256 and kind in ("pow2", "zipf"):
                 assert fb < n * 0.05  # the LUT resolves nearly everything
+
+
+def test_fused_path_slow_events_and_degenerate_streams(oracle, hostcore):
+    """total = 2^30 (the benchmark's shape): loop-2 events inside the fused loop, and streams whose
+    value sits at the very bottom of the range (data - lower == 0 for every symbol)."""
+    rng = np.random.default_rng(77)
+    w = np.arange(1, 257, dtype=np.float64) ** -1.1
+    c = np.maximum(1, (w / w.sum() * (1 << 30)).astype(np.int64))
+    c[0] += (1 << 30) - c.sum()
+    c = c.astype(np.uint32)
+    cum, total = oracle.calc_cum(c)
+    assert total == 1 << 30
+    n = 300_000
+    syms = rng.choice(256, size=n, p=c / c.sum()).astype(np.uint8)
+    ref = oracle.encode(syms, c, cum, total)
+    code, length, st = hc_encode(hostcore, syms, c, cum, total)
+    assert st == 0 and code == ref
+    dec, used, st, fb = hc_decode(hostcore, np.frombuffer(ref + bytes(32), dtype=np.uint8), 0, len(ref), n, c, cum,
+                                  total)
+    assert st == 0 and used == len(ref) and np.array_equal(dec, syms)
+    assert 0 < fb < n * 0.01  # loop-2 events take the exact path, nearly everything else the table
+    for sym in (0, 255):
+        syms = np.full(20_000, sym, dtype=np.uint8)
+        ref = oracle.encode(syms, c, cum, total)
+        code, length, st = hc_encode(hostcore, syms, c, cum, total)
+        assert st == 0 and code == ref
+        dec, used, st, fb = hc_decode(hostcore, np.frombuffer(ref + bytes(32), dtype=np.uint8), 0, len(ref),
+                                      syms.size, c, cum, total)
+        assert st == 0 and used == len(ref) and np.array_equal(dec, syms)
+        assert fb < syms.size * 0.02
 
 
 def test_small_lut_forces_fallbacks_but_stays_exact(oracle, hostcore):
