@@ -619,11 +619,11 @@ static void launch_decode_variant(rcb_ctx* c, const rcb_model* m, const DecodeAr
     const bool regular = shared && (m->h_hdr0.flags & MODEL_REGULAR);
     // FUSED: range/total folded into the renormalisation shift, table-driven lookup (rcb_decode.cuh)
     const bool fused = shared && pow2 && !checked && regular && m->h_hdr0.div.shift >= 24;
-    size_t smem = 0;
+    size_t smem = (size_t)threads * RING_STRIDE;  // per-lane code-byte rings
     if (shared) {
         uint32_t nb = regular ? m->h_hdr0.nb : 0u;
         if (fused) nb = LUT_CAP;
-        smem = (size_t)nb * sizeof(LutEntry) + (size_t)m->K * sizeof(uint2);
+        smem += (size_t)nb * sizeof(LutEntry) + (size_t)m->K * sizeof(uint2);
     }
 #define RCB_DEC(SH, P2, CH, FU)                                                                        \
     do {                                                                                               \

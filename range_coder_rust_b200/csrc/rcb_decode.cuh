@@ -8,10 +8,17 @@
 // cum_freq is the out-of-line fallback.  Per-chunk models use the exact search
 // on their own table.  Like the encoder, run time is one lane's per-symbol
 // instruction stream, so the hot step is branch-free: funnel-shift window
-// refill with a predicated load three words ahead, select trees instead of
-// find-leading-one, (FUSED) range/total folded into the renormalisation shift,
-// and rare events handled per 32-bit word of output by checkpoint + exact
-// re-decode (see rcb_encode.cuh).
+// refill, select trees instead of find-leading-one, (FUSED) range/total folded
+// into the renormalisation shift, and rare events handled per 32-bit word of
+// output by checkpoint + exact re-decode (see rcb_encode.cuh).
+//
+// Code bytes reach a lane through a private 128-byte ring in shared memory
+// filled by cp.async (LDGSTS) in 16-byte pieces, issued warp-synchronously once
+// per output word.  Lanes consume their streams at data-dependent rates, and the
+// register scoreboard is per warp: any global load into a register that a later
+// (even predicated-off) instruction reads stalls the whole warp for the load's
+// latency.  cp.async has no destination register, so the only loads on the
+// symbol path are shared-memory loads.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -35,42 +42,89 @@ struct DecodeArgs {
     uint32_t* status;
 };
 
-// Sequential reader of one chunk's bytes: aligned 32-bit loads, three words of
-// lookahead in registers (the load issued at one refill is consumed three
-// refills later, ~15 symbols, so its latency never reaches the coder).  Loads
-// are clamped to the last word of the stream so a corrupt stream cannot make a
-// lane read outside the caller's buffer.
-struct GlobalFetch {
-    const uint32_t* base;  // word that holds the chunk's first byte
-    uint32_t idx;          // words consumed so far; w0 is word idx
-    uint32_t last;         // last readable word (from base)
-    uint32_t w0, w1, w2;
-    __device__ __forceinline__ uint32_t load(uint32_t i) const { return __ldg(base + (i < last ? i : last)); }
-    __device__ __forceinline__ void init(const uint8_t* stream, uint64_t off, uint64_t total_bytes) {
-        const uint64_t word0 = off >> 2;
-        base = reinterpret_cast<const uint32_t*>(stream) + word0;
-        // the stream is readable up to the next multiple of 16 bytes (rcb200.h)
-        const uint64_t lastw = (((total_bytes + 15) >> 4) << 2) - 1 - word0;
-        last = lastw > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)lastw;
-        idx = 0;
-        w0 = load(0);
-        w1 = load(1);
-        w2 = load(2);
-    }
-    __device__ __forceinline__ uint32_t peek_be32() const { return bswap32(w0); }
+constexpr uint32_t RING_PIECES = 8;                   // 16-byte pieces per lane
+constexpr uint32_t RING_STRIDE = RING_PIECES * 16 + 16;  // 144 bytes: 16-byte aligned, spreads banks
+
+// ---------------------------------------------------------------------------
+// Fetch for the hot loops: words come from the lane's shared-memory ring.
+// Positions are absolute word / piece indices from `pbase` (the 16-byte aligned
+// address at or below the chunk's first byte).
+// ---------------------------------------------------------------------------
+struct RingFetch {
+    uint32_t ring;   // shared-space address of this lane's ring
+    uint32_t rd;     // words consumed; `cur` holds word rd
+    uint32_t cur;
+    __device__ __forceinline__ uint32_t slot(uint32_t w) const { return ring + (w & (RING_PIECES * 4 - 1)) * 4; }
+    __device__ __forceinline__ uint32_t peek_be32() const { return bswap32(cur); }
     __device__ __forceinline__ void advance_if(bool p) {
-        idx += p ? 1u : 0u;
-        w0 = p ? w1 : w0;
-        w1 = p ? w2 : w1;
-        const uint32_t j = idx + 2u;
-        const uint32_t* q = base + (j < last ? j : last);
-        asm volatile(
-            "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@q ld.global.nc.b32 %0, [%2];\n\t}"
-            : "+r"(w2)
-            : "r"((uint32_t)p), "l"(q)
-            : "memory");
+        rd += p ? 1u : 0u;
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@q ld.shared.b32 %0, [%2];\n\t}"
+                     : "+r"(cur)
+                     : "r"((uint32_t)p), "r"(slot(rd))
+                     : "memory");
     }
-    __device__ __forceinline__ uint32_t words_fetched() const { return idx; }
+    __device__ __forceinline__ void reload() {
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(cur) : "r"(slot(rd)) : "memory");
+    }
+};
+
+// Ring producer side (per lane): pieces [.., wr) have been requested.
+struct RingFill {
+    const uint8_t* pbase;  // 16-byte aligned
+    uint32_t wr;           // pieces requested so far
+    uint32_t npieces;      // pieces that exist in the readable stream
+    uint32_t pend;         // bytes requested in the most recent committed group
+    __device__ __forceinline__ void issue_if(bool p, uint32_t ring) {
+        const uint32_t saddr = ring + (wr & (RING_PIECES - 1)) * 16;
+        const uint8_t* g = pbase + (uint64_t)wr * 16;
+        asm volatile(
+            "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q cp.async.cg.shared.global [%0], [%1], 16;\n\t}"
+            :
+            : "r"(saddr), "l"(g), "r"((uint32_t)p)
+            : "memory");
+        wr += p ? 1u : 0u;
+    }
+    // Once per output word, all lanes together: retire older groups, top the ring up (<= 2 pieces).
+    __device__ __forceinline__ void round(RingFetch& f) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        uint32_t occ = wr * 16 - f.rd * 4;  // bytes requested and not yet consumed
+        if (occ < 64u + pend) {             // backstop (rare): less than 64 completed bytes ahead
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            pend = 0;
+        }
+        const bool p1 = (occ <= RING_PIECES * 16 - 16) & (wr < npieces);
+        issue_if(p1, f.ring);
+        occ += p1 ? 16u : 0u;
+        const bool p2 = (occ <= RING_PIECES * 16 - 16) & (wr < npieces);
+        issue_if(p2, f.ring);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        pend = (p1 ? 16u : 0u) + (p2 ? 16u : 0u);
+    }
+    // (Re)start after the read position moved arbitrarily (initial fill, exact out-of-line path).
+    __device__ __forceinline__ void resync(RingFetch& f) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (f.rd * 4 >= wr * 16) wr = f.rd >> 2;  // consumed past everything requested
+#pragma unroll 1
+        // signed: right after a restart the read position sits up to 12 bytes inside piece wr
+        while (((int32_t)(wr * 16 - f.rd * 4) <= (int32_t)(RING_PIECES * 16 - 16)) & (wr < npieces))
+            issue_if(true, f.ring);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        pend = 0;
+        f.reload();
+    }
+};
+
+// ---------------------------------------------------------------------------
+// Fetch for the exact out-of-line path: plain global loads (clamped to the
+// readable stream), no lookahead needed there.
+// ---------------------------------------------------------------------------
+struct GlobalFetch {
+    const uint32_t* base;  // pbase as words
+    uint32_t idx;          // words consumed
+    uint32_t last;         // last readable word
+    __device__ __forceinline__ uint32_t peek_be32() const { return bswap32(__ldg(base + (idx < last ? idx : last))); }
+    __device__ __forceinline__ void advance_if(bool p) { idx += p ? 1u : 0u; }
 };
 
 __device__ __forceinline__ void prefetch_l2_bulk_dec(const void* p, uint32_t bytes) {
@@ -85,21 +139,21 @@ __device__ __forceinline__ LutEntry lds_lut(uint32_t saddr) {
     return e;
 }
 
-// Lane state that travels by value through the exact (out-of-line) paths.
+// Lane state that travels by value through the exact (out-of-line) path.
 struct DecLaneState {
     uint64_t lo, rg;
     uint32_t dh, dl, wh, wl, cnt;
     const uint32_t* base;
-    uint32_t idx, last, w0, w1, w2;
+    uint32_t rd, last;
     uint32_t err, syms;  // syms: symbols decoded by the call, packed like the output word
 };
 
 // One symbol on the exact path: the reference's search in the product domain plus the
 // generic renormalisation (literal loops when needed).
-template <bool CHECKED>
-__device__ __forceinline__ uint32_t dec_symbol_exact(uint64_t& lo, uint64_t& rg, DecSink<GlobalFetch>& sink,
-                                                     uint32_t& err, const uint2* tab, uint32_t K,
-                                                     const DivParams& div, bool pow2) {
+template <bool CHECKED, class Sink>
+__device__ __forceinline__ uint32_t dec_symbol_exact(uint64_t& lo, uint64_t& rg, Sink& sink, uint32_t& err,
+                                                     const uint2* tab, uint32_t K, const DivParams& div,
+                                                     bool pow2) {
     const uint64_t rpt = pow2 ? range_par_total<true>(rg, div) : range_par_total<false>(rg, div);
     const uint64_t d = sink.data() - lo;  // examples/sample_impl.rs:29
     const uint32_t sym = find_index_exact(d, rpt, K, [&](uint32_t i) { return tab[i].x; });
@@ -124,13 +178,7 @@ template <bool CHECKED>
 __device__ __noinline__ DecLaneState dec_exact(DecLaneState s, const uint2* tab, uint32_t K, DivParams div,
                                                uint32_t pow2, uint32_t n_syms, uint32_t sym_bits,
                                                uint32_t lut_saddr, float lut_scale) {
-    GlobalFetch gf;
-    gf.base = s.base;
-    gf.idx = s.idx;
-    gf.last = s.last;
-    gf.w0 = s.w0;
-    gf.w1 = s.w1;
-    gf.w2 = s.w2;
+    GlobalFetch gf{s.base, s.rd, s.last};
     DecSink<GlobalFetch> sink(gf);
     sink.dh = s.dh;
     sink.dl = s.dl;
@@ -164,26 +212,24 @@ __device__ __noinline__ DecLaneState dec_exact(DecLaneState s, const uint2* tab,
     s.wh = sink.wh;
     s.wl = sink.wl;
     s.cnt = sink.cnt;
-    s.idx = sink.f.idx;
-    s.w0 = sink.f.w0;
-    s.w1 = sink.f.w1;
-    s.w2 = sink.f.w2;
+    s.rd = sink.f.idx;
     return s;
 }
 
 template <typename SYM, bool SHARED, bool POW2, bool CHECKED, bool FUSED>
-__global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
+__global__ void __launch_bounds__(256, 1) decode_kernel(DecodeArgs a) {
     extern __shared__ __align__(16) uint8_t s_raw[];
     __shared__ ModelHdr s_hdr;
-    // shared layout: LutEntry[nb or 4096] | uint2[K]
-    LutEntry* s_lut = reinterpret_cast<LutEntry*>(s_raw);
+    // shared layout: rings[blockDim.x][RING_STRIDE] | LutEntry[nb or 4096] | uint2[K]
+    uint8_t* s_ring = s_raw;
+    LutEntry* s_lut = reinterpret_cast<LutEntry*>(s_raw + (size_t)blockDim.x * RING_STRIDE);
     uint2* s_tab = nullptr;
     if (SHARED) {
         if (threadIdx.x == 0) s_hdr = a.hdrs[0];
         __syncthreads();
         const uint32_t nb = (s_hdr.flags & MODEL_REGULAR) ? s_hdr.nb : 0u;
         const uint32_t nb_pad = FUSED ? 4096u : nb;  // FUSED indexes any of 4096 entries
-        s_tab = reinterpret_cast<uint2*>(s_raw + (size_t)nb_pad * sizeof(LutEntry));
+        s_tab = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(s_lut) + (size_t)nb_pad * sizeof(LutEntry));
         const uint4* gl = reinterpret_cast<const uint4*>(a.lut);
         uint4* sl = reinterpret_cast<uint4*>(s_lut);
         const uint32_t total = s_hdr.div.total;
@@ -209,26 +255,38 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
 
     const uint64_t off0 = a.offsets[chunk], off1 = a.offsets[chunk + 1];
     const uint64_t total_bytes = a.offsets[a.n_chunks];
+    const uint64_t pb = off0 & ~15ull;                               // piece base (byte offset)
+    const uint64_t readable = ((total_bytes + 15) & ~15ull) - pb;    // rcb200.h: readable to the next 16
     const uint32_t skip = (uint32_t)(off0 & 3u);
-    GlobalFetch gf;
-    gf.init(a.stream, off0, total_bytes);
-    DecSink<GlobalFetch> sink(gf);
+    const uint32_t rd0 = (uint32_t)((off0 - pb) >> 2);
+
+    RingFill fill;
+    fill.pbase = a.stream + pb;
+    fill.wr = 0;
+    fill.npieces = readable > (0xFFFFFFF0ull << 4) ? 0xFFFFFFF0u : (uint32_t)(readable >> 4);
+    fill.pend = 0;
+    RingFetch rf;
+    rf.ring = (uint32_t)__cvta_generic_to_shared(s_ring + (size_t)threadIdx.x * RING_STRIDE);
+    rf.rd = rd0;
+    rf.cur = 0;
+    const uint32_t last_word = fill.npieces * 4 - 1;
+
     // L2 prefetch of this lane's code bytes in 1 KiB granules, two granules ahead
     constexpr uint32_t PF_WORDS = 256;
-    const uint8_t* pf_base = a.stream + (off0 & ~15ull);
-    const uint64_t pf_avail = ((total_bytes + 15) & ~15ull) - (off0 & ~15ull);
-    uint32_t pf_next = 0;  // next granule (in words from base) to request
+    uint32_t pf_next = 0;  // next granule (in words from pbase) to request
     auto prefetch_to = [&](uint32_t upto_words) {
         while (pf_next < upto_words) {
             const uint64_t o = (uint64_t)pf_next * 4;
-            if (o < pf_avail) {
-                const uint64_t left = pf_avail - o;
-                prefetch_l2_bulk_dec(pf_base + o, (uint32_t)(left < PF_WORDS * 4 ? left : PF_WORDS * 4));
+            if (o < readable) {
+                const uint64_t left = readable - o;
+                prefetch_l2_bulk_dec(fill.pbase + o, (uint32_t)(left < PF_WORDS * 4 ? left : PF_WORDS * 4));
             }
             pf_next += PF_WORDS;
         }
     };
     prefetch_to(2 * PF_WORDS);
+    fill.resync(rf);  // initial fill: RING_PIECES pieces, wait, load word rd0
+    DecSink<RingFetch> sink(rf);
     sink.prime(skip);  // src/decoder.rs:14-23
 
     uint64_t lo = 0, rg = ~0ull;
@@ -237,10 +295,10 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
     constexpr uint32_t PER = 4 / sizeof(SYM);  // symbols per 32-bit store
     constexpr uint32_t SYM_BITS = 8 * sizeof(SYM);
     auto snapshot = [&]() -> DecLaneState {
-        return DecLaneState{lo, rg, sink.dh, sink.dl, sink.wh, sink.wl, sink.cnt, sink.f.base,
-                            sink.f.idx, sink.f.last, sink.f.w0, sink.f.w1, sink.f.w2, err, 0u};
+        return DecLaneState{lo, rg, sink.dh, sink.dl, sink.wh, sink.wl, sink.cnt,
+                            reinterpret_cast<const uint32_t*>(fill.pbase), sink.f.rd, last_word, err, 0u};
     };
-    auto restore = [&](const DecLaneState& st) {
+    auto restore = [&](const DecLaneState& st) {  // after the exact path: adopt its state, restart the ring
         lo = st.lo;
         rg = st.rg;
         sink.dh = st.dh;
@@ -248,11 +306,9 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
         sink.wh = st.wh;
         sink.wl = st.wl;
         sink.cnt = st.cnt;
-        sink.f.idx = st.idx;
-        sink.f.w0 = st.w0;
-        sink.f.w1 = st.w1;
-        sink.f.w2 = st.w2;
+        sink.f.rd = st.rd;
         err = st.err;
+        fill.resync(sink.f);
     };
 
     uint64_t done = 0;
@@ -267,7 +323,8 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
         const uint32_t lut_saddr = (uint32_t)__cvta_generic_to_shared(s_lut);
 #pragma unroll 1
         for (uint64_t i = 0; i < nw; i++) {
-            if (sink.f.idx + PF_WORDS >= pf_next) prefetch_to(sink.f.idx + 2 * PF_WORDS);
+            if (sink.f.rd + PF_WORDS >= pf_next) prefetch_to(sink.f.rd + 2 * PF_WORDS);
+            fill.round(sink.f);
             rg = rpt << fp.s;  // checkpoint in the generic form (low s bits never matter)
             const DecLaneState chk = snapshot();
             uint32_t acc = 0;
@@ -329,7 +386,8 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
     if (!FUSED) {
 #pragma unroll 1
         for (uint64_t i = 0; i < nw; i++) {
-            if (sink.f.idx + PF_WORDS >= pf_next) prefetch_to(sink.f.idx + 2 * PF_WORDS);
+            if (sink.f.rd + PF_WORDS >= pf_next) prefetch_to(sink.f.rd + 2 * PF_WORDS);
+            fill.round(sink.f);
             uint32_t acc = 0;
 #pragma unroll
             for (uint32_t b = 0; b < PER; b++) acc |= step() << (SYM_BITS * b);
@@ -338,9 +396,13 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
         done = nw * PER;
     }
 #pragma unroll 1
-    for (uint64_t i = done; i < cnt; i++) dst[i] = (SYM)step();
+    for (uint64_t i = done; i < cnt; i++) {
+        fill.round(sink.f);
+        dst[i] = (SYM)step();
+    }
 
-    const uint32_t used = sink.used(sink.f.words_fetched(), skip);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    const uint32_t used = sink.used(sink.f.rd - rd0, skip);
     if (!err && (uint64_t)used > off1 - off0) err = ST_TRUNCATED;  // src/decoder.rs:33
     a.status[chunk] = err;
 }

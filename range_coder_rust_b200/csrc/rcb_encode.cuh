@@ -119,7 +119,7 @@ __device__ __noinline__ EncWordState enc_word_exact(EncWordState s, EncEntries<S
 // SHARED: one table for all chunks, staged in shared memory.
 // !SHARED: one table per chunk, read through L1/L2 from global memory.
 template <typename SYM, bool SHARED, bool POW2, bool CHECKED, bool RANGECHK, bool FUSED>
-__global__ void __launch_bounds__(256) encode_kernel(EncodeArgs a) {
+__global__ void __launch_bounds__(256, 1) encode_kernel(EncodeArgs a) {
     extern __shared__ __align__(16) uint8_t s_raw[];
     uint2* s_tab = reinterpret_cast<uint2*>(s_raw);
     __shared__ ModelHdr s_hdr;
