@@ -117,8 +117,9 @@ int rcb_histogram(rcb_ctx *ctx, const void *d_syms, uint64_t n_syms, int sym_byt
 /* FreqTable::calc_cum (examples/sample_impl.rs:61-69): c = counts, cum =
  * exclusive prefix sum, total = sum.  count_bytes is 8 (uint64[n_models][K]) or
  * 4 (uint32[n_models][K]).  When a u64 sum exceeds 2^32-1 (total_freq is u32,
- * src/pmodel.rs:10) the counts are first shifted right by the smallest sh with
- * (sum>>sh)+K <= 2^32-1, non-zero counts staying >= 1 (build-defined
+ * src/pmodel.rs:10, and the reference has no rule for that) the counts are
+ * rescaled to total = 2^31: c' = c ? max(1, floor(c * 2^31 / sum)) : 0, the
+ * rounding difference going to the largest count (build-defined
  * extension; identical in the oracle).  Synchronises. */
 int rcb_model_from_counts(rcb_ctx *ctx, rcb_model *m, const void *d_counts, int count_bytes);
 

@@ -227,24 +227,38 @@ uint32_t rco_calc_cum(const uint32_t *c, uint32_t K, uint32_t *cum) {
     return cum_total;
 }
 
-/* SURVEY App. C.2 (build-defined; identity == the reference whenever it applies) */
+/* Build-defined extension; identity == the reference whenever it applies.
+ * sum > 2^32-1: rescale to total = 2^31 exactly: c' = c ? max(1, floor(c*2^31/sum)) : 0, then
+ * the difference 2^31 - sum(c') goes to the largest count (lowest index on ties).
+ * Returns 1 when the counts were rescaled, 0 for the identity. */
 int rco_normalise(const uint64_t *counts, uint32_t K, uint32_t *c) {
-    /* sum can exceed u64 only for absurd inputs; saturate */
     unsigned __int128 sum = 0;
-    for (uint32_t i = 0; i < K; i++) sum += counts[i];
-    int sh = 0;
-    if (sum > 0xFFFFFFFFull) {
-        while ((sum >> sh) + K > 0xFFFFFFFFull) sh++;
-    }
+    uint64_t vmax = 0;
+    uint32_t imax = 0;
     for (uint32_t i = 0; i < K; i++) {
-        uint64_t v = counts[i];
-        if (sh) {
-            uint64_t s = v >> sh;
-            v = v == 0 ? 0 : (s == 0 ? 1 : s);
+        sum += counts[i];
+        if (counts[i] > vmax) {
+            vmax = counts[i];
+            imax = i;
         }
-        c[i] = (uint32_t)v;
     }
-    return sh;
+    if (sum <= 0xFFFFFFFFull) {
+        for (uint32_t i = 0; i < K; i++) c[i] = (uint32_t)counts[i];
+        return 0;
+    }
+    int64_t scaled = 0;
+    for (uint32_t i = 0; i < K; i++) {
+        uint32_t v = 0;
+        if (counts[i]) {
+            unsigned __int128 q = ((unsigned __int128)counts[i] << 31) / sum;
+            v = (uint32_t)q;
+            if (v == 0) v = 1;
+        }
+        c[i] = v;
+        scaled += v;
+    }
+    c[imax] = (uint32_t)((int64_t)c[imax] + ((int64_t)1 << 31) - scaled);
+    return 1;
 }
 
 /* ------------------------------------------------------------------------- */

@@ -72,10 +72,10 @@ void rco_histogram(const void *syms, uint64_t n, int sym_bytes, uint32_t K,
 /* examples/sample_impl.rs:61-69: exclusive prefix sum, returns total.
  * (u32 wrapping exactly like release-mode Rust.) */
 uint32_t rco_calc_cum(const uint32_t *c, uint32_t K, uint32_t *cum);
-/* Build-defined extension: identity when the
- * u64 counts sum to <= 2^32-1 (the reference rule), otherwise the smallest
- * right shift sh with (sum>>sh)+K <= 2^32-1, c' = c ? max(1, c>>sh) : 0.
- * Returns the shift used. */
+/* Build-defined extension: identity when the u64 counts sum to <= 2^32-1 (the
+ * reference rule), otherwise rescale to total = 2^31 exactly: c' = c ? max(1, floor(c*2^31/sum)) : 0
+ * and the difference 2^31 - sum(c') is added to the largest count (lowest index on ties).
+ * Returns 1 if rescaled. */
 int rco_normalise(const uint64_t *counts, uint32_t K, uint32_t *c);
 
 /* Chunked drivers used as the CPU baseline ("one chunk per thread at a time").

@@ -158,47 +158,110 @@ __global__ void __launch_bounds__(256) hist_chunks_kernel(const SYM* __restrict_
 //   c   = normalise(counts)            (identity unless a u64 sum > 2^32-1)
 //   cum = exclusive prefix sum of c    (warp-shuffle scan + carry across tiles)
 //   total = sum c
+// Normalisation (build-defined: total_freq is u32 in the reference, src/pmodel.rs:10, and it has
+// no rule for larger sums): when sum > 2^32-1 the counts are rescaled to total = 2^31 exactly,
+//   c'_i = 0 if c_i == 0 else max(1, floor(c_i * 2^31 / sum)),
+// and the difference 2^31 - sum(c') (|.| <= K) is added to the symbol with the largest count
+// (lowest index on ties).  A power-of-two total keeps range/total a shift.  Identical in the oracle.
+__device__ __forceinline__ uint32_t scale_count(unsigned long long c, unsigned long long sum) {
+    if (c == 0) return 0u;
+    const unsigned __int128 q = ((unsigned __int128)c << 31) / sum;
+    const uint32_t v = (uint32_t)q;  // < 2^31
+    return v ? v : 1u;
+}
+
 template <typename CNT>
 __global__ void __launch_bounds__(256) counts_to_tables_kernel(const CNT* __restrict__ counts,
                                                                uint32_t K, uint2* tabs,
                                                                uint32_t* totals) {
     __shared__ unsigned long long s_warp[8];
+    __shared__ unsigned long long s_wmax[8];
+    __shared__ uint32_t s_widx[8];
+    __shared__ unsigned long long s_sum;
     __shared__ unsigned long long s_carry;
-    __shared__ uint32_t s_shift;
+    __shared__ uint32_t s_imax;
+    __shared__ long long s_delta;
     const uint64_t model = blockIdx.x;
     const CNT* cnt = counts + model * K;
     uint2* tab = tabs + model * K;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 
-    // pass 1: sum (u64) to decide the normalisation shift
-    unsigned long long part = 0;
-    for (uint32_t i = threadIdx.x; i < K; i += blockDim.x) part += (unsigned long long)cnt[i];
+    // pass 1: sum (u64) and the position of the largest count (lowest index on ties)
+    unsigned long long part = 0, vmax = 0;
+    uint32_t imax = 0xFFFFFFFFu;
+    for (uint32_t i = threadIdx.x; i < K; i += blockDim.x) {
+        const unsigned long long v = (unsigned long long)cnt[i];
+        part += v;
+        if (v > vmax || (v == vmax && i < imax)) {
+            vmax = v;
+            imax = i;
+        }
+    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
-    if (lane == 0) s_warp[warp] = part;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long sum = 0;
-        for (uint32_t w = 0; w < (blockDim.x >> 5); w++) sum += s_warp[w];
-        uint32_t sh = 0;
-        if (sum > 0xFFFFFFFFull)
-            while ((sum >> sh) + K > 0xFFFFFFFFull) sh++;
-        s_shift = sh;
-        s_carry = 0;
+    for (int o = 16; o > 0; o >>= 1) {
+        part += __shfl_down_sync(0xffffffffu, part, o);
+        const unsigned long long ov = __shfl_down_sync(0xffffffffu, vmax, o);
+        const uint32_t oi = __shfl_down_sync(0xffffffffu, imax, o);
+        if (ov > vmax || (ov == vmax && oi < imax)) {
+            vmax = ov;
+            imax = oi;
+        }
+    }
+    if (lane == 0) {
+        s_warp[warp] = part;
+        s_wmax[warp] = vmax;
+        s_widx[warp] = imax;
     }
     __syncthreads();
-    const uint32_t sh = s_shift;
+    if (threadIdx.x == 0) {
+        unsigned long long sum = 0, bv = 0;
+        uint32_t bi = 0xFFFFFFFFu;
+        for (uint32_t w = 0; w < nwarps; w++) {
+            sum += s_warp[w];
+            if (s_wmax[w] > bv || (s_wmax[w] == bv && s_widx[w] < bi)) {
+                bv = s_wmax[w];
+                bi = s_widx[w];
+            }
+        }
+        s_sum = sum;
+        s_imax = bi;
+        s_carry = 0;
+        s_delta = 0;
+    }
+    __syncthreads();
+    const unsigned long long sum = s_sum;
+    const bool rescale = sum > 0xFFFFFFFFull;
 
-    // pass 2: tiles of blockDim.x symbols, exclusive scan with running carry
+    // pass 2 (only when rescaling): sum of the scaled counts -> correction for the largest symbol
+    if (rescale) {
+        unsigned long long sp = 0;
+        for (uint32_t i = threadIdx.x; i < K; i += blockDim.x) sp += scale_count((unsigned long long)cnt[i], sum);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sp += __shfl_down_sync(0xffffffffu, sp, o);
+        __syncthreads();
+        if (lane == 0) s_warp[warp] = sp;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long t = 0;
+            for (uint32_t w = 0; w < nwarps; w++) t += s_warp[w];
+            s_delta = (long long)(1ull << 31) - (long long)t;
+        }
+        __syncthreads();
+    }
+    const long long delta = s_delta;
+    const uint32_t fix = s_imax;
+
+    // pass 3: tiles of blockDim.x symbols, exclusive scan with running carry
     for (uint32_t base = 0; base < K; base += blockDim.x) {
         uint32_t i = base + threadIdx.x;
         unsigned long long raw = i < K ? (unsigned long long)cnt[i] : 0ull;
-        uint32_t c = 0;
-        if (raw) {
-            unsigned long long s = raw >> sh;
-            c = (uint32_t)(s ? s : 1ull);
+        uint32_t c = (uint32_t)raw;
+        if (rescale) {
+            c = scale_count(raw, sum);
+            if (i == fix) c = (uint32_t)((long long)c + delta);
         }
         uint32_t incl = warp_incl_scan(c, lane);
+        __syncthreads();
         if (lane == 31) s_warp[warp] = incl;
         __syncthreads();
         uint32_t woff = 0;

@@ -80,8 +80,8 @@ def histogram(syms, K):
 def normalise(counts):
     counts = np.ascontiguousarray(counts, dtype=np.uint64)
     c = np.zeros(counts.size, dtype=np.uint32)
-    sh = lib().rco_normalise(_p(counts), counts.size, _p(c))
-    return c, sh
+    scaled = lib().rco_normalise(_p(counts), counts.size, _p(c))
+    return c, scaled
 
 
 def calc_cum(c):

@@ -234,10 +234,11 @@ def test_count_normalisation_above_u32(ctx, oracle):
     d_counts = torch.from_numpy(counts.view(np.int64)).to(ctx.device)
     model = ctx.model_from_counts(d_counts)
     c, cum, total, flags = model.tables()
-    rc, sh = oracle.normalise(counts)
+    rc, scaled = oracle.normalise(counts)
     rcum, rtotal = oracle.calc_cum(rc)
-    assert sh > 0 and total == rtotal and np.array_equal(c, rc) and np.array_equal(cum, rcum)
-    assert c[200] == 0 and c[201] == 1 and not (flags & 1)
+    assert scaled == 1 and total == rtotal == 1 << 31
+    assert np.array_equal(c, rc) and np.array_equal(cum, rcum)
+    assert c[200] == 0 and c[201] == 1 and (flags & 1)  # rescaled totals are powers of two
     used = np.flatnonzero(rc)
     p = rc[used].astype(np.float64)
     syms = rng.choice(used, size=300_000, p=p / p.sum()).astype(np.uint8)
