@@ -175,6 +175,33 @@ int rcb_decode_host(rcb_ctx *ctx, const uint8_t *h_stream, const uint64_t *h_off
                     uint64_t n_syms, int sym_bytes, uint64_t chunk_syms, const rcb_model *m,
                     void *h_syms_out);
 
+/* ---- continued single-stream coder: the reference's per-symbol API ----------
+ * Encoder / Decoder keep (lower_bound, range[, data]) between calls
+ * (src/encoder.rs:7-11, src/decoder.rs:6-12).  These entry points code a slice
+ * of symbols on one GPU lane from a caller-held state and return the new state,
+ * so a host mirror of Encoder::encode / Decoder::decode (include/rcb200.hpp)
+ * needs no CPU arithmetic.  Host pointers; shared model (n_models == 1) only. */
+typedef struct rcb_stream_state {
+    uint64_t lower_bound; /* RangeCoder::lower_bound, src/range_coder.rs:9  */
+    uint64_t range;       /* RangeCoder::range,       src/range_coder.rs:11 */
+    uint64_t data;        /* Decoder::data,           src/decoder.rs:9      */
+    uint64_t consumed;    /* Decoder: code bytes shifted into data (0 = Decoder::new not run yet) */
+    uint32_t status;      /* RCB_ST_* of the last call */
+    uint32_t pad;
+} rcb_stream_state;
+/* RangeCoder::new (src/range_coder.rs:13-20): lower 0, range u64::MAX */
+void rcb_stream_state_init(rcb_stream_state *st);
+/* Encoder::encode for n symbols (src/encoder.rs:24-37); finish != 0 appends
+ * Encoder::finish (src/encoder.rs:40-46).  h_per_symbol (may be NULL) gets each
+ * symbol's emitted byte count -- encode()'s return value.  m may be NULL when
+ * n_syms == 0 (finish alone). */
+int rcb_encode_stream(rcb_ctx *ctx, rcb_stream_state *st, const void *h_syms, uint64_t n_syms,
+                      int sym_bytes, const rcb_model *m, uint8_t *h_out, uint64_t out_cap,
+                      uint64_t *h_n_out, uint32_t *h_per_symbol, int finish);
+/* Decoder::new on the first call, then Decoder::decode n times (src/decoder.rs:14-54). */
+int rcb_decode_stream(rcb_ctx *ctx, rcb_stream_state *st, const uint8_t *h_code, uint64_t code_len,
+                      uint64_t n_syms, int sym_bytes, const rcb_model *m, void *h_syms_out);
+
 /* ---- synthetic data (benchmark inputs; not in the reference)
  * symbol j = #{ i < K-1 : thr[t][i] <= mix64(seed + j*GOLDEN) >> 32 },
  * t = (j / chunk_syms) % n_tables; h_thr = uint32[n_tables][K-1]. */

@@ -1,0 +1,270 @@
+// rcb200.hpp -- host-side mirror of the reference crate's public API
+// (diegodox/range_coder_rust, src/lib.rs:1-13) on top of the C ABI in rcb200.h.
+//
+// The reference is Rust; this image has no Rust toolchain, so the host side is
+// C++ with the same names, argument meaning and error behaviour:
+//   range_coder::PModel            src/pmodel.rs:4-41
+//   range_coder::RangeCoder        src/range_coder.rs:7-40,138-146
+//   range_coder::Encoder           src/encoder.rs:7-55
+//   range_coder::Decoder           src/decoder.rs:6-55
+//   range_coder::error::RangeCoderError  src/error.rs:3-13
+// plus range_coder::gpu::{encode_chunks, decode_chunks}: the bulk entry points a
+// caller switches its per-symbol loops to (INTEGRATION.md shows the Rust binding).
+//
+// Every arithmetic step runs on the GPU (rcb_encode_stream / rcb_decode_stream /
+// rcb_*_chunks); nothing here codes symbols on the CPU.  Where the reference
+// panics (unwrap on an Err, divide by zero, pop_front on an empty buffer) these
+// types throw; where it would never return (a coded symbol with c_freq == 0)
+// they throw RangeCoderPanic("zero frequency").
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <deque>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "rcb200.h"
+
+namespace range_coder {
+
+namespace error {
+// src/error.rs:3-13
+struct RangeCoderError : std::runtime_error {
+    enum Kind { LowerBoundOverflow, UpperBoundOverflow } kind;
+    uint64_t lower_bound, add_val, range;
+    RangeCoderError(Kind k, uint64_t lo, uint64_t add, uint64_t rg)
+        : std::runtime_error(k == LowerBoundOverflow
+                                 ? "Overflow happend while lower_bound uppdating " + std::to_string(lo) + " + " +
+                                       std::to_string(add) + " , " + std::to_string(rg)
+                                 : "Overflow happend when calc upper_bound " + std::to_string(lo) + " + " +
+                                       std::to_string(rg)),
+          kind(k), lower_bound(lo), add_val(add), range(rg) {}
+};
+}  // namespace error
+
+// what a Rust panic (unwrap, divide by zero, index out of bounds) becomes here
+struct RangeCoderPanic : std::runtime_error {
+    int code;  // rcb_error
+    RangeCoderPanic(int c, const std::string& where) : std::runtime_error(where + ": " + rcb_strerror(c)), code(c) {}
+};
+
+inline void check(int rc, const char* where, const rcb_stream_state* st = nullptr) {
+    if (rc == RCB_OK) return;
+    if (st && rc == RCB_ERR_LOWER_OVERFLOW)
+        throw error::RangeCoderError(error::RangeCoderError::LowerBoundOverflow, st->lower_bound, 0, st->range);
+    if (st && rc == RCB_ERR_UPPER_OVERFLOW)
+        throw error::RangeCoderError(error::RangeCoderError::UpperBoundOverflow, st->lower_bound, 0, st->range);
+    throw RangeCoderPanic(rc, where);
+}
+
+// One GPU context per thread (the reference's types are single-threaded owned values).
+class Context {
+public:
+    explicit Context(int device = 0) { check(rcb_ctx_create(device, nullptr, &h_), "rcb_ctx_create"); }
+    ~Context() { rcb_ctx_destroy(h_); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    rcb_ctx* handle() const { return h_; }
+    static Context& thread_default() {
+        thread_local Context ctx(0);
+        return ctx;
+    }
+
+private:
+    rcb_ctx* h_ = nullptr;
+};
+
+class Decoder;
+
+// src/pmodel.rs:4-41.  The trait has no alphabet-size method; a GPU kernel needs one to
+// snapshot the tables, so alphabet_count() (examples/sample_impl.rs:55-57) is part of the mirror.
+class PModel {
+public:
+    virtual ~PModel() = default;
+    virtual uint32_t c_freq(size_t index) const = 0;
+    virtual uint32_t cum_freq(size_t index) const = 0;
+    virtual uint32_t total_freq() const = 0;
+    virtual size_t alphabet_count() const = 0;
+    // Not consulted by the GPU path: the lookup of examples/sample_impl.rs:27-45 is built in.
+    virtual size_t find_index(const Decoder&) const { throw std::logic_error("find_index runs on the GPU"); }
+    // src/pmodel.rs:14-40 (f64 diagnostic, never used by the coder)
+    double ideal_code_length(size_t index) const {
+        double p = (double)c_freq(index);
+        if (p == 0.0) throw std::domain_error("code length is undefind when probability is zero");
+        return (std::log((double)total_freq()) - std::log(p)) / std::log(2.0);
+    }
+};
+
+// Dense device snapshot of a PModel (the table boundary of SURVEY 8 b2).
+class ModelSnapshot {
+public:
+    ModelSnapshot(Context& ctx, const PModel& pm) : ctx_(ctx), K_((uint32_t)pm.alphabet_count()) {
+        std::vector<uint32_t> c(K_), cum(K_);
+        for (uint32_t i = 0; i < K_; i++) {
+            c[i] = pm.c_freq(i);
+            cum[i] = pm.cum_freq(i);
+        }
+        uint32_t total = pm.total_freq();
+        check(rcb_model_create(ctx.handle(), K_, 1, &m_), "rcb_model_create");
+        int rc = rcb_model_from_tables(ctx.handle(), m_, c.data(), cum.data(), &total);
+        if (rc) {
+            rcb_model_destroy(m_);
+            check(rc, "rcb_model_from_tables");  // total_freq == 0: the reference divides by zero
+        }
+    }
+    ~ModelSnapshot() { rcb_model_destroy(m_); }
+    ModelSnapshot(const ModelSnapshot&) = delete;
+    ModelSnapshot& operator=(const ModelSnapshot&) = delete;
+    const rcb_model* handle() const { return m_; }
+    uint32_t alphabet_count() const { return K_; }
+    int sym_bytes() const { return K_ <= 256 ? 1 : 2; }
+
+private:
+    Context& ctx_;
+    uint32_t K_;
+    rcb_model* m_ = nullptr;
+};
+
+// src/range_coder.rs:7-40,138-146 (state + getters; the update runs on the GPU)
+class RangeCoder {
+public:
+    RangeCoder() { rcb_stream_state_init(&st_); }
+    uint64_t lower_bound() const { return st_.lower_bound; }
+    uint64_t range() const { return st_.range; }
+    uint64_t range_par_total(uint32_t total_freq) const {
+        if (total_freq == 0) throw RangeCoderPanic(RCB_ERR_ZERO_TOTAL, "range_par_total");
+        return st_.range / (uint64_t)total_freq;
+    }
+    uint64_t upper_bound() const {
+        uint64_t u = st_.lower_bound + st_.range;
+        if (u < st_.lower_bound)
+            throw error::RangeCoderError(error::RangeCoderError::UpperBoundOverflow, st_.lower_bound, 0, st_.range);
+        return u;
+    }
+    rcb_stream_state& state() { return st_; }
+    const rcb_stream_state& state() const { return st_; }
+
+private:
+    rcb_stream_state st_;
+};
+
+// src/encoder.rs:7-55
+class Encoder {
+public:
+    RangeCoder range_coder;  // pub field in the reference (src/encoder.rs:8)
+    explicit Encoder(Context& ctx = Context::thread_default()) : ctx_(ctx) {}
+    const std::deque<uint8_t>& peek_code() const { return code_; }
+    // one symbol; returns the number of bytes it produced (computed on the GPU)
+    uint32_t encode(const PModel& pmodel, size_t index) {
+        ModelSnapshot snap(ctx_, pmodel);
+        return encode(snap, index);
+    }
+    uint32_t encode(const ModelSnapshot& snap, size_t index) {
+        uint8_t sym[2] = {(uint8_t)index, (uint8_t)(index >> 8)};
+        if (index >= snap.alphabet_count()) throw RangeCoderPanic(RCB_ERR_SYMBOL_OUT_OF_RANGE, "Encoder::encode");
+        uint8_t out[16];
+        uint64_t n = 0;
+        check(rcb_encode_stream(ctx_.handle(), &range_coder.state(), sym, 1, snap.sym_bytes(), snap.handle(), out,
+                                sizeof out, &n, nullptr, 0),
+              "Encoder::encode", &range_coder.state());
+        code_.insert(code_.end(), out, out + n);
+        return (uint32_t)n;
+    }
+    // a slice of symbols in one call (same bytes as calling encode() once per symbol)
+    template <class Sym>
+    void encode_slice(const ModelSnapshot& snap, const Sym* syms, size_t n) {
+        static_assert(sizeof(Sym) == 1 || sizeof(Sym) == 2, "u8 or u16 symbols");
+        if ((int)sizeof(Sym) != snap.sym_bytes()) throw std::invalid_argument("symbol width does not match K");
+        std::vector<uint8_t> out(n * 8 + 64);
+        uint64_t produced = 0;
+        check(rcb_encode_stream(ctx_.handle(), &range_coder.state(), syms, n, (int)sizeof(Sym), snap.handle(),
+                                out.data(), out.size(), &produced, nullptr, 0),
+              "Encoder::encode_slice", &range_coder.state());
+        code_.insert(code_.end(), out.begin(), out.begin() + produced);
+    }
+    // src/encoder.rs:40-46: consumes the encoder
+    std::deque<uint8_t> finish() {
+        uint8_t out[8];
+        uint64_t n = 0;
+        check(rcb_encode_stream(ctx_.handle(), &range_coder.state(), nullptr, 0, 1, nullptr, out, sizeof out, &n,
+                                nullptr, 1),
+              "Encoder::finish");
+        code_.insert(code_.end(), out, out + n);
+        return std::move(code_);
+    }
+
+private:
+    Context& ctx_;
+    std::deque<uint8_t> code_;
+};
+
+// src/decoder.rs:6-55
+class Decoder {
+public:
+    template <class Bytes>
+    explicit Decoder(const Bytes& code, Context& ctx = Context::thread_default())
+        : ctx_(ctx), buffer_(code.begin(), code.end()) {
+        if (buffer_.size() < 8) throw RangeCoderPanic(RCB_ERR_TRUNCATED_STREAM, "Decoder::new");  // decoder.rs:33
+    }
+    const RangeCoder& range_coder() const { return rc_; }
+    uint64_t data() const { return rc_.state().data; }
+    size_t decode(const PModel& pmodel) {
+        ModelSnapshot snap(ctx_, pmodel);
+        return decode(snap);
+    }
+    size_t decode(const ModelSnapshot& snap) {
+        uint8_t sym[2] = {0, 0};
+        check(rcb_decode_stream(ctx_.handle(), &rc_.state(), buffer_.data(), buffer_.size(), 1, snap.sym_bytes(),
+                                snap.handle(), sym),
+              "Decoder::decode", &rc_.state());
+        return (size_t)sym[0] | ((size_t)sym[1] << 8);
+    }
+    template <class Sym>
+    std::vector<Sym> decode_n(const ModelSnapshot& snap, size_t n) {
+        std::vector<Sym> out(n);
+        check(rcb_decode_stream(ctx_.handle(), &rc_.state(), buffer_.data(), buffer_.size(), n, (int)sizeof(Sym),
+                                snap.handle(), out.data()),
+              "Decoder::decode_n", &rc_.state());
+        return out;
+    }
+
+private:
+    Context& ctx_;
+    RangeCoder rc_;
+    std::vector<uint8_t> buffer_;
+};
+
+// Bulk entry points: every chunk of chunk_syms symbols is one independent Encoder run.
+namespace gpu {
+struct Encoded {
+    std::vector<uint8_t> stream;     // concatenated Encoder::finish() outputs
+    std::vector<uint64_t> offsets;   // chunk i = stream[offsets[i] .. offsets[i+1])
+};
+template <class Sym>
+Encoded encode_chunks(Context& ctx, const ModelSnapshot& snap, const std::vector<Sym>& syms, uint64_t chunk_syms) {
+    const uint64_t n = syms.size(), n_chunks = chunk_syms ? (n + chunk_syms - 1) / chunk_syms : 0;
+    Encoded e;
+    e.offsets.resize(n_chunks + 1);
+    e.stream.resize(rcb_encode_bound(ctx.handle(), snap.handle(), n, (int)sizeof(Sym), chunk_syms) + 16);
+    uint64_t bytes = 0;
+    check(rcb_encode_host(ctx.handle(), syms.data(), n, (int)sizeof(Sym), chunk_syms, snap.handle(), e.stream.data(),
+                          e.stream.size(), e.offsets.data(), &bytes),
+          "gpu::encode_chunks");
+    e.stream.resize(bytes);
+    return e;
+}
+template <class Sym>
+std::vector<Sym> decode_chunks(Context& ctx, const ModelSnapshot& snap, const Encoded& e, uint64_t n_syms,
+                               uint64_t chunk_syms) {
+    std::vector<Sym> out(n_syms);
+    std::vector<uint8_t> padded(e.stream);
+    padded.resize((padded.size() + 31) & ~size_t(15));
+    check(rcb_decode_host(ctx.handle(), padded.data(), e.offsets.data(), n_syms, (int)sizeof(Sym), chunk_syms,
+                          snap.handle(), out.data()),
+          "gpu::decode_chunks");
+    return out;
+}
+}  // namespace gpu
+
+}  // namespace range_coder

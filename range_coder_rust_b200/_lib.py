@@ -47,6 +47,9 @@ SIGNATURES = {
     "rcb_decode_result": (ci, [vp]),
     "rcb_encode_host": (ci, [vp, vp, u64, ci, u64, vp, vp, u64, vp, u64p]),
     "rcb_decode_host": (ci, [vp, vp, vp, u64, ci, u64, vp, vp]),
+    "rcb_stream_state_init": (None, [vp]),
+    "rcb_encode_stream": (ci, [vp, vp, vp, u64, ci, vp, vp, u64, u64p, vp, ci]),
+    "rcb_decode_stream": (ci, [vp, vp, vp, u64, u64, ci, vp, vp]),
     "rcb_generate": (ci, [vp, vp, u64, u64, ci, u32, u64, vp, u32, u64]),
 }
 

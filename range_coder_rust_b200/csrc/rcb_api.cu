@@ -11,6 +11,7 @@
 
 #include "../../include/rcb200.h"
 #include "rcb_kernels.cuh"
+#include "rcb_stream.cuh"
 
 using namespace rcb;
 
@@ -815,5 +816,81 @@ extern "C" int rcb_generate(rcb_ctx* c, void* d_out, uint64_t first, uint64_t n,
         c->last_err = e;
         return RCB_ERR_CUDA;
     }
+    return RCB_OK;
+}
+
+// ------------------------------------------------ continued single-stream coder
+static_assert(sizeof(rcb_stream_state) == sizeof(StreamState), "rcb_stream_state layout");
+
+extern "C" void rcb_stream_state_init(rcb_stream_state* st) {
+    if (!st) return;
+    memset(st, 0, sizeof *st);
+    st->range = ~0ull;  // src/range_coder.rs:13-20
+}
+
+extern "C" int rcb_encode_stream(rcb_ctx* c, rcb_stream_state* st, const void* h_syms, uint64_t n_syms,
+                                 int sym_bytes, const rcb_model* m, uint8_t* h_out, uint64_t out_cap,
+                                 uint64_t* h_n_out, uint32_t* h_per_symbol, int finish) {
+    if (!c || !st || !h_n_out) return RCB_ERR_INVALID_ARGUMENT;
+    if (n_syms && (!m || !m->ready || m->ctx != c)) return RCB_ERR_INVALID_ARGUMENT;  // finish alone: no model
+    if (m && m->n_models != 1) return RCB_ERR_UNSUPPORTED;
+    if (sym_bytes != 1 && sym_bytes != 2) return RCB_ERR_UNSUPPORTED;
+    if ((n_syms && !h_syms) || (out_cap && !h_out)) return RCB_ERR_INVALID_ARGUMENT;
+    CK(c, cudaSetDevice(c->device));
+    const size_t sym_b = (size_t)((n_syms * sym_bytes + 15) & ~15ull);
+    const size_t out_b = (size_t)((out_cap + 15) & ~15ull);
+    const size_t per_b = (size_t)((n_syms * 4 + 15) & ~15ull);
+    int r = ensure_h2d(c, 64 + sym_b + out_b + per_b + 16);
+    if (r) return r;
+    uint8_t* base = (uint8_t*)c->h2d;
+    StreamState* d_st = (StreamState*)base;
+    uint64_t* d_n = (uint64_t*)(base + 48);
+    uint8_t* d_syms = base + 64;
+    uint8_t* d_out = d_syms + sym_b;
+    uint32_t* d_per = (uint32_t*)(d_out + out_b);
+    CK(c, cudaMemcpyAsync(d_st, st, sizeof(StreamState), cudaMemcpyHostToDevice, c->stream));
+    if (n_syms) CK(c, cudaMemcpyAsync(d_syms, h_syms, n_syms * sym_bytes, cudaMemcpyHostToDevice, c->stream));
+    encode_stream_kernel<<<1, 1, 0, c->stream>>>(d_st, d_syms, n_syms, sym_bytes, m ? m->d_tab : nullptr,
+                                                  m ? m->d_hdr : nullptr, m ? m->K : 0u, d_out, out_cap, d_n,
+                                                  h_per_symbol ? d_per : nullptr, finish);
+    CK_LAUNCH(c);
+    uint64_t n_out = 0;
+    CK(c, cudaMemcpyAsync(st, d_st, sizeof(StreamState), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(&n_out, d_n, sizeof n_out, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    *h_n_out = n_out;
+    if (st->status) return status_to_error(st->status);
+    if (n_out) CK(c, cudaMemcpyAsync(h_out, d_out, n_out, cudaMemcpyDeviceToHost, c->stream));
+    if (h_per_symbol && n_syms)
+        CK(c, cudaMemcpyAsync(h_per_symbol, d_per, n_syms * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return RCB_OK;
+}
+
+extern "C" int rcb_decode_stream(rcb_ctx* c, rcb_stream_state* st, const uint8_t* h_code, uint64_t code_len,
+                                 uint64_t n_syms, int sym_bytes, const rcb_model* m, void* h_syms_out) {
+    if (!c || !st || !m || !m->ready || m->ctx != c) return RCB_ERR_INVALID_ARGUMENT;
+    if (m->n_models != 1) return RCB_ERR_UNSUPPORTED;
+    if (sym_bytes != 1 && sym_bytes != 2) return RCB_ERR_UNSUPPORTED;
+    if ((code_len && !h_code) || (n_syms && !h_syms_out)) return RCB_ERR_INVALID_ARGUMENT;
+    CK(c, cudaSetDevice(c->device));
+    const size_t code_b = (size_t)((code_len + 15) & ~15ull);
+    const size_t sym_b = (size_t)((n_syms * sym_bytes + 15) & ~15ull);
+    int r = ensure_h2d(c, 64 + code_b + sym_b + 16);
+    if (r) return r;
+    uint8_t* base = (uint8_t*)c->h2d;
+    StreamState* d_st = (StreamState*)base;
+    uint8_t* d_code = base + 64;
+    uint8_t* d_syms = d_code + code_b;
+    CK(c, cudaMemcpyAsync(d_st, st, sizeof(StreamState), cudaMemcpyHostToDevice, c->stream));
+    if (code_len) CK(c, cudaMemcpyAsync(d_code, h_code, code_len, cudaMemcpyHostToDevice, c->stream));
+    decode_stream_kernel<<<1, 1, 0, c->stream>>>(d_st, d_code, code_len, n_syms, sym_bytes, m->d_tab, m->d_hdr, m->K,
+                                                  d_syms);
+    CK_LAUNCH(c);
+    CK(c, cudaMemcpyAsync(st, d_st, sizeof(StreamState), cudaMemcpyDeviceToHost, c->stream));
+    if (n_syms)
+        CK(c, cudaMemcpyAsync(h_syms_out, d_syms, n_syms * sym_bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (st->status) return status_to_error(st->status);
     return RCB_OK;
 }
