@@ -27,7 +27,7 @@ static_assert((int)RCB_MODEL_REGULAR == (int)MODEL_REGULAR, "model flags");
 struct rcb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    int enc_threads = 128, dec_threads = 128;
+    int enc_threads = 0, dec_threads = 0;  // 0 = choose from the lane count
     int sm_count = 148;
     uint8_t* staging = nullptr;
     size_t staging_bytes = 0;
@@ -189,10 +189,10 @@ extern "C" int rcb_ctx_synchronize(rcb_ctx* c) {
 
 extern "C" int rcb_ctx_set_block_threads(rcb_ctx* c, int enc, int dec) {
     if (!c) return RCB_ERR_INVALID_ARGUMENT;
-    auto okv = [](int v) { return v == 0 || (v >= 32 && v <= 256 && v % 32 == 0); };
+    auto okv = [](int v) { return v == 0 || (v >= 32 && v <= 512 && v % 32 == 0); };
     if (!okv(enc) || !okv(dec)) return RCB_ERR_INVALID_ARGUMENT;
-    c->enc_threads = enc ? enc : 128;
-    c->dec_threads = dec ? dec : 128;
+    c->enc_threads = enc;
+    c->dec_threads = dec;
     return RCB_OK;
 }
 
@@ -223,6 +223,17 @@ extern "C" int rcb_ctx_get_timings(rcb_ctx* c, float* ms, int n) {
     }
     for (int i = 0; i < n && i < 5; i++) ms[i] = v[i];
     return RCB_OK;
+}
+
+// Threads per block of the coder kernels.  One lane per chunk: with few lanes (<= 128 per SM) small
+// blocks spread the warps over all SMs (latency-bound regime, one warp per scheduler); with many
+// lanes bigger blocks share one copy of the shared-memory tables (throughput regime).
+static int pick_threads(const rcb_ctx* c, int user, uint64_t n_chunks) {
+    if (user) return user;
+    const uint64_t sms = (uint64_t)(c->sm_count > 0 ? c->sm_count : 148);
+    if (n_chunks > sms * 512) return 512;
+    if (n_chunks > sms * 128) return 256;
+    return 128;
 }
 
 static int ensure_chunks(rcb_ctx* c, uint64_t n_chunks) {
@@ -455,43 +466,82 @@ extern "C" uint64_t rcb_encode_bound(rcb_ctx* c, const rcb_model* m, uint64_t n_
     return n_chunks * staging_pitch(m, chunk_syms) + 16;
 }
 
-template <typename SYM>
-static void launch_encode_variant(rcb_ctx* c, const rcb_model* m, const EncodeArgs& a, int threads,
-                                  unsigned blocks) {
+// Launch geometry and kernel flavour of one encode call.
+struct EncPlan {
+    int table;      // TAB_*
+    int fmode;      // FM_*
+    bool checked;
+    int threads;
+    uint32_t lanes; // chunks per block
+    size_t smem;
+};
+
+static EncPlan plan_encode(const rcb_ctx* c, const rcb_model* m, uint64_t n_chunks) {
+    EncPlan p;
     const bool shared = m->n_models == 1;
-    const bool pow2 = shared && (m->h_hdr0.flags & MODEL_POW2);
-    const bool checked = (m->bad_bits & 4u) != 0;
-    const bool rangechk = (uint64_t)m->K < (1ull << (8 * sizeof(SYM)));
-    const size_t smem = shared ? (size_t)m->K * sizeof(uint2) : 0;
-#define RCB_ENC(SH, P2, CH, RC, FU)                                                                    \
-    do {                                                                                               \
-        auto kern = encode_kernel<SYM, SH, P2, CH, RC, FU>;                                            \
-        if (smem > 48 * 1024)                                                                          \
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
-        kern<<<blocks, threads, smem, c->stream>>>(a);                                                 \
-    } while (0)
-#define RCB_ENC_RC(SH, P2, CH, FU)                   \
-    do {                                             \
-        if (rangechk) RCB_ENC(SH, P2, CH, true, FU); \
-        else RCB_ENC(SH, P2, CH, false, FU);         \
-    } while (0)
+    p.checked = (m->bad_bits & 4u) != 0;
+    const bool regular = (m->bad_bits & 8u) == 0;
+    p.threads = pick_threads(c, c->enc_threads, n_chunks);
     if (shared) {
-        if (pow2) {
-            // FUSED: range/total and the renormalisation shift collapse into one shift
-            const bool fused = !checked && m->h_hdr0.div.shift >= 24;
-            if (fused) RCB_ENC_RC(true, true, false, true);
-            else if (checked) RCB_ENC_RC(true, true, true, false);
-            else RCB_ENC_RC(true, true, false, false);
-        } else {
-            if (checked) RCB_ENC_RC(true, false, true, false);
-            else RCB_ENC_RC(true, false, false, false);
-        }
-    } else {
-        if (checked) RCB_ENC_RC(false, false, true, false);
-        else RCB_ENC_RC(false, false, false, false);
+        p.table = TAB_SHARED;
+        const bool pow2 = (m->h_hdr0.flags & MODEL_POW2) != 0;
+        p.fmode = p.checked ? FM_GENERIC : (pow2 ? (m->h_hdr0.div.shift >= 24 ? FM_BIG : FM_POW2) : FM_GEN);
+        p.lanes = (uint32_t)p.threads;
+        p.smem = (size_t)m->K * sizeof(uint2);
+        return p;
     }
-#undef RCB_ENC_RC
-#undef RCB_ENC
+    // per-chunk models: each lane's cum[K+1] in its own shared-memory row when it fits
+    const size_t row = ((size_t)m->K + 1) * sizeof(uint32_t);
+    const size_t budget = 220 * 1024;
+    const uint32_t lmax = (uint32_t)(budget / row);
+    if (!p.checked && regular && lmax >= 32) {
+        p.table = TAB_LANE;
+        p.fmode = FM_LANE;
+        uint32_t L = lmax < 512u ? lmax : 512u;
+        const uint64_t sms = (uint64_t)(c->sm_count > 0 ? c->sm_count : 148);
+        const uint64_t even = (n_chunks + sms - 1) / sms;  // one wave, all SMs busy, when it fits
+        if (even <= L) L = (uint32_t)(even ? even : 1);
+        if (c->enc_threads && (uint32_t)c->enc_threads < L) L = (uint32_t)c->enc_threads;
+        p.lanes = L;
+        p.threads = (int)((L + 31) / 32 * 32);
+        p.smem = (size_t)L * row;
+        return p;
+    }
+    p.table = TAB_GLOBAL;
+    p.fmode = FM_GENERIC;
+    p.lanes = (uint32_t)p.threads;
+    p.smem = 0;
+    return p;
+}
+
+template <typename SYM, int TABLE, int FMODE, bool CHECKED>
+static void launch_encode_rc(rcb_ctx* c, const EncodeArgs& a, const EncPlan& p, unsigned blocks, bool rangechk) {
+    auto go = [&](auto kern) {
+        if (p.smem > 48 * 1024)
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+        kern<<<blocks, p.threads, p.smem, c->stream>>>(a);
+    };
+    if (rangechk) go(encode_kernel<SYM, TABLE, FMODE, CHECKED, true>);
+    else go(encode_kernel<SYM, TABLE, FMODE, CHECKED, false>);
+}
+
+template <typename SYM>
+static void launch_encode_variant(rcb_ctx* c, const rcb_model* m, const EncodeArgs& a, const EncPlan& p,
+                                  unsigned blocks) {
+    const bool rangechk = (uint64_t)m->K < (1ull << (8 * sizeof(SYM)));
+    if (p.table == TAB_SHARED) {
+        switch (p.fmode) {
+            case FM_BIG: launch_encode_rc<SYM, TAB_SHARED, FM_BIG, false>(c, a, p, blocks, rangechk); break;
+            case FM_POW2: launch_encode_rc<SYM, TAB_SHARED, FM_POW2, false>(c, a, p, blocks, rangechk); break;
+            case FM_GEN: launch_encode_rc<SYM, TAB_SHARED, FM_GEN, false>(c, a, p, blocks, rangechk); break;
+            default: launch_encode_rc<SYM, TAB_SHARED, FM_GENERIC, true>(c, a, p, blocks, rangechk); break;
+        }
+    } else if (p.table == TAB_LANE) {
+        launch_encode_rc<SYM, TAB_LANE, FM_LANE, false>(c, a, p, blocks, rangechk);
+    } else {
+        if (p.checked) launch_encode_rc<SYM, TAB_GLOBAL, FM_GENERIC, true>(c, a, p, blocks, rangechk);
+        else launch_encode_rc<SYM, TAB_GLOBAL, FM_GENERIC, false>(c, a, p, blocks, rangechk);
+    }
 }
 
 static int encode_launch(rcb_ctx* c, const void* d_syms, uint64_t n_syms, int sym_bytes, uint64_t chunk_syms,
@@ -535,18 +585,18 @@ static int encode_launch(rcb_ctx* c, const void* d_syms, uint64_t n_syms, int sy
     a.tabs = m->d_tab;
     a.hdrs = m->d_hdr;
     a.K = m->K;
-    a.per_chunk = m->n_models != 1;
     a.staging = c->staging;
     a.pitch = pitch;
     a.lens = c->lens;
     a.status = d_status ? d_status : c->status;
-    const int threads = c->enc_threads;
-    const unsigned blocks = (unsigned)((n_chunks + threads - 1) / threads);
+    const EncPlan plan = plan_encode(c, m, n_chunks);
+    a.lanes_per_block = plan.lanes;
+    const unsigned blocks = (unsigned)((n_chunks + plan.lanes - 1) / plan.lanes);
     EV(c, 0);
     if (sym_bytes == 1)
-        launch_encode_variant<uint8_t>(c, m, a, threads, blocks);
+        launch_encode_variant<uint8_t>(c, m, a, plan, blocks);
     else
-        launch_encode_variant<uint16_t>(c, m, a, threads, blocks);
+        launch_encode_variant<uint16_t>(c, m, a, plan, blocks);
     CK_LAUNCH(c);
     EV(c, 1);
     scan_lengths_kernel<<<1, 1024, 0, c->stream>>>(c->lens, a.status, n_chunks, d_offsets, c->d_summary);
@@ -681,7 +731,7 @@ extern "C" int rcb_decode_chunks_async(rcb_ctx* c, const uint8_t* d_stream, cons
     a.per_chunk = m->n_models != 1;
     a.out = d_syms_out;
     a.status = d_status ? d_status : c->status;
-    const int threads = c->dec_threads;
+    const int threads = pick_threads(c, c->dec_threads, n_chunks);
     const unsigned blocks = (unsigned)((n_chunks + threads - 1) / threads);
     EV(c, 4);
     if (sym_bytes == 1)

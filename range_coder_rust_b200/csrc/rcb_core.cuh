@@ -295,12 +295,33 @@ struct EncSink {
 // caller renormalises (nlo, rgp) with renorm_slow.  hi/sh describe the bytes to
 // emit: the top sh/8 bytes of lower'.
 // ---------------------------------------------------------------------------
+// Three flavours of the same step (the lane always carries rpt = range / total):
+//   FUSE_BIG   total = 2^s, 24 <= s <= 31: rpt_next = range' >> (s - sh)      (one shift)
+//   FUSE_POW2  total = 2^s, any s        : rpt_next = (range' << sh) >> s     (two shifts)
+//   FUSE_GEN   any total                 : rpt_next = (range' << sh) / total  (multiply-high reciprocal)
+enum : int { FUSE_BIG = 0, FUSE_POW2 = 1, FUSE_GEN = 2 };
+
 struct FusedParams {
-    uint32_t s;      // log2(total)
-    uint32_t k0;     // s - 24: shift when n1 == 3
-    uint32_t thr;    // 2^(48 - s)
+    uint32_t s;      // log2(total) (power-of-two totals)
+    uint32_t k0;     // s - 24 (FUSE_BIG): shift when n1 == 3
+    DivParams div;   // FUSE_GEN
 };
 
+RCB_HD FusedParams make_fused(const DivParams& div) {
+    FusedParams fp;
+    fp.s = div.shift;
+    fp.k0 = div.shift >= 24u ? div.shift - 24u : 0u;
+    fp.div = div;
+    return fp;
+}
+
+// rpt of a lane that holds `range` (start of a chunk, or after the exact path)
+template <int MODE>
+RCB_HD uint64_t fused_rpt(uint64_t range, const FusedParams& fp) {
+    return MODE == FUSE_GEN ? range_par_total<false>(range, fp.div) : (range >> fp.s);
+}
+
+template <int MODE = FUSE_BIG>
 RCB_HD bool fused_step(uint64_t lo, uint64_t rpt, uint32_t cum, uint32_t c, const FusedParams& fp,
                        uint64_t& nlo, uint64_t& rgp, uint64_t& nrpt, uint32_t& sh) {
     nlo = lo + rpt * (uint64_t)cum;
@@ -308,9 +329,14 @@ RCB_HD bool fused_step(uint64_t lo, uint64_t rpt, uint32_t cum, uint32_t c, cons
     rgp = rpt * (uint64_t)c;
     const uint32_t xh = hi32(nlo) ^ hi32(up);
     const bool p1 = xh < (1u << 24), p2 = xh < (1u << 16), p3 = xh < (1u << 8);
-    const uint32_t k = p2 ? (p3 ? fp.k0 : fp.k0 + 8u) : (p1 ? fp.k0 + 16u : fp.k0 + 24u);
-    sh = (fp.k0 + 24u) - k;
-    nrpt = rgp >> k;
+    if (MODE == FUSE_BIG) {
+        const uint32_t k = p2 ? (p3 ? fp.k0 : fp.k0 + 8u) : (p1 ? fp.k0 + 16u : fp.k0 + 24u);
+        sh = (fp.k0 + 24u) - k;
+        nrpt = rgp >> k;
+    } else {
+        sh = p2 ? (p3 ? 24u : 16u) : (p1 ? 8u : 0u);
+        nrpt = fused_rpt<MODE>(rgp << sh, fp);
+    }
     // loop 2 stays idle iff range' << sh >= 2^48 iff range' >= 2^(48-sh): a test on the high word
     // of range' against 2^16 / 2^8 / 1 (exact for n1 <= 2; n1 == 3 and n1 >= 4, where the high
     // word is 0, conservatively take the literal loops).  Ready as early as the shift amount.
@@ -489,6 +515,7 @@ struct FusedDec {
     bool ok;      // ... and the fast renormalisation applies
 };
 
+template <int MODE = FUSE_BIG>
 RCB_HD FusedDec fused_decode_step(uint64_t lo, uint64_t rpt, uint64_t data, const LutEntry& e,
                                   const FusedParams& fp) {
     FusedDec r;
@@ -503,9 +530,14 @@ RCB_HD FusedDec fused_decode_step(uint64_t lo, uint64_t rpt, uint64_t data, cons
     r.rgp = up - r.nlo;
     const uint32_t xh = hi32(r.nlo) ^ hi32(up);
     const bool p1 = xh < (1u << 24), p2 = xh < (1u << 16), p3 = xh < (1u << 8);
-    const uint32_t k = p2 ? (p3 ? fp.k0 : fp.k0 + 8u) : (p1 ? fp.k0 + 16u : fp.k0 + 24u);
-    r.sh = (fp.k0 + 24u) - k;
-    r.nrpt = r.rgp >> k;
+    if (MODE == FUSE_BIG) {
+        const uint32_t k = p2 ? (p3 ? fp.k0 : fp.k0 + 8u) : (p1 ? fp.k0 + 16u : fp.k0 + 24u);
+        r.sh = (fp.k0 + 24u) - k;
+        r.nrpt = r.rgp >> k;
+    } else {
+        r.sh = p2 ? (p3 ? 24u : 16u) : (p1 ? 8u : 0u);
+        r.nrpt = fused_rpt<MODE>(r.rgp << r.sh, fp);
+    }
     const uint32_t need = p2 ? 1u : (p1 ? (1u << 8) : (1u << 16));  // see fused_step
     r.inside = inside;
     r.ok = inside & (hi32(r.rgp) >= need);

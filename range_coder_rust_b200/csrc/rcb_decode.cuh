@@ -185,7 +185,7 @@ __device__ __noinline__ DecLaneState dec_exact(DecLaneState s, const uint2* tab,
     sink.wh = s.wh;
     sink.wl = s.wl;
     sink.cnt = s.cnt;
-    const FusedParams fp{div.shift, div.shift - 24u, 1u << (48u - div.shift)};
+    const FusedParams fp = make_fused(div);
     uint32_t acc = 0;
 #pragma unroll 1
     for (uint32_t b = 0; b < n_syms; b++) {
@@ -217,7 +217,7 @@ __device__ __noinline__ DecLaneState dec_exact(DecLaneState s, const uint2* tab,
 }
 
 template <typename SYM, bool SHARED, bool POW2, bool CHECKED, bool FUSED>
-__global__ void __launch_bounds__(256, 1) decode_kernel(DecodeArgs a) {
+__global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
     extern __shared__ __align__(16) uint8_t s_raw[];
     __shared__ ModelHdr s_hdr;
     // shared layout: rings[blockDim.x][RING_STRIDE] | LutEntry[nb or 4096] | uint2[K]
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(256, 1) decode_kernel(DecodeArgs a) {
     const uint64_t nw = aligned ? cnt / PER : 0;
 
     if constexpr (FUSED) {
-        const FusedParams fp{div.shift, div.shift - 24u, 1u << (48u - div.shift)};
+        const FusedParams fp = make_fused(div);
         uint64_t rpt = rg >> fp.s;
         float rinv16 = lut_rinv16(hi32(rg), lut_scale);
         const uint32_t lut_saddr = (uint32_t)__cvta_generic_to_shared(s_lut);

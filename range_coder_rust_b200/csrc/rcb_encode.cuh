@@ -9,23 +9,34 @@
 //   - symbols arrive as 16-byte vectors, one vector of lookahead in registers,
 //     1 KiB bulk L2 prefetches ahead of that (a lane walks its own chunk, so a
 //     lone 16-byte load would be a random 32-byte DRAM sector);
-//   - the {cum, c} entries of the next 32-bit word of symbols are fetched from
+//   - the table entries of the next 32-bit word of symbols are fetched from
 //     shared memory while the current word is coded (ping-pong eA / eB);
 //   - byte emission is two funnel shifts plus a predicated 32-bit store, issued
 //     one symbol late so it overlaps the next symbol's multiply chain;
-//   - FUSED (power-of-two total >= 2^24, consistent table): range/total and the
-//     renormalisation shift are one shift (rcb_core.cuh: fused_step), and the
-//     rare events that need the reference's literal loops (loop 2, n1 >= 3) are
-//     handled per 32-bit word: the word is coded speculatively without any
+//   - FUSED (consistent table): the lane carries rpt = range / total and the
+//     renormalisation shift folds into the division (rcb_core.cuh: fused_step);
+//     the rare events that need the reference's literal loops (loop 2, n1 >= 3)
+//     are handled per 32-bit word: the word is coded speculatively without any
 //     branch, and if a lane saw such an event it restores its checkpoint and
 //     re-codes the word on the exact out-of-line path (stores are idempotent).
+//
+// Table placement (TABLE):
+//   TAB_SHARED   one {cum, c} table for all chunks, in shared memory
+//   TAB_LANE     one table per chunk, each lane's cum[K+1] in its own shared-memory row
+//                (adaptive per-chunk models; needs regular tables and (K+1)*4 bytes per lane)
+//   TAB_GLOBAL   one table per chunk, read through L1/L2 (any table, any K)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "rcb_core.cuh"
 
 namespace rcb {
+
+enum : int { TAB_SHARED = 0, TAB_LANE = 1, TAB_GLOBAL = 2 };
+enum : int { FM_GENERIC = -1, FM_BIG = FUSE_BIG, FM_POW2 = FUSE_POW2, FM_GEN = FUSE_GEN, FM_LANE = 3 };
 
 struct EncodeArgs {
     const void* syms;
@@ -35,7 +46,7 @@ struct EncodeArgs {
     const uint2* tabs;      // [n_models][K]
     const ModelHdr* hdrs;   // [n_models]
     uint32_t K;
-    uint32_t per_chunk;     // 1: model index = chunk
+    uint32_t lanes_per_block;  // chunks per block (<= blockDim.x)
     uint8_t* staging;       // [n_chunks][pitch]
     uint64_t pitch;
     uint32_t* lens;         // [n_chunks]
@@ -69,7 +80,7 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) 
 
 template <int SPW>
 struct EncEntries {
-    uint2 e[SPW];
+    uint2 e[SPW];  // {cum, c}
 };
 
 // Lane state of the fused loop; travels by value through the exact re-code path.
@@ -83,7 +94,7 @@ struct EncWordState {
 // Exact re-code of one word of symbols from a checkpoint (rare): fused arithmetic where it
 // applies, the reference's literal loops (renorm_slow) where it does not.  Out of line so the
 // unrolled hot loop stays small for the instruction cache.
-template <int SPW>
+template <int SPW, int MODE>
 __device__ __noinline__ EncWordState enc_word_exact(EncWordState s, EncEntries<SPW> en, FusedParams fp,
                                                     uint8_t* row, uint32_t cap) {
     RowStore rs{row};
@@ -91,11 +102,11 @@ __device__ __noinline__ EncWordState enc_word_exact(EncWordState s, EncEntries<S
     sink.pend = s.pend;
     sink.nb = s.nb;
     sink.pos = s.pos;
-#pragma unroll 1
+#pragma unroll
     for (int b = 0; b < SPW; b++) {
         uint64_t nlo, rgp, nrpt;
         uint32_t sh;
-        const bool ok = fused_step(s.lo, s.rpt, en.e[b].x, en.e[b].y, fp, nlo, rgp, nrpt, sh);
+        const bool ok = fused_step<MODE>(s.lo, s.rpt, en.e[b].x, en.e[b].y, fp, nlo, rgp, nrpt, sh);
         sink.put(s.em_hi, s.em_sh);
         if (ok) {
             s.em_hi = hi32(nlo);
@@ -107,7 +118,7 @@ __device__ __noinline__ EncWordState enc_word_exact(EncWordState s, EncEntries<S
             uint64_t lo = nlo, rg = rgp;
             renorm_slow<false>(lo, rg, sink, s.err);
             s.lo = lo;
-            s.rpt = rg >> fp.s;
+            s.rpt = fused_rpt<MODE>(rg, fp);
         }
     }
     s.pend = sink.pend;
@@ -116,35 +127,52 @@ __device__ __noinline__ EncWordState enc_word_exact(EncWordState s, EncEntries<S
     return s;
 }
 
-// SHARED: one table for all chunks, staged in shared memory.
-// !SHARED: one table per chunk, read through L1/L2 from global memory.
-template <typename SYM, bool SHARED, bool POW2, bool CHECKED, bool RANGECHK, bool FUSED>
-__global__ void __launch_bounds__(256, 1) encode_kernel(EncodeArgs a) {
+template <typename SYM, int TABLE, int FMODE, bool CHECKED, bool RANGECHK>
+__global__ void __launch_bounds__(512, 1) encode_kernel(EncodeArgs a) {
     extern __shared__ __align__(16) uint8_t s_raw[];
-    uint2* s_tab = reinterpret_cast<uint2*>(s_raw);
     __shared__ ModelHdr s_hdr;
-    if (SHARED) {
-        for (uint32_t i = threadIdx.x; i < a.K; i += blockDim.x) s_tab[i] = a.tabs[i];
+    const uint32_t K = a.K;
+    const uint32_t L = a.lanes_per_block;
+    const uint64_t block_first = (uint64_t)blockIdx.x * L;
+    if (TABLE == TAB_SHARED) {
+        uint2* s_tab = reinterpret_cast<uint2*>(s_raw);
+        for (uint32_t i = threadIdx.x; i < K; i += blockDim.x) s_tab[i] = a.tabs[i];
         if (threadIdx.x == 0) s_hdr = a.hdrs[0];
         __syncthreads();
     }
-    const uint64_t chunk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (TABLE == TAB_LANE) {
+        // each lane's cum[0..K] (cum[K] = total) in its own row of K+1 words (odd pitch for K = 256:
+        // lanes reading the same symbol hit different banks); filled cooperatively, coalesced
+        uint32_t* rows = reinterpret_cast<uint32_t*>(s_raw);
+        const uint64_t left = a.n_chunks - block_first;
+        const uint32_t lanes = left < L ? (uint32_t)left : L;
+        const uint32_t pitch = K + 1;
+        for (uint32_t l = 0; l < lanes; l++) {
+            const uint2* t = a.tabs + (block_first + l) * K;
+            for (uint32_t i = threadIdx.x; i < K; i += blockDim.x) rows[l * pitch + i] = t[i].x;
+            if (threadIdx.x == 0) rows[l * pitch + K] = a.hdrs[block_first + l].div.total;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x >= L) return;
+    const uint64_t chunk = block_first + threadIdx.x;
     if (chunk >= a.n_chunks) return;
     const uint64_t first = chunk * a.chunk_syms;
     const uint64_t cnt = (a.n_syms - first < a.chunk_syms) ? (a.n_syms - first) : a.chunk_syms;
     const SYM* src = reinterpret_cast<const SYM*>(a.syms) + first;
 
-    const uint2* tab = SHARED ? s_tab : a.tabs + chunk * a.K;
+    const uint2* tab = TABLE == TAB_SHARED ? reinterpret_cast<const uint2*>(s_raw) : a.tabs + chunk * K;
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(s_raw) + (size_t)threadIdx.x * (K + 1);
     DivParams div;
-    bool pow2 = POW2;
-    if (SHARED) {
+    bool pow2;
+    if (TABLE == TAB_SHARED) {
         div = s_hdr.div;
+        pow2 = (s_hdr.flags & MODEL_POW2) != 0;
     } else {
         ModelHdr h = a.hdrs[chunk];
         div = h.div;
         pow2 = (h.flags & MODEL_POW2) != 0;
     }
-    const uint32_t K = a.K;
     const uint32_t cap = (uint32_t)a.pitch;
 
     uint64_t lo = 0, rg = ~0ull;  // src/range_coder.rs:13-20
@@ -154,28 +182,29 @@ __global__ void __launch_bounds__(256, 1) encode_kernel(EncodeArgs a) {
 
     constexpr int SPW = 4 / sizeof(SYM);  // symbols per 32-bit word
     using Entries = EncEntries<SPW>;
+    auto entry = [&](uint32_t s) -> uint2 {
+        if (RANGECHK && s >= K) {
+            if (!err) err = ST_SYMBOL_RANGE;
+            s = 0;
+        }
+        if (TABLE == TAB_LANE) {
+            const uint32_t cum = row[s];
+            return make_uint2(cum, row[s + 1] - cum);  // regular table: c = cum[s+1] - cum[s]
+        }
+        return tab[s];
+    };
     auto lookup = [&](uint32_t w) -> Entries {
         Entries r;
 #pragma unroll
-        for (int b = 0; b < SPW; b++) {
-            uint32_t s = sizeof(SYM) == 1 ? ((w >> (8 * b)) & 0xFFu) : ((w >> (16 * b)) & 0xFFFFu);
-            if (RANGECHK && s >= K) {
-                if (!err) err = ST_SYMBOL_RANGE;
-                s = 0;
-            }
-            r.e[b] = tab[s];
-        }
+        for (int b = 0; b < SPW; b++)
+            r.e[b] = entry(sizeof(SYM) == 1 ? ((w >> (8 * b)) & 0xFFu) : ((w >> (16 * b)) & 0xFFFFu));
         return r;
     };
     auto generic_symbol = [&](uint2 e) {
-        if (SHARED) {
-            update_symbol<POW2, CHECKED>(lo, rg, e.x, e.y, div, sink, err);
-        } else {
-            if (pow2)
-                update_symbol<true, CHECKED>(lo, rg, e.x, e.y, div, sink, err);
-            else
-                update_symbol<false, CHECKED>(lo, rg, e.x, e.y, div, sink, err);
-        }
+        if (pow2)
+            update_symbol<true, CHECKED>(lo, rg, e.x, e.y, div, sink, err);
+        else
+            update_symbol<false, CHECKED>(lo, rg, e.x, e.y, div, sink, err);
     };
 
     constexpr uint32_t PER = 16 / sizeof(SYM);
@@ -198,61 +227,74 @@ __global__ void __launch_bounds__(256, 1) encode_kernel(EncodeArgs a) {
             uint4 cur = ldg_stream_v4(v);
             Entries eA = lookup(cur.x);
             uint64_t i = 0;
-            if constexpr (FUSED) {
+            if constexpr (FMODE != FM_GENERIC) {
                 // fast sink: no capacity test per store; room for a whole vector is checked once
                 // per vector (16 symbols x at most 15 bytes + the deferred emission < 320 bytes)
                 EncSink<RowStore, false> fs(rs, cap);
-                const FusedParams fp{div.shift, div.shift - 24u, 1u << (48u - div.shift)};
-                uint64_t rpt = rg >> fp.s;
+                const FusedParams fp = make_fused(div);
                 uint32_t em_hi = 0, em_sh = 0;  // previous symbol's bytes, emitted one symbol late
-                auto code = [&](const Entries& en) {
-                    const EncWordState chk{lo, rpt, fs.pend, fs.nb, fs.pos, em_hi, em_sh, err};
-                    bool bad = false;
+                uint64_t rpt;
+                // one flavour of the word coder per division mode (FM_LANE picks per lane at run time)
+                auto run = [&](auto mode_tag) {
+                    constexpr int MODE = decltype(mode_tag)::value;
+                    rpt = fused_rpt<MODE>(rg, fp);
+                    auto code = [&](const Entries& en) {
+                        const EncWordState chk{lo, rpt, fs.pend, fs.nb, fs.pos, em_hi, em_sh, err};
+                        bool bad = false;
 #pragma unroll
-                    for (int b = 0; b < SPW; b++) {  // speculative: straight-line, no branch
-                        uint64_t nlo, rgp, nrpt;
-                        uint32_t sh;
-                        const bool ok = fused_step(lo, rpt, en.e[b].x, en.e[b].y, fp, nlo, rgp, nrpt, sh);
-                        fs.put(em_hi, em_sh);
-                        em_hi = hi32(nlo);
-                        em_sh = sh;
-                        lo = nlo << sh;
-                        rpt = nrpt;
-                        bad |= !ok;
-                    }
-                    if (RCB_UNLIKELY(bad)) {  // restore the checkpoint and re-code the word exactly
-                        const EncWordState r = enc_word_exact<SPW>(chk, en, fp, rs.row, cap);
-                        lo = r.lo;
-                        rpt = r.rpt;
-                        fs.pend = r.pend;
-                        fs.nb = r.nb;
-                        fs.pos = r.pos;
-                        em_hi = r.em_hi;
-                        em_sh = r.em_sh;
-                        err = r.err;
-                    }
-                };
+                        for (int b = 0; b < SPW; b++) {  // speculative: straight-line, no branch
+                            uint64_t nlo, rgp, nrpt;
+                            uint32_t sh;
+                            const bool ok = fused_step<MODE>(lo, rpt, en.e[b].x, en.e[b].y, fp, nlo, rgp, nrpt, sh);
+                            fs.put(em_hi, em_sh);
+                            em_hi = hi32(nlo);
+                            em_sh = sh;
+                            lo = nlo << sh;
+                            rpt = nrpt;
+                            bad |= !ok;
+                        }
+                        if (RCB_UNLIKELY(bad)) {  // restore the checkpoint and re-code the word exactly
+                            const EncWordState r = enc_word_exact<SPW, MODE>(chk, en, fp, rs.row, cap);
+                            lo = r.lo;
+                            rpt = r.rpt;
+                            fs.pend = r.pend;
+                            fs.nb = r.nb;
+                            fs.pos = r.pos;
+                            em_hi = r.em_hi;
+                            em_sh = r.em_sh;
+                            err = r.err;
+                        }
+                    };
 #pragma unroll 1
-                for (; i < nvec; i++) {
-                    if (fs.pos + 320u > cap) break;  // finish this chunk on the capacity-checked path
-                    prefetch_block(i);
-                    const uint4 nxt = (i + 1 < nvec) ? ldg_stream_v4(v + i + 1) : make_uint4(0, 0, 0, 0);
-                    Entries eB = lookup(cur.y);
-                    code(eA);
-                    eA = lookup(cur.z);
-                    code(eB);
-                    eB = lookup(cur.w);
-                    code(eA);
-                    eA = lookup(nxt.x);  // word 0 of the next vector (zeros past the end: entry 0, unused)
-                    code(eB);
-                    cur = nxt;
+                    for (; i < nvec; i++) {
+                        if (fs.pos + 320u > cap) break;  // finish this chunk on the capacity-checked path
+                        prefetch_block(i);
+                        const uint4 nxt = (i + 1 < nvec) ? ldg_stream_v4(v + i + 1) : make_uint4(0, 0, 0, 0);
+                        Entries eB = lookup(cur.y);
+                        code(eA);
+                        eA = lookup(cur.z);
+                        code(eB);
+                        eB = lookup(cur.w);
+                        code(eA);
+                        eA = lookup(nxt.x);  // word 0 of the next vector (zeros past the end: unused)
+                        code(eB);
+                        cur = nxt;
+                    }
+                    // back to the generic (lower, range) form: range = rpt * total keeps range / total
+                    // == rpt, the only way `range` is used before the next update
+                    rg = MODE == FUSE_GEN ? rpt * (uint64_t)div.total : rpt << fp.s;
+                };
+                if constexpr (FMODE == FM_LANE) {
+                    if (pow2) run(std::integral_constant<int, FUSE_POW2>{});
+                    else run(std::integral_constant<int, FUSE_GEN>{});
+                } else {
+                    run(std::integral_constant<int, FMODE>{});
                 }
                 sink.pend = fs.pend;
                 sink.nb = fs.nb;
                 sink.pos = fs.pos;
                 sink.put(em_hi, em_sh);
-                rg = rpt << fp.s;  // the dropped low s bits never influence range / total (the next use)
-                done = i * PER;    // anything left runs through the scalar, capacity-checked loop below
+                done = i * PER;  // anything left runs through the scalar, capacity-checked loop below
             } else {
                 auto code = [&](const Entries& en) {
 #pragma unroll
@@ -277,14 +319,7 @@ __global__ void __launch_bounds__(256, 1) encode_kernel(EncodeArgs a) {
         }
     }
 #pragma unroll 1
-    for (uint64_t i = done; i < cnt; i++) {
-        uint32_t s = (uint32_t)src[i];
-        if (RANGECHK && s >= K) {
-            if (!err) err = ST_SYMBOL_RANGE;
-            s = 0;
-        }
-        generic_symbol(tab[s]);
-    }
+    for (uint64_t i = done; i < cnt; i++) generic_symbol(entry((uint32_t)src[i]));
 
     uint32_t len = sink.finish(lo);  // src/encoder.rs:40-46
     if (!err && sink.overflowed()) err = ST_OUT_CAPACITY;

@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
 #include <vector>
 
 #include "../../range_coder_rust_b200/csrc/rcb_core.cuh"
@@ -114,36 +115,43 @@ extern "C" int64_t hc_encode(const uint8_t* syms, uint64_t n, int sym_bytes, uin
     uint32_t err = 0;
     HostStore hs{out};
     EncSink<HostStore> sink(hs, cap);
-    // fused pow2 path (mirrors encode_kernel's FUSED instantiation), selected like the kernel does
+    // fused paths (mirror encode_kernel's FM_BIG / FM_POW2 / FM_GEN instantiations), selected like
+    // the host dispatch does: any consistent table, flavour by the total
     bool consistent = true;
     for (uint32_t i = 0; i < K; i++)
         if ((uint64_t)cum[i] + c[i] > total) consistent = false;
-    if (pow2 && div.shift >= 24 && consistent && !checked) {
-        FusedParams fp{div.shift, div.shift - 24u, 1u << (48u - div.shift)};
-        uint64_t rpt = rg >> fp.s;
-        for (uint64_t i = 0; i < n; i++) {
-            uint32_t s = load_sym(syms, i, sym_bytes);
-            if (s >= K) {
-                if (!err) err = ST_SYMBOL_RANGE;
-                s = 0;
+    if (consistent && !checked) {
+        const FusedParams fp = make_fused(div);
+        auto run = [&](auto tag) -> int64_t {
+            constexpr int MODE = decltype(tag)::value;
+            uint64_t rpt = fused_rpt<MODE>(rg, fp);
+            for (uint64_t i = 0; i < n; i++) {
+                uint32_t s = load_sym(syms, i, sym_bytes);
+                if (s >= K) {
+                    if (!err) err = ST_SYMBOL_RANGE;
+                    s = 0;
+                }
+                uint64_t nlo, rgp, nrpt;
+                uint32_t sh;
+                if (fused_step<MODE>(lo, rpt, cum[s], c[s], fp, nlo, rgp, nrpt, sh)) {
+                    sink.put((uint32_t)(nlo >> 32), sh);
+                    lo = nlo << sh;
+                    rpt = nrpt;
+                } else {
+                    lo = nlo;
+                    rg = rgp;
+                    renorm_slow<false>(lo, rg, sink, err);
+                    rpt = fused_rpt<MODE>(rg, fp);
+                }
             }
-            uint64_t nlo, rgp, nrpt;
-            uint32_t sh;
-            if (fused_step(lo, rpt, cum[s], c[s], fp, nlo, rgp, nrpt, sh)) {
-                sink.put((uint32_t)(nlo >> 32), sh);
-                lo = nlo << sh;
-                rpt = nrpt;
-            } else {
-                lo = nlo;
-                rg = rgp;
-                renorm_slow<false>(lo, rg, sink, err);
-                rpt = rg >> fp.s;
-            }
-        }
-        uint32_t len = sink.finish(lo);
-        if (!err && sink.overflowed()) err = ST_OUT_CAPACITY;
-        *status = err;
-        return (int64_t)len;
+            uint32_t len = sink.finish(lo);
+            if (!err && sink.overflowed()) err = ST_OUT_CAPACITY;
+            *status = err;
+            return (int64_t)len;
+        };
+        if (pow2 && div.shift >= 24) return run(std::integral_constant<int, FUSE_BIG>{});
+        if (pow2) return run(std::integral_constant<int, FUSE_POW2>{});
+        return run(std::integral_constant<int, FUSE_GEN>{});
     }
     for (uint64_t i = 0; i < n; i++) {
         uint32_t s = load_sym(syms, i, sym_bytes);
@@ -188,7 +196,7 @@ extern "C" int64_t hc_decode(const uint8_t* stream, uint64_t off0, uint64_t off1
     uint32_t err = 0;
     // fused pow2 path (mirrors decode_kernel's FUSED instantiation)
     if (lut_ok && pow2 && h.div.shift >= 24 && (h.flags & MODEL_CONSISTENT) && !checked && lut_cap == 4096) {
-        FusedParams fp{h.div.shift, h.div.shift - 24u, 1u << (48u - h.div.shift)};
+        FusedParams fp = make_fused(h.div);
         std::vector<LutEntry> pad(4096);
         for (uint32_t b = 0; b < 4096; b++) {
             if (b < h.nb) pad[b] = lut[b];
