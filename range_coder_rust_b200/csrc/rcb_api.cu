@@ -11,6 +11,7 @@
 
 #include "../../include/rcb200.h"
 #include "rcb_kernels.cuh"
+#include "rcb_decode_row.cuh"
 #include "rcb_stream.cuh"
 
 using namespace rcb;
@@ -661,42 +662,131 @@ extern "C" int rcb_encode_result(rcb_ctx* c, uint64_t* h_out_bytes) {
 }
 
 // ------------------------------------------------------------------- decode
-template <typename SYM>
-static void launch_decode_variant(rcb_ctx* c, const rcb_model* m, const DecodeArgs& a, int threads,
-                                  unsigned blocks) {
+// Launch geometry and kernel flavour of one decode call.
+struct DecPlan {
+    int kind;       // 0: fat-LUT fused kernel / generic (rcb_decode.cuh), 1: row kernel (rcb_decode_row.cuh)
+    int table;      // TAB_*
+    int fmode;      // FM_* (row kernel), FM_BIG / FM_GENERIC (kind 0)
+    bool checked, pow2, lut16;
+    int threads;
+    uint32_t lanes, nb;
+    size_t smem;
+};
+
+static DecPlan plan_decode(const rcb_ctx* c, const rcb_model* m, uint64_t n_chunks) {
+    DecPlan p;
+    memset(&p, 0, sizeof p);
     const bool shared = m->n_models == 1;
-    const bool pow2 = shared && (m->h_hdr0.flags & MODEL_POW2);
-    const bool checked = (m->bad_bits & 4u) != 0;
-    const bool regular = shared && (m->h_hdr0.flags & MODEL_REGULAR);
-    // FUSED: range/total folded into the renormalisation shift, table-driven lookup (rcb_decode.cuh)
-    const bool fused = shared && pow2 && !checked && regular && m->h_hdr0.div.shift >= 24;
-    size_t smem = (size_t)threads * RING_STRIDE;  // per-lane code-byte rings
+    p.checked = (m->bad_bits & 4u) != 0;
+    const bool regular = (m->bad_bits & 8u) == 0;
+    p.threads = pick_threads(c, c->dec_threads, n_chunks);
+    p.lanes = (uint32_t)p.threads;
+    const size_t budget = 216 * 1024;
+    const size_t row = ((size_t)m->K + 1) * sizeof(uint32_t);
+    p.lut16 = m->K > 256;
+    const size_t lut_elem = p.lut16 ? 2 : 1;
     if (shared) {
-        uint32_t nb = regular ? m->h_hdr0.nb : 0u;
-        if (fused) nb = LUT_CAP;
-        smem += (size_t)nb * sizeof(LutEntry) + (size_t)m->K * sizeof(uint2);
+        p.table = TAB_SHARED;
+        p.pow2 = (m->h_hdr0.flags & MODEL_POW2) != 0;
+        const uint32_t shift = m->h_hdr0.div.shift;
+        const uint64_t total = m->h_hdr0.div.total;
+        if (!p.checked && regular) {
+            // fat LUT (two candidates per 1/4096 of the range): only when no bucket can hold two boundaries
+            const bool fat_ok = p.pow2 && shift >= 24 && (uint64_t)m->min_c >= (total >> 12) + (total >> 15) + 1;
+            if (fat_ok) {
+                p.kind = 0;
+                p.fmode = FM_BIG;
+                p.smem = (size_t)p.threads * RING_STRIDE + (size_t)LUT_CAP * sizeof(LutEntry) + (size_t)m->K * sizeof(uint2);
+                return p;
+            }
+            // thin LUT over the cum row: smallest power of two with bucket width <= min c (<= 65536 buckets)
+            uint64_t want = m->min_c ? (total + m->min_c - 1) / m->min_c : 65536;
+            uint32_t nb = 256;
+            while (nb < want && nb < 65536) nb <<= 1;
+            while (nb > 256 && (size_t)p.threads * RING_STRIDE + row + (size_t)nb * lut_elem > budget) nb >>= 1;
+            if ((size_t)p.threads * RING_STRIDE + row + (size_t)nb * lut_elem <= budget) {
+                p.kind = 1;
+                p.nb = nb;
+                p.fmode = p.pow2 ? (shift >= 24 ? FM_BIG : FM_POW2) : FM_GEN;
+                p.smem = (size_t)p.threads * RING_STRIDE + row + (size_t)nb * lut_elem;
+                return p;
+            }
+        }
+        // inconsistent / irregular / oversized tables: generic kernel (bucket LUT when regular, exact search)
+        p.kind = 0;
+        p.fmode = FM_GENERIC;
+        const uint32_t nbg = (m->h_hdr0.flags & MODEL_REGULAR) ? m->h_hdr0.nb : 0u;
+        p.smem = (size_t)p.threads * RING_STRIDE + (size_t)nbg * sizeof(LutEntry) + (size_t)m->K * sizeof(uint2);
+        return p;
     }
-#define RCB_DEC(SH, P2, CH, FU)                                                                        \
-    do {                                                                                               \
-        auto kern = decode_kernel<SYM, SH, P2, CH, FU>;                                                \
-        if (smem > 48 * 1024)                                                                          \
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
-        kern<<<blocks, threads, smem, c->stream>>>(a);                                                 \
-    } while (0)
-#define RCB_DEC_CH(SH, P2)                         \
-    do {                                           \
-        if (checked) RCB_DEC(SH, P2, true, false); \
-        else RCB_DEC(SH, P2, false, false);        \
-    } while (0)
-    if (shared) {
-        if (fused) RCB_DEC(true, true, false, true);
-        else if (pow2) RCB_DEC_CH(true, true);
-        else RCB_DEC_CH(true, false);
+    // per-chunk models: each lane owns a cum row + a thin LUT in shared memory when they fit
+    const size_t lane_min = RING_STRIDE + row + 256 * lut_elem;
+    const uint32_t lmax = (uint32_t)(budget / lane_min);
+    if (!p.checked && regular && lmax >= 32) {
+        uint32_t L = lmax < 512u ? lmax : 512u;
+        const uint64_t sms = (uint64_t)(c->sm_count > 0 ? c->sm_count : 148);
+        const uint64_t even = (n_chunks + sms - 1) / sms;  // one wave over all SMs when it fits
+        if (even <= L) L = (uint32_t)(even ? even : 1);
+        if (c->dec_threads && (uint32_t)c->dec_threads < L) L = (uint32_t)c->dec_threads;
+        p.threads = (int)((L + 31) / 32 * 32);
+        const size_t fixed = (size_t)p.threads * RING_STRIDE + (size_t)L * row;
+        size_t per_lane = (budget - fixed) / L / lut_elem;
+        uint32_t nb = (uint32_t)(per_lane > 4096 ? 4096 : per_lane) & ~15u;
+        p.kind = 1;
+        p.table = TAB_LANE;
+        p.fmode = FM_LANE;
+        p.lanes = L;
+        p.nb = nb;
+        p.smem = fixed + (size_t)L * nb * lut_elem;
+        return p;
+    }
+    p.kind = 0;
+    p.table = TAB_GLOBAL;
+    p.fmode = FM_GENERIC;
+    p.smem = (size_t)p.threads * RING_STRIDE;
+    return p;
+}
+
+template <typename SYM>
+static void launch_decode_variant(rcb_ctx* c, const rcb_model* m, const DecodeArgs& a, const DecPlan& p,
+                                  unsigned blocks) {
+    auto go = [&](auto kern) {
+        if (p.smem > 48 * 1024)
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+        kern<<<blocks, p.threads, p.smem, c->stream>>>(a);
+    };
+    (void)m;
+    if (p.table == TAB_SHARED) {
+        if (p.fmode == FM_BIG) go(decode_kernel<SYM, true, true, false, true>);
+        else if (p.pow2) {
+            if (p.checked) go(decode_kernel<SYM, true, true, true, false>);
+            else go(decode_kernel<SYM, true, true, false, false>);
+        } else {
+            if (p.checked) go(decode_kernel<SYM, true, false, true, false>);
+            else go(decode_kernel<SYM, true, false, false, false>);
+        }
     } else {
-        RCB_DEC_CH(false, false);
+        if (p.checked) go(decode_kernel<SYM, false, false, true, false>);
+        else go(decode_kernel<SYM, false, false, false, false>);
     }
-#undef RCB_DEC_CH
-#undef RCB_DEC
+}
+
+template <typename SYM, typename LUT_T>
+static void launch_decode_row(rcb_ctx* c, const DecodeRowArgs& a, const DecPlan& p, unsigned blocks) {
+    auto go = [&](auto kern) {
+        if (p.smem > 48 * 1024)
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+        kern<<<blocks, p.threads, p.smem, c->stream>>>(a);
+    };
+    if (p.table == TAB_LANE) {
+        go(decode_row_kernel<SYM, TAB_LANE, FM_LANE, LUT_T>);
+    } else {
+        switch (p.fmode) {
+            case FM_BIG: go(decode_row_kernel<SYM, TAB_SHARED, FM_BIG, LUT_T>); break;
+            case FM_POW2: go(decode_row_kernel<SYM, TAB_SHARED, FM_POW2, LUT_T>); break;
+            default: go(decode_row_kernel<SYM, TAB_SHARED, FM_GEN, LUT_T>); break;
+        }
+    }
 }
 
 extern "C" int rcb_decode_chunks_async(rcb_ctx* c, const uint8_t* d_stream, const uint64_t* d_offsets,
@@ -731,13 +821,36 @@ extern "C" int rcb_decode_chunks_async(rcb_ctx* c, const uint8_t* d_stream, cons
     a.per_chunk = m->n_models != 1;
     a.out = d_syms_out;
     a.status = d_status ? d_status : c->status;
-    const int threads = pick_threads(c, c->dec_threads, n_chunks);
-    const unsigned blocks = (unsigned)((n_chunks + threads - 1) / threads);
+    const DecPlan plan = plan_decode(c, m, n_chunks);
+    const unsigned blocks = (unsigned)((n_chunks + plan.lanes - 1) / plan.lanes);
     EV(c, 4);
-    if (sym_bytes == 1)
-        launch_decode_variant<uint8_t>(c, m, a, threads, blocks);
-    else
-        launch_decode_variant<uint16_t>(c, m, a, threads, blocks);
+    if (plan.kind == 0) {
+        if (sym_bytes == 1)
+            launch_decode_variant<uint8_t>(c, m, a, plan, blocks);
+        else
+            launch_decode_variant<uint16_t>(c, m, a, plan, blocks);
+    } else {
+        DecodeRowArgs ra;
+        ra.stream = a.stream;
+        ra.offsets = a.offsets;
+        ra.n_syms = a.n_syms;
+        ra.chunk_syms = a.chunk_syms;
+        ra.n_chunks = a.n_chunks;
+        ra.tabs = a.tabs;
+        ra.hdrs = a.hdrs;
+        ra.K = a.K;
+        ra.lanes_per_block = plan.lanes;
+        ra.nb = plan.nb;
+        ra.out = a.out;
+        ra.status = a.status;
+        if (sym_bytes == 1) {
+            if (plan.lut16) launch_decode_row<uint8_t, uint16_t>(c, ra, plan, blocks);
+            else launch_decode_row<uint8_t, uint8_t>(c, ra, plan, blocks);
+        } else {
+            if (plan.lut16) launch_decode_row<uint16_t, uint16_t>(c, ra, plan, blocks);
+            else launch_decode_row<uint16_t, uint8_t>(c, ra, plan, blocks);
+        }
+    }
     CK_LAUNCH(c);
     EV(c, 5);
     status_summary_kernel<<<1, 1024, 0, c->stream>>>(a.status, n_chunks, c->d_summary + 4);

@@ -544,4 +544,33 @@ RCB_HD FusedDec fused_decode_step(uint64_t lo, uint64_t rpt, uint64_t data, cons
     return r;
 }
 
+
+// Renormalisation half of the fused decode step, for callers that pick the symbol themselves
+// (row kernel: candidates from a thin LUT, then a short scan): from lower' and upper' of the
+// chosen symbol to the shift, the next rpt and the "fast renormalisation applies" flag.
+struct FusedRenorm {
+    uint64_t rgp, nrpt;
+    uint32_t sh;
+    bool ok;
+};
+
+template <int MODE>
+RCB_HD FusedRenorm fused_renorm(uint64_t nlo, uint64_t up, const FusedParams& fp) {
+    FusedRenorm r;
+    r.rgp = up - nlo;
+    const uint32_t xh = hi32(nlo) ^ hi32(up);
+    const bool p1 = xh < (1u << 24), p2 = xh < (1u << 16), p3 = xh < (1u << 8);
+    if (MODE == FUSE_BIG) {
+        const uint32_t k = p2 ? (p3 ? fp.k0 : fp.k0 + 8u) : (p1 ? fp.k0 + 16u : fp.k0 + 24u);
+        r.sh = (fp.k0 + 24u) - k;
+        r.nrpt = r.rgp >> k;
+    } else {
+        r.sh = p2 ? (p3 ? 24u : 16u) : (p1 ? 8u : 0u);
+        r.nrpt = fused_rpt<MODE>(r.rgp << r.sh, fp);
+    }
+    const uint32_t need = p2 ? 1u : (p1 ? (1u << 8) : (1u << 16));  // see fused_step
+    r.ok = hi32(r.rgp) >= need;
+    return r;
+}
+
 }  // namespace rcb

@@ -1,0 +1,289 @@
+// rcb_decode_row.cuh -- K5b: decode for tables that do not fit the fat-LUT kernel of
+// rcb_decode.cuh: per-chunk (adaptive) models, large alphabets (K = 4096), and shared
+// tables whose total is not a power of two >= 2^24.
+//
+// Same reference semantics (src/decoder.rs:14-54, examples/sample_impl.rs:27-45), same
+// lane state and code-byte ring.  The table is the cum_freq row cum[0..K] (cum[K] = total)
+// in shared memory -- one row per lane (TAB_LANE) or one for the block (TAB_SHARED) -- plus a
+// thin bucket -> symbol LUT (u8 / u16 entries) built in the kernel prologue:
+//   bucket b = floor(nb * (data - lower) / range)   (float estimate from the high words)
+//   s0 = lut[b];  candidates s0 and s0+1 with bounds cum[s0], cum[s0+1], cum[s0+2]
+// then the exact product-domain verification of fused_decode_step; a miss (several
+// symbols in one bucket, estimate off, loop 2, ...) takes the out-of-line exact search.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <type_traits>
+
+#include "rcb_core.cuh"
+#include "rcb_decode.cuh"
+#include "rcb_encode.cuh"  // TAB_*, FM_*
+
+namespace rcb {
+
+struct DecodeRowArgs {
+    const uint8_t* stream;
+    const uint64_t* offsets;  // [n_chunks+1]
+    uint64_t n_syms;
+    uint64_t chunk_syms;
+    uint64_t n_chunks;
+    const uint2* tabs;        // [n_models][K]
+    const ModelHdr* hdrs;     // [n_models]
+    uint32_t K;
+    uint32_t lanes_per_block;
+    uint32_t nb;              // LUT buckets (per lane or per block)
+    void* out;
+    uint32_t* status;
+};
+
+// Exact path for row tables (rare, out of line): the reference's binary search in the product
+// domain over cum[1..K-1], c = cum[s+1] - cum[s], generic renormalisation.
+__device__ __noinline__ DecLaneState dec_exact_row(DecLaneState s, const uint32_t* row, uint32_t K, DivParams div,
+                                                   uint32_t pow2, uint32_t n_syms, uint32_t sym_bits) {
+    GlobalFetch gf{s.base, s.rd, s.last};
+    DecSink<GlobalFetch> sink(gf);
+    sink.dh = s.dh;
+    sink.dl = s.dl;
+    sink.wh = s.wh;
+    sink.wl = s.wl;
+    sink.cnt = s.cnt;
+    uint32_t acc = 0;
+#pragma unroll 1
+    for (uint32_t b = 0; b < n_syms; b++) {
+        const uint64_t rpt = pow2 ? range_par_total<true>(s.rg, div) : range_par_total<false>(s.rg, div);
+        const uint64_t d = sink.data() - s.lo;  // examples/sample_impl.rs:29
+        const uint32_t sym = find_index_exact(d, rpt, K, [&](uint32_t i) { return row[i]; });
+        const uint32_t cum = row[sym], c = row[sym + 1] - cum;
+        s.lo = s.lo + rpt * (uint64_t)cum;  // src/decoder.rs:42-50
+        s.rg = rpt * (uint64_t)c;
+        renorm<false>(s.lo, s.rg, sink, s.err);
+        acc |= sym << (sym_bits * b);
+    }
+    s.syms = acc;
+    s.dh = sink.dh;
+    s.dl = sink.dl;
+    s.wh = sink.wh;
+    s.wl = sink.wl;
+    s.cnt = sink.cnt;
+    s.rd = sink.f.idx;
+    return s;
+}
+
+// symbol whose interval contains v (the reference's search on plain cum values)
+__device__ __forceinline__ uint32_t row_symbol_at(const uint32_t* row, uint32_t K, uint64_t v) {
+    uint32_t left = 0, right = K - 1;
+    while (left < right) {
+        const uint32_t mid = (left + right) >> 1;
+        if ((uint64_t)row[mid + 1] <= v) left = mid + 1; else right = mid;
+    }
+    return left;
+}
+
+template <typename SYM, int TABLE, int FMODE, typename LUT_T>
+__global__ void __launch_bounds__(512, 1) decode_row_kernel(DecodeRowArgs a) {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    __shared__ ModelHdr s_hdr;
+    const uint32_t K = a.K, L = a.lanes_per_block, nb = a.nb;
+    const uint64_t block_first = (uint64_t)blockIdx.x * L;
+    const uint32_t row_words = K + 1;
+    const uint32_t n_rows = TABLE == TAB_LANE ? L : 1u;
+    // shared layout: rings[blockDim.x][RING_STRIDE] | rows[n_rows][K+1] u32 | luts[n_rows][nb] LUT_T
+    uint8_t* s_ring = s_raw;
+    uint32_t* s_rows = reinterpret_cast<uint32_t*>(s_raw + (size_t)blockDim.x * RING_STRIDE);
+    LUT_T* s_luts = reinterpret_cast<LUT_T*>(s_rows + (size_t)n_rows * row_words);
+
+    // ---- prologue: cum rows (coalesced) and bucket LUTs
+    {
+        const uint64_t left = a.n_chunks - block_first;
+        const uint32_t lanes = TABLE == TAB_LANE ? (left < L ? (uint32_t)left : L) : 1u;
+        for (uint32_t l = 0; l < lanes; l++) {
+            const uint64_t model = TABLE == TAB_LANE ? block_first + l : 0;
+            const uint2* t = a.tabs + model * K;
+            for (uint32_t i = threadIdx.x; i < K; i += blockDim.x) s_rows[l * row_words + i] = t[i].x;
+            if (threadIdx.x == 0) s_rows[l * row_words + K] = a.hdrs[model].div.total;
+        }
+        if (TABLE == TAB_SHARED && threadIdx.x == 0) s_hdr = a.hdrs[0];
+        __syncthreads();
+        if (TABLE == TAB_SHARED) {
+            // entry b: symbol at the point 1/8 bucket below floor(b * total / nb)
+            const uint64_t total = s_rows[K];
+            const uint64_t margin = total / nb / 8 + 1;
+            const bool nb_pow2 = (nb & (nb - 1)) == 0;
+            const uint32_t nb_shift = 31u - (uint32_t)__clz((int)nb);
+            for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) {
+                uint64_t v0 = nb_pow2 ? ((uint64_t)b * total) >> nb_shift : (uint64_t)b * total / nb;
+                v0 = v0 > margin ? v0 - margin : 0;
+                s_luts[b] = (LUT_T)row_symbol_at(s_rows, K, v0);
+            }
+        } else if (threadIdx.x < lanes) {
+            // each lane walks its own row and its buckets together (both monotone)
+            const uint32_t* row = s_rows + threadIdx.x * row_words;
+            LUT_T* lut = s_luts + (size_t)threadIdx.x * nb;
+            const uint64_t total = row[K];
+            const uint64_t margin = total / nb / 8 + 1;
+            const uint64_t step_q = total / nb, step_r = total % nb;  // floor(b*total/nb), incrementally
+            uint64_t q = 0, r = 0;
+            uint32_t s = 0;
+            for (uint32_t b = 0; b < nb; b++) {
+                const uint64_t v0 = q > margin ? q - margin : 0;
+                while (s < K - 1 && (uint64_t)row[s + 1] <= v0) s++;
+                lut[b] = (LUT_T)s;
+                q += step_q;
+                r += step_r;
+                if (r >= nb) {
+                    r -= nb;
+                    q++;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x >= L) return;
+    const uint64_t chunk = block_first + threadIdx.x;
+    if (chunk >= a.n_chunks) return;
+    const uint64_t first = chunk * a.chunk_syms;
+    const uint64_t cnt = (a.n_syms - first < a.chunk_syms) ? (a.n_syms - first) : a.chunk_syms;
+    SYM* dst = reinterpret_cast<SYM*>(a.out) + first;
+
+    const uint32_t* row = s_rows + (TABLE == TAB_LANE ? (size_t)threadIdx.x * row_words : 0);
+    const LUT_T* lut = s_luts + (TABLE == TAB_LANE ? (size_t)threadIdx.x * nb : 0);
+    const ModelHdr hdr = TABLE == TAB_SHARED ? s_hdr : a.hdrs[chunk];
+    const DivParams div = hdr.div;
+    const bool pow2 = (hdr.flags & MODEL_POW2) != 0;
+
+    const uint64_t off0 = a.offsets[chunk], off1 = a.offsets[chunk + 1];
+    const uint64_t total_bytes = a.offsets[a.n_chunks];
+    const uint64_t pb = off0 & ~15ull;
+    const uint64_t readable = ((total_bytes + 15) & ~15ull) - pb;
+    const uint32_t skip = (uint32_t)(off0 & 3u);
+    const uint32_t rd0 = (uint32_t)((off0 - pb) >> 2);
+
+    RingFill fill;
+    fill.pbase = a.stream + pb;
+    fill.wr = 0;
+    fill.npieces = readable > (0xFFFFFFF0ull << 4) ? 0xFFFFFFF0u : (uint32_t)(readable >> 4);
+    fill.pend = 0;
+    RingFetch rf;
+    rf.ring = (uint32_t)__cvta_generic_to_shared(s_ring + (size_t)threadIdx.x * RING_STRIDE);
+    rf.rd = rd0;
+    rf.cur = 0;
+    const uint32_t last_word = fill.npieces * 4 - 1;
+
+    constexpr uint32_t PF_WORDS = 256;
+    uint32_t pf_next = 0;
+    auto prefetch_to = [&](uint32_t upto_words) {
+        while (pf_next < upto_words) {
+            const uint64_t o = (uint64_t)pf_next * 4;
+            if (o < readable) {
+                const uint64_t left = readable - o;
+                prefetch_l2_bulk_dec(fill.pbase + o, (uint32_t)(left < PF_WORDS * 4 ? left : PF_WORDS * 4));
+            }
+            pf_next += PF_WORDS;
+        }
+    };
+    prefetch_to(2 * PF_WORDS);
+    fill.resync(rf);
+    DecSink<RingFetch> sink(rf);
+    sink.prime(skip);  // src/decoder.rs:14-23
+
+    uint64_t lo = 0, rg = ~0ull;
+    uint32_t err = 0;
+    constexpr uint32_t PER = 4 / sizeof(SYM);
+    constexpr uint32_t SYM_BITS = 8 * sizeof(SYM);
+    const FusedParams fp = make_fused(div);
+    const float fnb = (float)nb;
+    const uint32_t nbm1 = nb - 1;
+
+    const bool aligned = (reinterpret_cast<uintptr_t>(dst) & 3u) == 0;
+    uint32_t* dw = reinterpret_cast<uint32_t*>(dst);
+    const uint64_t nw = aligned ? cnt / PER : 0;
+    uint64_t done = 0;
+
+    auto run = [&](auto mode_tag) {
+        constexpr int MODE = decltype(mode_tag)::value;
+        uint64_t rpt = fused_rpt<MODE>(rg, fp);
+        float rinv = fast_rcp((float)hi32(rg)) * fnb;
+        auto step = [&]() -> uint32_t {
+            const uint64_t data = sink.data();
+            // bucket estimate: nb * (data - lower) / range from the high words (>= 0)
+            const float bf = (float)(sink.dh - hi32(lo)) * rinv;
+            uint32_t b = __float_as_uint(__fadd_rz(bf, 8388608.0f)) & 0x7FFFFFu;
+            b = b < nbm1 ? b : nbm1;
+            uint32_t sym = lut[b];
+            // two candidates: sym and sym + 1 (zero-width neighbours fail the test and get scanned)
+            const uint64_t loA = lo + rpt * (uint64_t)row[sym];
+            const uint64_t loB = lo + rpt * (uint64_t)row[sym + 1u];
+            const uint64_t loC = lo + rpt * (uint64_t)row[sym + 2u < K ? sym + 2u : K];
+            const bool takeB = data >= loB;
+            uint64_t nlo = takeB ? loB : loA;
+            uint64_t up = takeB ? loC : loB;
+            sym += takeB ? 1u : 0u;
+            if (RCB_UNLIKELY(!((data >= nlo) & (data < up)))) {
+                // several symbols in this bucket (or the estimate was off): short exact scan in the
+                // product domain -- the reference's search result is the largest s with
+                // lower + rpt * cum[s] <= data, clamped to K-1 (examples/sample_impl.rs:33-44)
+                sym = sym < K - 1u ? sym : K - 1u;
+#pragma unroll 1
+                while (sym > 0u && lo + rpt * (uint64_t)row[sym] > data) sym--;
+#pragma unroll 1
+                while (sym < K - 1u && lo + rpt * (uint64_t)row[sym + 1u] <= data) sym++;
+                nlo = lo + rpt * (uint64_t)row[sym];
+                up = lo + rpt * (uint64_t)row[sym + 1u];
+            }
+            const FusedRenorm r = fused_renorm<MODE>(nlo, up, fp);
+            if (RCB_LIKELY(r.ok)) {
+                sink.put(0u, r.sh);
+                lo = nlo << r.sh;
+                rpt = r.nrpt;
+                rinv = fast_rcp((float)hi32(r.rgp << r.sh)) * fnb;
+                return sym;
+            }
+            rg = MODE == FUSE_GEN ? rpt * (uint64_t)div.total : rpt << fp.s;
+            const DecLaneState st{lo, rg, sink.dh, sink.dl, sink.wh, sink.wl, sink.cnt,
+                                  reinterpret_cast<const uint32_t*>(fill.pbase), sink.f.rd, last_word, err, 0u};
+            const DecLaneState x = dec_exact_row(st, row, K, div, pow2 ? 1u : 0u, 1u, 0u);
+            lo = x.lo;
+            rg = x.rg;
+            sink.dh = x.dh;
+            sink.dl = x.dl;
+            sink.wh = x.wh;
+            sink.wl = x.wl;
+            sink.cnt = x.cnt;
+            sink.f.rd = x.rd;
+            err = x.err;
+            fill.resync(sink.f);
+            rpt = fused_rpt<MODE>(rg, fp);
+            rinv = fast_rcp((float)hi32(rg)) * fnb;
+            return x.syms;
+        };
+#pragma unroll 1
+        for (uint64_t i = 0; i < nw; i++) {
+            if (sink.f.rd + PF_WORDS >= pf_next) prefetch_to(sink.f.rd + 2 * PF_WORDS);
+            fill.round(sink.f);
+            uint32_t acc = 0;
+#pragma unroll
+            for (uint32_t k = 0; k < PER; k++) acc |= step() << (SYM_BITS * k);
+            dw[i] = acc;
+        }
+        done = nw * PER;
+#pragma unroll 1
+        for (uint64_t i = done; i < cnt; i++) {
+            fill.round(sink.f);
+            dst[i] = (SYM)step();
+        }
+    };
+    if constexpr (FMODE == FM_LANE) {
+        if (pow2) run(std::integral_constant<int, FUSE_POW2>{});
+        else run(std::integral_constant<int, FUSE_GEN>{});
+    } else {
+        run(std::integral_constant<int, FMODE>{});
+    }
+
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    const uint32_t used = sink.used(sink.f.rd - rd0, skip);
+    if (!err && (uint64_t)used > off1 - off0) err = ST_TRUNCATED;  // src/decoder.rs:33
+    a.status[chunk] = err;
+}
+
+}  // namespace rcb
