@@ -45,6 +45,10 @@ struct rcb_ctx {
     uint64_t launches = 0;
     uint64_t pending_pitch = 0, pending_out_cap = 0, pending_n_chunks = 0;
     const uint64_t* pending_offsets = nullptr;
+    // host-buffer pipeline: slices of one batch on their own streams (copies overlap the coder kernels)
+    cudaStream_t slice_stream[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    unsigned long long* d_slice_summary = nullptr;  // [8][8]
+    unsigned long long* h_slice_summary = nullptr;  // pinned mirror
     bool timing = false;
     cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_enc = false, ev_dec = false;
@@ -171,6 +175,10 @@ extern "C" int rcb_ctx_destroy(rcb_ctx* c) {
     cudaFree(c->h2d);
     for (int i = 0; i < 7; i++)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 8; i++)
+        if (c->slice_stream[i]) cudaStreamDestroy(c->slice_stream[i]);
+    cudaFree(c->d_slice_summary);
+    cudaFreeHost(c->h_slice_summary);
     delete c;
     return RCB_OK;
 }
@@ -545,6 +553,45 @@ static void launch_encode_variant(rcb_ctx* c, const rcb_model* m, const EncodeAr
     }
 }
 
+// Issue encode + length scan + gather for a run of chunks on the ctx's current stream.  All buffers are
+// explicit so the host-buffer pipeline can run slices of one batch on several streams.
+// model_first: index of the first chunk's model (per-chunk models).
+static int encode_issue(rcb_ctx* c, const void* d_syms, uint64_t n_syms, int sym_bytes, uint64_t chunk_syms,
+                        const rcb_model* m, uint64_t model_first, uint8_t* staging, uint64_t pitch, uint32_t* lens,
+                        uint32_t* status, uint8_t* d_out, uint64_t out_cap, uint64_t* d_offsets,
+                        unsigned long long* d_summary, bool timed) {
+    const uint64_t n_chunks = (n_syms + chunk_syms - 1) / chunk_syms;
+    const bool shared = m->n_models == 1;
+    EncodeArgs a;
+    a.syms = d_syms;
+    a.n_syms = n_syms;
+    a.chunk_syms = chunk_syms;
+    a.n_chunks = n_chunks;
+    a.tabs = shared ? m->d_tab : m->d_tab + model_first * m->K;
+    a.hdrs = shared ? m->d_hdr : m->d_hdr + model_first;
+    a.K = m->K;
+    a.staging = staging;
+    a.pitch = pitch;
+    a.lens = lens;
+    a.status = status;
+    const EncPlan plan = plan_encode(c, m, n_chunks);
+    a.lanes_per_block = plan.lanes;
+    const unsigned blocks = (unsigned)((n_chunks + plan.lanes - 1) / plan.lanes);
+    if (sym_bytes == 1)
+        launch_encode_variant<uint8_t>(c, m, a, plan, blocks);
+    else
+        launch_encode_variant<uint16_t>(c, m, a, plan, blocks);
+    CK_LAUNCH(c);
+    if (timed) EV(c, 1);
+    scan_lengths_kernel<<<1, 1024, 0, c->stream>>>(lens, status, n_chunks, d_offsets, d_summary);
+    CK_LAUNCH(c);
+    if (timed) EV(c, 2);
+    gather_kernel<<<(unsigned)n_chunks, 256, 0, c->stream>>>(staging, pitch, lens, d_offsets, d_out, out_cap);
+    CK_LAUNCH(c);
+    if (timed) EV(c, 3);
+    return RCB_OK;
+}
+
 static int encode_launch(rcb_ctx* c, const void* d_syms, uint64_t n_syms, int sym_bytes, uint64_t chunk_syms,
                          const rcb_model* m, uint8_t* d_out, uint64_t out_cap, uint64_t* d_offsets,
                          uint32_t* d_status, uint64_t pitch_override) {
@@ -578,35 +625,10 @@ static int encode_launch(rcb_ctx* c, const void* d_syms, uint64_t n_syms, int sy
     c->pending_offsets = d_offsets;
     c->pending_n_chunks = n_chunks;
 
-    EncodeArgs a;
-    a.syms = d_syms;
-    a.n_syms = n_syms;
-    a.chunk_syms = chunk_syms;
-    a.n_chunks = n_chunks;
-    a.tabs = m->d_tab;
-    a.hdrs = m->d_hdr;
-    a.K = m->K;
-    a.staging = c->staging;
-    a.pitch = pitch;
-    a.lens = c->lens;
-    a.status = d_status ? d_status : c->status;
-    const EncPlan plan = plan_encode(c, m, n_chunks);
-    a.lanes_per_block = plan.lanes;
-    const unsigned blocks = (unsigned)((n_chunks + plan.lanes - 1) / plan.lanes);
     EV(c, 0);
-    if (sym_bytes == 1)
-        launch_encode_variant<uint8_t>(c, m, a, plan, blocks);
-    else
-        launch_encode_variant<uint16_t>(c, m, a, plan, blocks);
-    CK_LAUNCH(c);
-    EV(c, 1);
-    scan_lengths_kernel<<<1, 1024, 0, c->stream>>>(c->lens, a.status, n_chunks, d_offsets, c->d_summary);
-    CK_LAUNCH(c);
-    EV(c, 2);
-    gather_kernel<<<(unsigned)n_chunks, 256, 0, c->stream>>>(c->staging, pitch, c->lens, d_offsets, d_out,
-                                                            out_cap);
-    CK_LAUNCH(c);
-    EV(c, 3);
+    r = encode_issue(c, d_syms, n_syms, sym_bytes, chunk_syms, m, 0, c->staging, pitch, c->lens,
+                     d_status ? d_status : c->status, d_out, out_cap, d_offsets, c->d_summary, true);
+    if (r) return r;
     c->ev_enc = c->timing;
     return RCB_OK;
 }
@@ -789,41 +811,28 @@ static void launch_decode_row(rcb_ctx* c, const DecodeRowArgs& a, const DecPlan&
     }
 }
 
-extern "C" int rcb_decode_chunks_async(rcb_ctx* c, const uint8_t* d_stream, const uint64_t* d_offsets,
-                                       uint64_t n_syms, int sym_bytes, uint64_t chunk_syms,
-                                       const rcb_model* m, void* d_syms_out, uint32_t* d_status) {
-    if (!c || !m || !m->ready || m->ctx != c || !d_offsets || chunk_syms == 0) return RCB_ERR_INVALID_ARGUMENT;
-    if (n_syms && (!d_stream || !d_syms_out)) return RCB_ERR_INVALID_ARGUMENT;
-    if (sym_bytes != 1 && sym_bytes != 2) return RCB_ERR_UNSUPPORTED;
-    if ((reinterpret_cast<uintptr_t>(d_stream) & 15u) || (reinterpret_cast<uintptr_t>(d_syms_out) & 15u) ||
-        (reinterpret_cast<uintptr_t>(d_offsets) & 7u))
-        return RCB_ERR_INVALID_ARGUMENT;
+// Issue decode + status summary for a run of chunks on the ctx's current stream (explicit buffers, see
+// encode_issue).  d_offsets points at the run's first entry; offsets stay relative to d_stream.
+static int decode_issue(rcb_ctx* c, const uint8_t* d_stream, const uint64_t* d_offsets, uint64_t n_syms,
+                        int sym_bytes, uint64_t chunk_syms, const rcb_model* m, uint64_t model_first,
+                        void* d_syms_out, uint32_t* status, unsigned long long* d_summary, bool timed) {
     const uint64_t n_chunks = (n_syms + chunk_syms - 1) / chunk_syms;
-    if (m->n_models != 1 && m->n_models != n_chunks) return RCB_ERR_INVALID_ARGUMENT;
-    if (n_chunks > 0x7FFFFFFFull) return RCB_ERR_UNSUPPORTED;
-    CK(c, cudaSetDevice(c->device));
-    if (n_chunks == 0) {
-        CK(c, cudaMemsetAsync(c->d_summary + 4, 0, 4 * sizeof(unsigned long long), c->stream));
-        return RCB_OK;
-    }
-    int r = ensure_chunks(c, n_chunks);
-    if (r) return r;
+    const bool shared = m->n_models == 1;
     DecodeArgs a;
     a.stream = d_stream;
     a.offsets = d_offsets;
     a.n_syms = n_syms;
     a.chunk_syms = chunk_syms;
     a.n_chunks = n_chunks;
-    a.tabs = m->d_tab;
-    a.hdrs = m->d_hdr;
+    a.tabs = shared ? m->d_tab : m->d_tab + model_first * m->K;
+    a.hdrs = shared ? m->d_hdr : m->d_hdr + model_first;
     a.lut = m->d_lut;
     a.K = m->K;
-    a.per_chunk = m->n_models != 1;
+    a.per_chunk = !shared;
     a.out = d_syms_out;
-    a.status = d_status ? d_status : c->status;
+    a.status = status;
     const DecPlan plan = plan_decode(c, m, n_chunks);
     const unsigned blocks = (unsigned)((n_chunks + plan.lanes - 1) / plan.lanes);
-    EV(c, 4);
     if (plan.kind == 0) {
         if (sym_bytes == 1)
             launch_decode_variant<uint8_t>(c, m, a, plan, blocks);
@@ -852,10 +861,36 @@ extern "C" int rcb_decode_chunks_async(rcb_ctx* c, const uint8_t* d_stream, cons
         }
     }
     CK_LAUNCH(c);
-    EV(c, 5);
-    status_summary_kernel<<<1, 1024, 0, c->stream>>>(a.status, n_chunks, c->d_summary + 4);
+    if (timed) EV(c, 5);
+    status_summary_kernel<<<1, 1024, 0, c->stream>>>(status, n_chunks, d_summary);
     CK_LAUNCH(c);
-    EV(c, 6);
+    if (timed) EV(c, 6);
+    return RCB_OK;
+}
+
+extern "C" int rcb_decode_chunks_async(rcb_ctx* c, const uint8_t* d_stream, const uint64_t* d_offsets,
+                                       uint64_t n_syms, int sym_bytes, uint64_t chunk_syms,
+                                       const rcb_model* m, void* d_syms_out, uint32_t* d_status) {
+    if (!c || !m || !m->ready || m->ctx != c || !d_offsets || chunk_syms == 0) return RCB_ERR_INVALID_ARGUMENT;
+    if (n_syms && (!d_stream || !d_syms_out)) return RCB_ERR_INVALID_ARGUMENT;
+    if (sym_bytes != 1 && sym_bytes != 2) return RCB_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(d_stream) & 15u) || (reinterpret_cast<uintptr_t>(d_syms_out) & 15u) ||
+        (reinterpret_cast<uintptr_t>(d_offsets) & 7u))
+        return RCB_ERR_INVALID_ARGUMENT;
+    const uint64_t n_chunks = (n_syms + chunk_syms - 1) / chunk_syms;
+    if (m->n_models != 1 && m->n_models != n_chunks) return RCB_ERR_INVALID_ARGUMENT;
+    if (n_chunks > 0x7FFFFFFFull) return RCB_ERR_UNSUPPORTED;
+    CK(c, cudaSetDevice(c->device));
+    if (n_chunks == 0) {
+        CK(c, cudaMemsetAsync(c->d_summary + 4, 0, 4 * sizeof(unsigned long long), c->stream));
+        return RCB_OK;
+    }
+    int r = ensure_chunks(c, n_chunks);
+    if (r) return r;
+    EV(c, 4);
+    r = decode_issue(c, d_stream, d_offsets, n_syms, sym_bytes, chunk_syms, m, 0, d_syms_out,
+                     d_status ? d_status : c->status, c->d_summary + 4, true);
+    if (r) return r;
     c->ev_dec = c->timing;
     return RCB_OK;
 }
@@ -879,6 +914,26 @@ extern "C" int rcb_decode_chunks(rcb_ctx* c, const uint8_t* d_stream, const uint
 }
 
 // ------------------------------------------------------- host-buffer wrappers
+// H2D, code, D2H inside the call.  Large batches are cut into up to 8 slices of whole chunks, each on
+// its own stream: slice k's copy-in overlaps slice k-1's kernels and slice k-2's copy-out, and the
+// slices' kernels run side by side (a slice of the lanes takes as long as all of them: the coder is
+// latency-bound per lane, so the kernels must overlap rather than queue).
+static int ensure_slices(rcb_ctx* c, int n) {
+    for (int i = 0; i < n; i++)
+        if (!c->slice_stream[i]) CK(c, cudaStreamCreateWithFlags(&c->slice_stream[i], cudaStreamNonBlocking));
+    if (!c->d_slice_summary) {
+        CK(c, cudaMalloc(&c->d_slice_summary, 64 * sizeof(unsigned long long)));
+        CK(c, cudaMallocHost(&c->h_slice_summary, 64 * sizeof(unsigned long long)));
+    }
+    return RCB_OK;
+}
+
+static int pick_slices(uint64_t n_chunks, uint64_t bytes) {
+    int s = 8;
+    while (s > 1 && (n_chunks / s < 64 || bytes / s < (8u << 20))) s >>= 1;
+    return s;
+}
+
 extern "C" int rcb_encode_host(rcb_ctx* c, const void* h_syms, uint64_t n_syms, int sym_bytes,
                                uint64_t chunk_syms, const rcb_model* m, uint8_t* h_out, uint64_t out_cap,
                                uint64_t* h_offsets, uint64_t* h_out_bytes) {
@@ -886,26 +941,129 @@ extern "C" int rcb_encode_host(rcb_ctx* c, const void* h_syms, uint64_t n_syms, 
     if (sym_bytes != 1 && sym_bytes != 2) return RCB_ERR_UNSUPPORTED;
     if (n_syms && !h_syms) return RCB_ERR_INVALID_ARGUMENT;
     const uint64_t n_chunks = (n_syms + chunk_syms - 1) / chunk_syms;
+    if (m->n_models != 1 && m->n_models != n_chunks) return RCB_ERR_INVALID_ARGUMENT;
     const uint64_t in_bytes = (n_syms * sym_bytes + 15) & ~15ull;
-    const uint64_t bound = rcb_encode_bound(c, m, n_syms, sym_bytes, chunk_syms) + 16;
-    const uint64_t off_bytes = ((n_chunks + 1) * sizeof(uint64_t) + 15) & ~15ull;
+    const uint64_t pitch = staging_pitch(m, chunk_syms);
+    const uint64_t bound = n_chunks * pitch + 32;
     CK(c, cudaSetDevice(c->device));
+    const int S = pick_slices(n_chunks, n_syms * sym_bytes);
+    const uint64_t off_bytes = ((n_chunks + 1 + S) * sizeof(uint64_t) + 15) & ~15ull;
     int r = ensure_h2d(c, in_bytes + bound + off_bytes + 64);
     if (r) return r;
     uint8_t* d_in = (uint8_t*)c->h2d;
     uint8_t* d_out = d_in + in_bytes;
     uint64_t* d_off = (uint64_t*)(d_out + ((bound + 15) & ~15ull));
-    if (n_syms)
-        CK(c, cudaMemcpyAsync(d_in, h_syms, n_syms * sym_bytes, cudaMemcpyHostToDevice, c->stream));
-    uint64_t total = 0;
-    r = rcb_encode_chunks(c, d_in, n_syms, sym_bytes, chunk_syms, m, d_out, bound, d_off, nullptr, &total);
-    *h_out_bytes = total;
+    if (S == 1 || (chunk_syms * sym_bytes) % 16 != 0) {
+        if (n_syms)
+            CK(c, cudaMemcpyAsync(d_in, h_syms, n_syms * sym_bytes, cudaMemcpyHostToDevice, c->stream));
+        uint64_t total = 0;
+        r = rcb_encode_chunks(c, d_in, n_syms, sym_bytes, chunk_syms, m, d_out, bound, d_off, nullptr, &total);
+        *h_out_bytes = total;
+        if (r) return r;
+        if (total > out_cap) return RCB_ERR_OUT_CAPACITY;
+        CK(c, cudaMemcpyAsync(h_offsets, d_off, (n_chunks + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                              c->stream));
+        if (total) CK(c, cudaMemcpyAsync(h_out, d_out, total, cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        return RCB_OK;
+    }
+    // ---- sliced pipeline
+    r = ensure_slices(c, S);
     if (r) return r;
-    if (total > out_cap) return RCB_ERR_OUT_CAPACITY;
-    CK(c, cudaMemcpyAsync(h_offsets, d_off, (n_chunks + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost,
-                          c->stream));
-    if (total) CK(c, cudaMemcpyAsync(h_out, d_out, total, cudaMemcpyDeviceToHost, c->stream));
+    r = ensure_chunks(c, n_chunks);
+    if (r) return r;
+    r = ensure_staging(c, (size_t)(n_chunks * pitch + 64));
+    if (r) return r;
     CK(c, cudaStreamSynchronize(c->stream));
+    cudaStream_t user_stream = c->stream;
+    uint64_t first[9];
+    for (int k = 0; k <= S; k++) first[k] = n_chunks * k / S;
+    int rc = RCB_OK;
+    for (int k = 0; k < S && rc == RCB_OK; k++) {
+        const uint64_t c0 = first[k], c1 = first[k + 1], nk = c1 - c0;
+        const uint64_t s0 = c0 * chunk_syms, s1 = c1 * chunk_syms < n_syms ? c1 * chunk_syms : n_syms;
+        c->stream = c->slice_stream[k];
+        cudaError_t e = cudaMemcpyAsync(d_in + s0 * sym_bytes, (const uint8_t*)h_syms + s0 * sym_bytes,
+                                        (s1 - s0) * sym_bytes, cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) {
+            c->last_err = e;
+            rc = RCB_ERR_CUDA;
+            break;
+        }
+        // slice-local offsets (k extra slots before it), output region at the slice's worst-case position
+        rc = encode_issue(c, d_in + s0 * sym_bytes, s1 - s0, sym_bytes, chunk_syms, m, c0, c->staging + c0 * pitch,
+                          pitch, c->lens + c0, c->status + c0, d_out + c0 * pitch, nk * pitch, d_off + c0 + k,
+                          c->d_slice_summary + 8 * k, false);
+        if (rc) break;
+        e = cudaMemcpyAsync(c->h_slice_summary + 8 * k, c->d_slice_summary + 8 * k, 4 * sizeof(unsigned long long),
+                            cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(c->h_slice_summary + 8 * k + 4, d_off + c0 + k + nk, sizeof(unsigned long long),
+                                cudaMemcpyDeviceToHost, c->stream);
+        if (e != cudaSuccess) {
+            c->last_err = e;
+            rc = RCB_ERR_CUDA;
+        }
+    }
+    uint64_t base = 0;
+    uint64_t bases[8];
+    bool staging_overflow = false;
+    for (int k = 0; k < S && rc == RCB_OK; k++) {
+        const uint64_t c0 = first[k], nk = first[k + 1] - c0;
+        cudaError_t e = cudaStreamSynchronize(c->slice_stream[k]);
+        if (e != cudaSuccess) {
+            c->last_err = e;
+            rc = RCB_ERR_CUDA;
+            break;
+        }
+        const unsigned long long* sum = c->h_slice_summary + 8 * k;
+        if (sum[0]) {
+            if ((uint32_t)sum[2] == ST_OUT_CAPACITY) staging_overflow = true;
+            else rc = status_to_error((uint32_t)sum[2]);
+            break;
+        }
+        const uint64_t bytes = sum[4];
+        bases[k] = base;
+        if (base + bytes <= out_cap) {
+            e = cudaMemcpyAsync(h_out + base, d_out + c0 * pitch, bytes, cudaMemcpyDeviceToHost, c->slice_stream[k]);
+            if (e == cudaSuccess)
+                // the slice's last entry is the next slice's first: only the final slice copies it
+                e = cudaMemcpyAsync(h_offsets + c0, d_off + c0 + k, (nk + (k == S - 1 ? 1 : 0)) * sizeof(uint64_t),
+                                    cudaMemcpyDeviceToHost, c->slice_stream[k]);
+            if (e != cudaSuccess) {
+                c->last_err = e;
+                rc = RCB_ERR_CUDA;
+                break;
+            }
+        }
+        base += bytes;
+    }
+    for (int k = 0; k < S; k++) cudaStreamSynchronize(c->slice_stream[k]);
+    c->stream = user_stream;
+    if (staging_overflow) {
+        // a staging row was too small for this data (rare): the one-shot path sizes it exactly and reruns
+        if (n_syms)
+            CK(c, cudaMemcpyAsync(d_in, h_syms, n_syms * sym_bytes, cudaMemcpyHostToDevice, c->stream));
+        uint64_t total = 0;
+        r = rcb_encode_chunks(c, d_in, n_syms, sym_bytes, chunk_syms, m, d_out, bound, d_off, nullptr, &total);
+        *h_out_bytes = total;
+        if (r) return r;
+        if (total > out_cap) return RCB_ERR_OUT_CAPACITY;
+        CK(c, cudaMemcpyAsync(h_offsets, d_off, (n_chunks + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                              c->stream));
+        if (total) CK(c, cudaMemcpyAsync(h_out, d_out, total, cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        return RCB_OK;
+    }
+    if (rc) return rc;
+    *h_out_bytes = base;
+    if (base > out_cap) return RCB_ERR_OUT_CAPACITY;
+    // slice-local offsets -> offsets into the concatenated stream (slice k's last entry is slice k+1's first)
+    for (int k = S - 1; k >= 0; k--) {
+        const uint64_t c0 = first[k], nk = first[k + 1] - c0;
+        if (k == S - 1) h_offsets[c0 + nk] += bases[k];
+        for (uint64_t i = 0; i < nk; i++) h_offsets[c0 + i] += bases[k];
+    }
     return RCB_OK;
 }
 
@@ -916,8 +1074,9 @@ extern "C" int rcb_decode_host(rcb_ctx* c, const uint8_t* h_stream, const uint64
     if (sym_bytes != 1 && sym_bytes != 2) return RCB_ERR_UNSUPPORTED;
     if (n_syms && (!h_stream || !h_syms_out)) return RCB_ERR_INVALID_ARGUMENT;
     const uint64_t n_chunks = (n_syms + chunk_syms - 1) / chunk_syms;
+    if (m->n_models != 1 && m->n_models != n_chunks) return RCB_ERR_INVALID_ARGUMENT;
     const uint64_t total = h_offsets[n_chunks];
-    const uint64_t st_bytes = (total + 31) & ~15ull;
+    const uint64_t st_bytes = (total + 47) & ~15ull;
     const uint64_t off_bytes = ((n_chunks + 1) * sizeof(uint64_t) + 15) & ~15ull;
     const uint64_t out_bytes = (n_syms * sym_bytes + 15) & ~15ull;
     CK(c, cudaSetDevice(c->device));
@@ -926,14 +1085,69 @@ extern "C" int rcb_decode_host(rcb_ctx* c, const uint8_t* h_stream, const uint64
     uint8_t* d_st = (uint8_t*)c->h2d;
     uint64_t* d_off = (uint64_t*)(d_st + st_bytes);
     uint8_t* d_out = (uint8_t*)d_off + off_bytes;
-    if (total) CK(c, cudaMemcpyAsync(d_st, h_stream, total, cudaMemcpyHostToDevice, c->stream));
-    CK(c, cudaMemcpyAsync(d_off, h_offsets, (n_chunks + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice,
-                          c->stream));
-    r = rcb_decode_chunks(c, d_st, d_off, n_syms, sym_bytes, chunk_syms, m, d_out, nullptr);
+    const int S = pick_slices(n_chunks, n_syms * sym_bytes);
+    if (S == 1 || (chunk_syms * sym_bytes) % 16 != 0) {
+        if (total) CK(c, cudaMemcpyAsync(d_st, h_stream, total, cudaMemcpyHostToDevice, c->stream));
+        CK(c, cudaMemcpyAsync(d_off, h_offsets, (n_chunks + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice,
+                              c->stream));
+        r = rcb_decode_chunks(c, d_st, d_off, n_syms, sym_bytes, chunk_syms, m, d_out, nullptr);
+        if (r) return r;
+        if (n_syms)
+            CK(c, cudaMemcpyAsync(h_syms_out, d_out, n_syms * sym_bytes, cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        return RCB_OK;
+    }
+    // ---- sliced pipeline
+    r = ensure_slices(c, S);
     if (r) return r;
-    if (n_syms)
-        CK(c, cudaMemcpyAsync(h_syms_out, d_out, n_syms * sym_bytes, cudaMemcpyDeviceToHost, c->stream));
+    r = ensure_chunks(c, n_chunks);
+    if (r) return r;
+    CK(c, cudaMemcpyAsync(d_off, h_offsets, (n_chunks + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
+    cudaStream_t user_stream = c->stream;
+    int rc = RCB_OK;
+    uint64_t first[9];
+    for (int k = 0; k <= S; k++) first[k] = n_chunks * k / S;
+    for (int k = 0; k < S && rc == RCB_OK; k++) {
+        const uint64_t c0 = first[k], c1 = first[k + 1];
+        const uint64_t s0 = c0 * chunk_syms, s1 = c1 * chunk_syms < n_syms ? c1 * chunk_syms : n_syms;
+        const uint64_t b0 = h_offsets[c0], b1 = h_offsets[c1];
+        if (b1 < b0 || b1 > total) {
+            rc = RCB_ERR_INVALID_ARGUMENT;
+            break;
+        }
+        c->stream = c->slice_stream[k];
+        cudaError_t e = cudaSuccess;
+        if (b1 > b0) e = cudaMemcpyAsync(d_st + b0, h_stream + b0, b1 - b0, cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) {
+            c->last_err = e;
+            rc = RCB_ERR_CUDA;
+            break;
+        }
+        rc = decode_issue(c, d_st, d_off + c0, s1 - s0, sym_bytes, chunk_syms, m, c0, d_out + s0 * sym_bytes,
+                          c->status + c0, c->d_slice_summary + 8 * k, false);
+        if (rc) break;
+        e = cudaMemcpyAsync((uint8_t*)h_syms_out + s0 * sym_bytes, d_out + s0 * sym_bytes, (s1 - s0) * sym_bytes,
+                            cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(c->h_slice_summary + 8 * k, c->d_slice_summary + 8 * k,
+                                4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream);
+        if (e != cudaSuccess) {
+            c->last_err = e;
+            rc = RCB_ERR_CUDA;
+        }
+    }
+    for (int k = 0; k < S; k++) {
+        cudaError_t e = cudaStreamSynchronize(c->slice_stream[k]);
+        if (e != cudaSuccess && rc == RCB_OK) {
+            c->last_err = e;
+            rc = RCB_ERR_CUDA;
+        }
+    }
+    c->stream = user_stream;
+    if (rc) return rc;
+    for (int k = 0; k < S; k++)
+        if (c->h_slice_summary[8 * k]) return status_to_error((uint32_t)c->h_slice_summary[8 * k + 2]);
     return RCB_OK;
 }
 

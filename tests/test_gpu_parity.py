@@ -327,6 +327,31 @@ def test_host_buffer_entry_points(ctx, oracle):
     assert np.array_equal(back, syms)
 
 
+def test_host_buffer_pipeline_slices(ctx, oracle):
+    """Large host batches run as slices on several streams; results must not depend on that."""
+    thr = oracle.zipf_thresholds(256, 1.1)
+    n, chunk = 48 * 1024 * 1024 + 4096 * 3, 16384  # 3075 chunks -> 4 slices
+    syms = oracle.generate(n, 256, 0x5EED0001, thr)
+    c, cum, total = oracle.model_from_symbols(syms, 256)
+    model = ctx.model_from_tables(c, cum, total)
+    out, offsets, nbytes = ctx.encode_host(syms, chunk, model)
+    ref_stream, ref_offsets = oracle.encode_chunks(syms, chunk, c, cum, total)
+    assert nbytes == ref_stream.size and np.array_equal(offsets, ref_offsets)
+    assert np.array_equal(out[:nbytes], ref_stream)
+    back = ctx.decode_host(out[:nbytes], offsets, syms.size, chunk, model)
+    assert np.array_equal(back, syms)
+    # per-chunk models through the same pipeline
+    d = to_dev(ctx, syms)
+    counts = ctx.histogram(d, 256, chunk_syms=chunk)
+    pm = ctx.model_from_counts(counts)
+    out2, offsets2, nbytes2 = ctx.encode_host(syms, chunk, pm)
+    s2, o2, nb2 = ctx.encode_chunks(d, chunk, pm)
+    assert nbytes2 == nb2 and np.array_equal(offsets2, dev_to_np(o2).astype(np.uint64))
+    assert np.array_equal(out2[:nbytes2], dev_to_np(s2, nb2))
+    back2 = ctx.decode_host(out2[:nbytes2], offsets2, syms.size, chunk, pm)
+    assert np.array_equal(back2, syms)
+
+
 # ------------------------------------------------ full-size properties (1 GiB)
 def test_full_size_round_trip_and_sampled_parity(ctx, oracle):
     """BASELINE.json configs[1] at full size: 1 GiB Zipf(1.1), 64 KiB chunks.
