@@ -202,6 +202,37 @@ int rcb_encode_stream(rcb_ctx *ctx, rcb_stream_state *st, const void *h_syms, ui
 int rcb_decode_stream(rcb_ctx *ctx, rcb_stream_state *st, const uint8_t *h_code, uint64_t code_len,
                       uint64_t n_syms, int sym_bytes, const rcb_model *m, void *h_syms_out);
 
+/* ---- framed container (the reference has no wire format:
+ * Encoder::finish returns raw bytes and the symbol count / model travel out of
+ * band, src/encoder.rs:40-46, examples/sample_impl.rs:113).  Little-endian:
+ *   "RCB2" | version u32 | sym_bytes u32 | K u32 | model_mode u32 (0 shared, 1 per chunk)
+ *   | chunk_syms u64 | n_syms u64 | n_chunks u64 | payload_bytes u64
+ *   | model: shared    -> total u32, reserved u32, cum[K] u32, c[K] u32
+ *            per chunk -> c[n_chunks][K] u32 (cum = exclusive scan, total = sum)
+ *   | offsets u64[n_chunks+1] | payload (chunk i = payload[offsets[i]..offsets[i+1]),
+ *     exactly the reference's finish() bytes for that chunk)
+ * Pure host-side byte layout; all coding stays in the entry points above. */
+typedef struct rcb_frame_info {
+    uint32_t version, sym_bytes, K, model_mode;
+    uint64_t chunk_syms, n_syms, n_chunks, payload_bytes;
+    uint64_t model_off, offsets_off, payload_off, frame_bytes;
+} rcb_frame_info;
+uint64_t rcb_frame_bound(uint32_t K, uint64_t n_chunks, int per_chunk, uint64_t payload_bytes);
+/* model tables are read back from the device; h_stream/h_offsets as produced by rcb_encode_host */
+int rcb_frame_write(rcb_ctx *ctx, const rcb_model *m, int sym_bytes, uint64_t chunk_syms, uint64_t n_syms,
+                    const uint8_t *h_stream, const uint64_t *h_offsets, uint8_t *h_frame,
+                    uint64_t frame_cap, uint64_t *h_frame_bytes);
+/* validates the header and section sizes against len */
+int rcb_frame_parse(const uint8_t *h_frame, uint64_t len, rcb_frame_info *info);
+/* device model from the frame's model section (caller destroys it) */
+int rcb_frame_model(rcb_ctx *ctx, const uint8_t *h_frame, const rcb_frame_info *info, rcb_model **out);
+/* encode_host + frame_write / parse + model + decode_host */
+int rcb_frame_encode_host(rcb_ctx *ctx, const void *h_syms, uint64_t n_syms, int sym_bytes,
+                          uint64_t chunk_syms, const rcb_model *m, uint8_t *h_frame, uint64_t frame_cap,
+                          uint64_t *h_frame_bytes);
+int rcb_frame_decode_host(rcb_ctx *ctx, const uint8_t *h_frame, uint64_t len, void *h_syms_out,
+                          uint64_t out_cap_bytes, uint64_t *h_n_syms);
+
 /* ---- synthetic data (benchmark inputs; not in the reference)
  * symbol j = #{ i < K-1 : thr[t][i] <= mix64(seed + j*GOLDEN) >> 32 },
  * t = (j / chunk_syms) % n_tables; h_thr = uint32[n_tables][K-1]. */

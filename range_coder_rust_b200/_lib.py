@@ -50,6 +50,12 @@ SIGNATURES = {
     "rcb_stream_state_init": (None, [vp]),
     "rcb_encode_stream": (ci, [vp, vp, vp, u64, ci, vp, vp, u64, u64p, vp, ci]),
     "rcb_decode_stream": (ci, [vp, vp, vp, u64, u64, ci, vp, vp]),
+    "rcb_frame_bound": (u64, [u32, u64, ci, u64]),
+    "rcb_frame_write": (ci, [vp, vp, ci, u64, u64, vp, vp, vp, u64, u64p]),
+    "rcb_frame_parse": (ci, [vp, u64, vp]),
+    "rcb_frame_model": (ci, [vp, vp, vp, ctypes.POINTER(vp)]),
+    "rcb_frame_encode_host": (ci, [vp, vp, u64, ci, u64, vp, vp, u64, u64p]),
+    "rcb_frame_decode_host": (ci, [vp, vp, u64, vp, u64, u64p]),
     "rcb_generate": (ci, [vp, vp, u64, u64, ci, u32, u64, vp, u32, u64]),
 }
 

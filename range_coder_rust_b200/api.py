@@ -22,6 +22,13 @@ def _np_ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
 
 
+class FrameInfo(ctypes.Structure):
+    """struct rcb_frame_info (include/rcb200.h)."""
+    _fields_ = [(n, ctypes.c_uint32) for n in ("version", "sym_bytes", "K", "model_mode")] + \
+               [(n, ctypes.c_uint64) for n in ("chunk_syms", "n_syms", "n_chunks", "payload_bytes", "model_off",
+                                               "offsets_off", "payload_off", "frame_bytes")]
+
+
 class Model:
     """Dense snapshot of a PModel (src/pmodel.rs:4-13): one table shared by all
     chunks (n_models == 1) or one per chunk."""
@@ -250,6 +257,37 @@ class Context:
                                       chunk_syms, model.h, _np_ptr(out_np))
         self._check(rc, "rcb_decode_host")
         return out_np
+
+    # ------------------------------------------------------- framed container
+    def frame_encode(self, syms_np, chunk_syms, model):
+        """encode_host + the RCB2 container (rcb200.h); returns the frame as uint8[]."""
+        syms_np = np.ascontiguousarray(syms_np)
+        sb, n = syms_np.dtype.itemsize, syms_np.size
+        n_chunks = (n + chunk_syms - 1) // chunk_syms
+        cap = self.lib.rcb_frame_bound(model.K, n_chunks, int(model.n_models != 1),
+                                       self.encode_bound(model, n, sb, chunk_syms))
+        frame = np.empty(cap, dtype=np.uint8)
+        nbytes = ctypes.c_uint64()
+        rc = self.lib.rcb_frame_encode_host(self.h, _np_ptr(syms_np), n, sb, chunk_syms, model.h, _np_ptr(frame),
+                                            frame.size, ctypes.byref(nbytes))
+        self._check(rc, "rcb_frame_encode_host")
+        return frame[:int(nbytes.value)]
+
+    def frame_info(self, frame_np):
+        frame_np = np.ascontiguousarray(frame_np, dtype=np.uint8)
+        info = FrameInfo()
+        self._check(self.lib.rcb_frame_parse(_np_ptr(frame_np), frame_np.size, ctypes.byref(info)), "rcb_frame_parse")
+        return info
+
+    def frame_decode(self, frame_np):
+        frame_np = np.ascontiguousarray(frame_np, dtype=np.uint8)
+        info = self.frame_info(frame_np)
+        out = np.empty(info.n_syms, dtype=np.uint8 if info.sym_bytes == 1 else np.uint16)
+        n = ctypes.c_uint64()
+        rc = self.lib.rcb_frame_decode_host(self.h, _np_ptr(frame_np), frame_np.size, _np_ptr(out), out.nbytes,
+                                            ctypes.byref(n))
+        self._check(rc, "rcb_frame_decode_host")
+        return out
 
     # ------------------------------------------------------- synthetic data
     def generate(self, n, K, seed, thresholds, sym_bytes=1, chunk_syms=0, first=0, out=None):

@@ -1271,3 +1271,215 @@ extern "C" int rcb_decode_stream(rcb_ctx* c, rcb_stream_state* st, const uint8_t
     if (st->status) return status_to_error(st->status);
     return RCB_OK;
 }
+
+// ------------------------------------------------------------ framed container
+// Host-side byte layout only (see rcb200.h); no symbol is coded here.
+namespace {
+const uint64_t FRAME_HDR = 56;
+inline uint64_t al8(uint64_t x) { return (x + 7) & ~7ull; }
+inline uint64_t frame_model_bytes(uint32_t K, uint64_t n_chunks, int per_chunk) {
+    return per_chunk ? al8(n_chunks * (uint64_t)K * 4) : al8(8 + (uint64_t)K * 8);
+}
+template <typename T>
+inline void put_le(uint8_t* p, T v) { memcpy(p, &v, sizeof v); }  // x86-64 / aarch64 hosts are little-endian
+template <typename T>
+inline T get_le(const uint8_t* p) {
+    T v;
+    memcpy(&v, p, sizeof v);
+    return v;
+}
+}  // namespace
+
+extern "C" uint64_t rcb_frame_bound(uint32_t K, uint64_t n_chunks, int per_chunk, uint64_t payload_bytes) {
+    return FRAME_HDR + frame_model_bytes(K, n_chunks, per_chunk) + (n_chunks + 1) * 8 + payload_bytes;
+}
+
+extern "C" int rcb_frame_write(rcb_ctx* c, const rcb_model* m, int sym_bytes, uint64_t chunk_syms, uint64_t n_syms,
+                               const uint8_t* h_stream, const uint64_t* h_offsets, uint8_t* h_frame,
+                               uint64_t frame_cap, uint64_t* h_frame_bytes) {
+    if (!c || !m || !m->ready || !h_offsets || !h_frame || !h_frame_bytes || chunk_syms == 0)
+        return RCB_ERR_INVALID_ARGUMENT;
+    const uint64_t n_chunks = (n_syms + chunk_syms - 1) / chunk_syms;
+    const int per_chunk = m->n_models != 1;
+    if (per_chunk && m->n_models != n_chunks) return RCB_ERR_INVALID_ARGUMENT;
+    if (per_chunk && (m->bad_bits & 8u)) return RCB_ERR_UNSUPPORTED;  // per-chunk section stores c only
+    const uint64_t payload = h_offsets[n_chunks];
+    if (payload && !h_stream) return RCB_ERR_INVALID_ARGUMENT;
+    const uint64_t need = rcb_frame_bound(m->K, n_chunks, per_chunk, payload);
+    *h_frame_bytes = need;
+    if (need > frame_cap) return RCB_ERR_OUT_CAPACITY;
+    uint8_t* p = h_frame;
+    memcpy(p, "RCB2", 4);
+    put_le<uint32_t>(p + 4, 1);
+    put_le<uint32_t>(p + 8, (uint32_t)sym_bytes);
+    put_le<uint32_t>(p + 12, m->K);
+    put_le<uint32_t>(p + 16, (uint32_t)per_chunk);
+    put_le<uint32_t>(p + 20, 0);
+    put_le<uint64_t>(p + 24, chunk_syms);
+    put_le<uint64_t>(p + 32, n_syms);
+    put_le<uint64_t>(p + 40, n_chunks);
+    put_le<uint64_t>(p + 48, payload);
+    uint8_t* ms = p + FRAME_HDR;
+    CK(c, cudaSetDevice(c->device));
+    const size_t n_ent = (size_t)m->n_models * m->K;
+    uint2* tmp = (uint2*)malloc(n_ent * sizeof(uint2));
+    if (!tmp) return RCB_ERR_INVALID_ARGUMENT;
+    cudaError_t e = cudaMemcpyAsync(tmp, m->d_tab, n_ent * sizeof(uint2), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+        free(tmp);
+        c->last_err = e;
+        return RCB_ERR_CUDA;
+    }
+    memset(ms, 0, frame_model_bytes(m->K, n_chunks, per_chunk));
+    if (!per_chunk) {
+        put_le<uint32_t>(ms, m->h_hdr0.div.total);
+        for (uint32_t i = 0; i < m->K; i++) {
+            put_le<uint32_t>(ms + 8 + 4 * (uint64_t)i, tmp[i].x);
+            put_le<uint32_t>(ms + 8 + 4 * ((uint64_t)m->K + i), tmp[i].y);
+        }
+    } else {
+        for (size_t i = 0; i < n_ent; i++) put_le<uint32_t>(ms + 4 * i, tmp[i].y);
+    }
+    free(tmp);
+    uint8_t* os = ms + frame_model_bytes(m->K, n_chunks, per_chunk);
+    memcpy(os, h_offsets, (n_chunks + 1) * 8);
+    if (payload) memcpy(os + (n_chunks + 1) * 8, h_stream, payload);
+    return RCB_OK;
+}
+
+extern "C" int rcb_frame_parse(const uint8_t* h_frame, uint64_t len, rcb_frame_info* info) {
+    if (!h_frame || !info || len < FRAME_HDR) return RCB_ERR_INVALID_ARGUMENT;
+    if (memcmp(h_frame, "RCB2", 4) != 0) return RCB_ERR_INVALID_ARGUMENT;
+    rcb_frame_info f;
+    f.version = get_le<uint32_t>(h_frame + 4);
+    f.sym_bytes = get_le<uint32_t>(h_frame + 8);
+    f.K = get_le<uint32_t>(h_frame + 12);
+    f.model_mode = get_le<uint32_t>(h_frame + 16);
+    f.chunk_syms = get_le<uint64_t>(h_frame + 24);
+    f.n_syms = get_le<uint64_t>(h_frame + 32);
+    f.n_chunks = get_le<uint64_t>(h_frame + 40);
+    f.payload_bytes = get_le<uint64_t>(h_frame + 48);
+    if (f.version != 1 || (f.sym_bytes != 1 && f.sym_bytes != 2) || f.K == 0 || f.K > MAX_K || f.model_mode > 1 ||
+        f.chunk_syms == 0)
+        return RCB_ERR_INVALID_ARGUMENT;
+    if (f.n_chunks != (f.n_syms + f.chunk_syms - 1) / f.chunk_syms) return RCB_ERR_INVALID_ARGUMENT;
+    if (f.n_chunks > (1ull << 40) || f.payload_bytes > len) return RCB_ERR_INVALID_ARGUMENT;
+    f.model_off = FRAME_HDR;
+    f.offsets_off = f.model_off + frame_model_bytes(f.K, f.n_chunks, (int)f.model_mode);
+    f.payload_off = f.offsets_off + (f.n_chunks + 1) * 8;
+    f.frame_bytes = f.payload_off + f.payload_bytes;
+    if (f.frame_bytes > len) return RCB_ERR_TRUNCATED_STREAM;
+    // offsets must be monotone and end at payload_bytes
+    uint64_t prev = 0;
+    for (uint64_t i = 0; i <= f.n_chunks; i++) {
+        const uint64_t o = get_le<uint64_t>(h_frame + f.offsets_off + 8 * i);
+        if (o < prev || o > f.payload_bytes) return RCB_ERR_INVALID_ARGUMENT;
+        prev = o;
+    }
+    if (prev != f.payload_bytes) return RCB_ERR_INVALID_ARGUMENT;
+    *info = f;
+    return RCB_OK;
+}
+
+extern "C" int rcb_frame_model(rcb_ctx* c, const uint8_t* h_frame, const rcb_frame_info* f, rcb_model** out) {
+    if (!c || !h_frame || !f || !out) return RCB_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    const uint64_t n_models = f->model_mode ? f->n_chunks : 1;
+    if (n_models == 0) return RCB_ERR_INVALID_ARGUMENT;
+    rcb_model* m = nullptr;
+    int r = rcb_model_create(c, f->K, n_models, &m);
+    if (r) return r;
+    const uint8_t* ms = h_frame + f->model_off;
+    const size_t n_ent = (size_t)n_models * f->K;
+    uint32_t* cc = (uint32_t*)malloc(n_ent * 4);
+    uint32_t* cum = (uint32_t*)malloc(n_ent * 4);
+    uint32_t* tot = (uint32_t*)malloc(n_models * 4);
+    if (!cc || !cum || !tot) {
+        free(cc);
+        free(cum);
+        free(tot);
+        rcb_model_destroy(m);
+        return RCB_ERR_INVALID_ARGUMENT;
+    }
+    if (!f->model_mode) {
+        tot[0] = get_le<uint32_t>(ms);
+        for (uint32_t i = 0; i < f->K; i++) {
+            cum[i] = get_le<uint32_t>(ms + 8 + 4 * (uint64_t)i);
+            cc[i] = get_le<uint32_t>(ms + 8 + 4 * ((uint64_t)f->K + i));
+        }
+    } else {
+        for (uint64_t j = 0; j < n_models; j++) {
+            uint32_t run = 0;  // examples/sample_impl.rs:61-69
+            for (uint32_t i = 0; i < f->K; i++) {
+                const uint32_t v = get_le<uint32_t>(ms + 4 * (j * f->K + i));
+                cc[j * f->K + i] = v;
+                cum[j * f->K + i] = run;
+                run += v;
+            }
+            tot[j] = run;
+        }
+    }
+    r = rcb_model_from_tables(c, m, cc, cum, tot);
+    free(cc);
+    free(cum);
+    free(tot);
+    if (r) {
+        rcb_model_destroy(m);
+        return r;
+    }
+    *out = m;
+    return RCB_OK;
+}
+
+extern "C" int rcb_frame_encode_host(rcb_ctx* c, const void* h_syms, uint64_t n_syms, int sym_bytes,
+                                     uint64_t chunk_syms, const rcb_model* m, uint8_t* h_frame, uint64_t frame_cap,
+                                     uint64_t* h_frame_bytes) {
+    if (!c || !m || !m->ready || !h_frame || !h_frame_bytes || chunk_syms == 0) return RCB_ERR_INVALID_ARGUMENT;
+    const uint64_t n_chunks = (n_syms + chunk_syms - 1) / chunk_syms;
+    const uint64_t cap = rcb_encode_bound(c, m, n_syms, sym_bytes, chunk_syms) + 64;
+    uint8_t* stream = (uint8_t*)malloc(cap);
+    uint64_t* offs = (uint64_t*)malloc((n_chunks + 1) * 8);
+    if (!stream || !offs) {
+        free(stream);
+        free(offs);
+        return RCB_ERR_INVALID_ARGUMENT;
+    }
+    uint64_t bytes = 0;
+    int r = rcb_encode_host(c, h_syms, n_syms, sym_bytes, chunk_syms, m, stream, cap, offs, &bytes);
+    if (r == RCB_OK)
+        r = rcb_frame_write(c, m, sym_bytes, chunk_syms, n_syms, stream, offs, h_frame, frame_cap, h_frame_bytes);
+    free(stream);
+    free(offs);
+    return r;
+}
+
+extern "C" int rcb_frame_decode_host(rcb_ctx* c, const uint8_t* h_frame, uint64_t len, void* h_syms_out,
+                                     uint64_t out_cap_bytes, uint64_t* h_n_syms) {
+    rcb_frame_info f;
+    int r = rcb_frame_parse(h_frame, len, &f);
+    if (r) return r;
+    if (h_n_syms) *h_n_syms = f.n_syms;
+    if (f.n_syms * f.sym_bytes > out_cap_bytes) return RCB_ERR_OUT_CAPACITY;
+    if (f.n_syms == 0) return RCB_OK;
+    rcb_model* m = nullptr;
+    r = rcb_frame_model(c, h_frame, &f, &m);
+    if (r) return r;
+    // payload padded to a multiple of 16 bytes for the device reader; offsets may be unaligned in the frame
+    uint8_t* stream = (uint8_t*)malloc((size_t)f.payload_bytes + 64);
+    uint64_t* offs = (uint64_t*)malloc((size_t)(f.n_chunks + 1) * 8);
+    if (!stream || !offs) {
+        free(stream);
+        free(offs);
+        rcb_model_destroy(m);
+        return RCB_ERR_INVALID_ARGUMENT;
+    }
+    memcpy(stream, h_frame + f.payload_off, (size_t)f.payload_bytes);
+    memset(stream + f.payload_bytes, 0, 64);
+    memcpy(offs, h_frame + f.offsets_off, (size_t)(f.n_chunks + 1) * 8);
+    r = rcb_decode_host(c, stream, offs, f.n_syms, (int)f.sym_bytes, f.chunk_syms, m, h_syms_out);
+    free(stream);
+    free(offs);
+    rcb_model_destroy(m);
+    return r;
+}

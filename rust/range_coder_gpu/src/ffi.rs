@@ -1,0 +1,119 @@
+//! Raw declarations of include/rcb200.h (the subset the safe layer uses).
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)]
+pub struct RcbCtx {
+    _p: [u8; 0],
+}
+#[repr(C)]
+pub struct RcbModel {
+    _p: [u8; 0],
+}
+
+/// `rcb_stream_state`: RangeCoder { lower_bound, range } (src/range_coder.rs:7-12 of the reference)
+/// + Decoder::data (src/decoder.rs:8-12) + bookkeeping.
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct RcbStreamState {
+    pub lower_bound: u64,
+    pub range: u64,
+    pub data: u64,
+    pub consumed: u64,
+    pub status: u32,
+    pub pad: u32,
+}
+
+pub const RCB_OK: c_int = 0;
+pub const RCB_ERR_ZERO_TOTAL: c_int = -3;
+pub const RCB_ERR_ZERO_FREQ_SYMBOL: c_int = -4;
+pub const RCB_ERR_LOWER_OVERFLOW: c_int = -5;
+pub const RCB_ERR_UPPER_OVERFLOW: c_int = -6;
+pub const RCB_ERR_SYMBOL_OUT_OF_RANGE: c_int = -7;
+pub const RCB_ERR_OUT_CAPACITY: c_int = -8;
+pub const RCB_ERR_TRUNCATED_STREAM: c_int = -9;
+
+extern "C" {
+    pub fn rcb_ctx_create(device: c_int, stream: *mut c_void, out: *mut *mut RcbCtx) -> c_int;
+    pub fn rcb_ctx_destroy(ctx: *mut RcbCtx) -> c_int;
+    pub fn rcb_strerror(code: c_int) -> *const c_char;
+
+    pub fn rcb_model_create(ctx: *mut RcbCtx, k: u32, n_models: u64, out: *mut *mut RcbModel) -> c_int;
+    pub fn rcb_model_destroy(m: *mut RcbModel) -> c_int;
+    pub fn rcb_model_from_tables(
+        ctx: *mut RcbCtx,
+        m: *mut RcbModel,
+        c: *const u32,
+        cum: *const u32,
+        total: *const u32,
+    ) -> c_int;
+
+    pub fn rcb_encode_bound(ctx: *mut RcbCtx, m: *const RcbModel, n: u64, sym_bytes: c_int, chunk: u64) -> u64;
+    pub fn rcb_encode_host(
+        ctx: *mut RcbCtx,
+        syms: *const c_void,
+        n: u64,
+        sym_bytes: c_int,
+        chunk: u64,
+        m: *const RcbModel,
+        out: *mut u8,
+        cap: u64,
+        offsets: *mut u64,
+        out_bytes: *mut u64,
+    ) -> c_int;
+    pub fn rcb_decode_host(
+        ctx: *mut RcbCtx,
+        stream: *const u8,
+        offsets: *const u64,
+        n: u64,
+        sym_bytes: c_int,
+        chunk: u64,
+        m: *const RcbModel,
+        out: *mut c_void,
+    ) -> c_int;
+
+    pub fn rcb_stream_state_init(st: *mut RcbStreamState);
+    pub fn rcb_encode_stream(
+        ctx: *mut RcbCtx,
+        st: *mut RcbStreamState,
+        h_syms: *const c_void,
+        n_syms: u64,
+        sym_bytes: c_int,
+        m: *const RcbModel,
+        h_out: *mut u8,
+        out_cap: u64,
+        h_n_out: *mut u64,
+        h_per_symbol: *mut u32,
+        finish: c_int,
+    ) -> c_int;
+    pub fn rcb_decode_stream(
+        ctx: *mut RcbCtx,
+        st: *mut RcbStreamState,
+        h_code: *const u8,
+        code_len: u64,
+        n_syms: u64,
+        sym_bytes: c_int,
+        m: *const RcbModel,
+        h_syms_out: *mut c_void,
+    ) -> c_int;
+
+    pub fn rcb_frame_bound(k: u32, n_chunks: u64, per_chunk: c_int, payload: u64) -> u64;
+    pub fn rcb_frame_encode_host(
+        ctx: *mut RcbCtx,
+        syms: *const c_void,
+        n: u64,
+        sym_bytes: c_int,
+        chunk: u64,
+        m: *const RcbModel,
+        frame: *mut u8,
+        cap: u64,
+        frame_bytes: *mut u64,
+    ) -> c_int;
+    pub fn rcb_frame_decode_host(
+        ctx: *mut RcbCtx,
+        frame: *const u8,
+        len: u64,
+        out: *mut c_void,
+        out_cap_bytes: u64,
+        n_syms: *mut u64,
+    ) -> c_int;
+}

@@ -81,3 +81,22 @@ def test_version_and_strerror():
     assert lib.rcb_version() == 100
     assert lib.rcb_strerror(0) == b"ok"
     assert b"LowerBoundOverflow" in lib.rcb_strerror(_lib.RCB_ERR_LOWER_OVERFLOW)
+
+
+def test_rust_ffi_declarations_match_header():
+    """rust/range_coder_gpu/src/ffi.rs cannot be compiled here (no Rust toolchain): at least keep its
+    extern block in step with include/rcb200.h -- same names, same parameter counts."""
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "rcb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    rs = open(os.path.join(root, "rust", "range_coder_gpu", "src", "ffi.rs")).read()
+    decls = re.findall(r"pub fn (rcb_\w+)\s*\((.*?)\)\s*(?:->\s*[\w:* ]+)?;", rs, flags=re.S)
+    assert len(decls) >= 12
+    for name, params in decls:
+        m = re.search(r"\b%s\s*\((.*?)\)\s*;" % name, hdr, flags=re.S)
+        assert m, f"{name} not declared in rcb200.h"
+        n_c = 0 if m.group(1).strip() in ("", "void") else m.group(1).count(",") + 1
+        n_rs = len([p for p in params.split(",") if p.strip()])
+        assert n_c == n_rs, f"{name}: header has {n_c} parameters, ffi.rs {n_rs}"
