@@ -57,54 +57,92 @@ def workload_name(a):
 
 
 # ----------------------------------------------------------------- clocks
+def nvml_handle(index):
+    """NVML handle of torch's cuda:<index> (by UUID, so CUDA_VISIBLE_DEVICES does not matter)."""
+    import pynvml
+    import torch
+
+    pynvml.nvmlInit()
+    uuid = str(torch.cuda.get_device_properties(index).uuid)
+    if not uuid.startswith("GPU-"):
+        uuid = "GPU-" + uuid
+    try:
+        return pynvml.nvmlDeviceGetHandleByUUID(uuid)
+    except Exception:
+        return pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+
+
 class ClockSampler:
-    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML from a thread of this process while the timed
+    region runs (every ~2 ms; `nvidia-smi -lms` starts too slowly for a region of tens of ms)."""
 
     def __init__(self, index):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.max_mhz = None
+        self.error = None
+
+    def _sample(self, pynvml, h):
+        self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+        r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+        for bit, name in ((pynvml.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"),
+                          (pynvml.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                          (pynvml.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                          (pynvml.nvmlClocksEventReasonHwPowerBrakeSlowdown, "hw_power_brake_slowdown"),
+                          (pynvml.nvmlClocksEventReasonSwPowerCap, "sw_power_cap")):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _run(self, pynvml, h):
+        while not self.stop_flag.is_set():
+            try:
+                self._sample(pynvml, h)
+            except Exception as e:  # keep what we have
+                self.error = repr(e)
+                return
+            time.sleep(0.002)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+            import pynvml
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            h = nvml_handle(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._run, args=(pynvml, h), daemon=True)
+            self.thread.start()
+        except Exception as e:
+            self.error = repr(e)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self.stop_flag.set()
+        if self.thread:
+            self.thread.join(timeout=5)
+        out = {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+               "samples": len(self.samples), "reasons": sorted(self.reasons)}
+        if self.error:
+            out["error"] = self.error
+        return out
+
+
+def bind_near_gpu(index):
+    """Run this rank on the CPUs NVML reports as local to its GPU, so that the pinned host buffers of the
+    end-to-end leg are allocated on the GPU's NUMA node.  Returns the previous affinity (to restore)."""
+    try:
+        import pynvml
+
+        h = nvml_handle(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, x in enumerate(words) for b in range(64) if (x >> b) & 1}
+        old = os.sched_getaffinity(0)
+        cpus &= old
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return old
+    except Exception:
+        return None
 
 
 # -------------------------------------------------------- reference arm (CPU)
@@ -310,6 +348,7 @@ def run_ours(a):
     # ---- end to end through the host-buffer C ABI (pinned host memory, copies inside the timed region)
     e2e = None
     if not a.no_e2e:
+        old_affinity = bind_near_gpu(local_rank)
         h_syms = torch.empty(n_syms, dtype=d_syms.dtype, pin_memory=True)
         h_syms.copy_(d_syms)
         h_stream = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
@@ -337,6 +376,8 @@ def run_ours(a):
                "h2d_bytes_per_step": int(n + nb + off_bytes), "d2h_bytes_per_step": int(nb + off_bytes + n),
                "steps": a.e2e_steps, "ms_per_step": dt / a.e2e_steps * 1e3,
                "api": "rcb_encode_host + rcb_decode_host (C ABI, pinned host buffers)"}
+        if old_affinity:
+            os.sched_setaffinity(0, old_affinity)
 
     # ---- CPU baseline (rank 0, N=1): oracle port on a bounded sample of the same workload; doubles as parity check
     cpu = None

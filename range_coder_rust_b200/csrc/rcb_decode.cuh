@@ -73,12 +73,11 @@ struct RingFill {
     const uint8_t* pbase;  // 16-byte aligned
     uint32_t wr;           // pieces requested so far
     uint32_t npieces;      // pieces that exist in the readable stream
-    uint32_t pend;         // bytes requested in the most recent committed group
     __device__ __forceinline__ void issue_if(bool p, uint32_t ring) {
         const uint32_t saddr = ring + (wr & (RING_PIECES - 1)) * 16;
         const uint8_t* g = pbase + (uint64_t)wr * 16;
         asm volatile(
-            "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q cp.async.cg.shared.global [%0], [%1], 16;\n\t}"
+            "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q cp.async.cg.shared.global.L2::256B [%0], [%1], 16;\n\t}"
             :
             : "r"(saddr), "l"(g), "r"((uint32_t)p)
             : "memory");
@@ -88,19 +87,29 @@ struct RingFill {
     __device__ __forceinline__ void round(RingFetch& f) {
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         uint32_t occ = wr * 16 - f.rd * 4;  // bytes requested and not yet consumed
-        if (occ < 64u + pend) {             // backstop (rare): less than 64 completed bytes ahead
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            pend = 0;
-        }
+        // No "ring ran dry" check is needed: wait_group 1 leaves only the newest group (<= 32 bytes, the
+        // pieces furthest ahead) in flight; a word consumes <= 12 bytes on the fast path and the ring is
+        // topped up to > 112 bytes every round, so the completed part never drops below ~64 bytes.  The
+        // exact path (which may consume more) drains the ring first and re-attaches or resyncs after.
         const bool p1 = (occ <= RING_PIECES * 16 - 16) & (wr < npieces);
         issue_if(p1, f.ring);
         occ += p1 ? 16u : 0u;
         const bool p2 = (occ <= RING_PIECES * 16 - 16) & (wr < npieces);
         issue_if(p2, f.ring);
         asm volatile("cp.async.commit_group;" ::: "memory");
-        pend = (p1 ? 16u : 0u) + (p2 ? 16u : 0u);
     }
-    // (Re)start after the read position moved arbitrarily (initial fill, exact out-of-line path).
+    // Before the exact out-of-line path: everything requested has landed, so that path can read the ring.
+    __device__ __forceinline__ void drain() {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    // After it (drain() was called before): the ring still holds every requested piece.
+    __device__ __forceinline__ void after_exact(RingFetch& f) {
+        if (RCB_LIKELY(f.rd * 4 < wr * 16))
+            f.reload();
+        else
+            resync(f);
+    }
+    // (Re)start after the read position moved arbitrarily (initial fill, exact path past the ring).
     __device__ __forceinline__ void resync(RingFetch& f) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (f.rd * 4 >= wr * 16) wr = f.rd >> 2;  // consumed past everything requested
@@ -110,21 +119,40 @@ struct RingFill {
             issue_if(true, f.ring);
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        pend = 0;
         f.reload();
     }
 };
 
 // ---------------------------------------------------------------------------
-// Fetch for the exact out-of-line path: plain global loads (clamped to the
-// readable stream), no lookahead needed there.
+// Fetch for the exact out-of-line path: the current word is cached; a new word comes from the
+// lane's ring while it is inside the requested window [ring_lo, ring_hi) (the caller drained the
+// ring first), else from global memory (clamped to the readable stream).
 // ---------------------------------------------------------------------------
 struct GlobalFetch {
     const uint32_t* base;  // pbase as words
-    uint32_t idx;          // words consumed
+    uint32_t idx;          // words consumed; `cur` holds word idx
     uint32_t last;         // last readable word
-    __device__ __forceinline__ uint32_t peek_be32() const { return bswap32(__ldg(base + (idx < last ? idx : last))); }
-    __device__ __forceinline__ void advance_if(bool p) { idx += p ? 1u : 0u; }
+    uint32_t ring;         // shared-space address of the lane's ring (0: none)
+    uint32_t ring_lo, ring_hi;
+    uint32_t cur;
+    __device__ __forceinline__ GlobalFetch(const uint32_t* b, uint32_t i, uint32_t l, uint32_t r = 0, uint32_t rlo = 0,
+                                           uint32_t rhi = 0)
+        : base(b), idx(i), last(l), ring(r), ring_lo(rlo), ring_hi(rhi) {
+        load();
+    }
+    __device__ __forceinline__ void load() {
+        if (ring && idx >= ring_lo && idx < ring_hi)
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(cur) : "r"(ring + (idx & (RING_PIECES * 4 - 1)) * 4) : "memory");
+        else
+            cur = __ldg(base + (idx < last ? idx : last));
+    }
+    __device__ __forceinline__ uint32_t peek_be32() const { return bswap32(cur); }
+    __device__ __forceinline__ void advance_if(bool p) {
+        if (p) {
+            idx++;
+            load();
+        }
+    }
 };
 
 __device__ __forceinline__ void prefetch_l2_bulk_dec(const void* p, uint32_t bytes) {
@@ -146,6 +174,7 @@ struct DecLaneState {
     const uint32_t* base;
     uint32_t rd, last;
     uint32_t err, syms;  // syms: symbols decoded by the call, packed like the output word
+    uint32_t ring, ring_hi;  // drained ring: words [ring_hi - 32, ring_hi) are in shared memory (ring 0: none)
 };
 
 // One symbol on the exact path: the reference's search in the product domain plus the
@@ -178,7 +207,8 @@ template <bool CHECKED>
 __device__ __noinline__ DecLaneState dec_exact(DecLaneState s, const uint2* tab, uint32_t K, DivParams div,
                                                uint32_t pow2, uint32_t n_syms, uint32_t sym_bits,
                                                uint32_t lut_saddr, float lut_scale) {
-    GlobalFetch gf{s.base, s.rd, s.last};
+    GlobalFetch gf(s.base, s.rd, s.last, s.ring, s.ring_hi > RING_PIECES * 4 ? s.ring_hi - RING_PIECES * 4 : 0u,
+                   s.ring_hi);
     DecSink<GlobalFetch> sink(gf);
     sink.dh = s.dh;
     sink.dl = s.dl;
@@ -239,6 +269,7 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
         __syncthreads();
     }
     const uint64_t chunk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned live = __ballot_sync(0xFFFFFFFFu, chunk < a.n_chunks);  // lanes of this warp that hold a chunk
     if (chunk >= a.n_chunks) return;
     const uint64_t first = chunk * a.chunk_syms;
     const uint64_t cnt = (a.n_syms - first < a.chunk_syms) ? (a.n_syms - first) : a.chunk_syms;
@@ -264,14 +295,14 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
     fill.pbase = a.stream + pb;
     fill.wr = 0;
     fill.npieces = readable > (0xFFFFFFF0ull << 4) ? 0xFFFFFFF0u : (uint32_t)(readable >> 4);
-    fill.pend = 0;
     RingFetch rf;
     rf.ring = (uint32_t)__cvta_generic_to_shared(s_ring + (size_t)threadIdx.x * RING_STRIDE);
     rf.rd = rd0;
     rf.cur = 0;
     const uint32_t last_word = fill.npieces * 4 - 1;
 
-    // L2 prefetch of this lane's code bytes in 1 KiB granules, two granules ahead
+    // L2 prefetch of the first 2 KiB of this lane's code bytes; afterwards every ring piece carries a
+    // 256-byte L2 prefetch hint (no per-word prefetch branch in the loops)
     constexpr uint32_t PF_WORDS = 256;
     uint32_t pf_next = 0;  // next granule (in words from pbase) to request
     auto prefetch_to = [&](uint32_t upto_words) {
@@ -296,9 +327,10 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
     constexpr uint32_t SYM_BITS = 8 * sizeof(SYM);
     auto snapshot = [&]() -> DecLaneState {
         return DecLaneState{lo, rg, sink.dh, sink.dl, sink.wh, sink.wl, sink.cnt,
-                            reinterpret_cast<const uint32_t*>(fill.pbase), sink.f.rd, last_word, err, 0u};
+                            reinterpret_cast<const uint32_t*>(fill.pbase), sink.f.rd, last_word, err, 0u,
+                            sink.f.ring, fill.wr * 4};
     };
-    auto restore = [&](const DecLaneState& st) {  // after the exact path: adopt its state, restart the ring
+    auto restore = [&](const DecLaneState& st) {  // after the exact path: adopt its state, re-attach the ring
         lo = st.lo;
         rg = st.rg;
         sink.dh = st.dh;
@@ -308,7 +340,7 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
         sink.cnt = st.cnt;
         sink.f.rd = st.rd;
         err = st.err;
-        fill.resync(sink.f);
+        fill.after_exact(sink.f);
     };
 
     uint64_t done = 0;
@@ -321,16 +353,12 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
         uint64_t rpt = rg >> fp.s;
         float rinv16 = lut_rinv16(hi32(rg), lut_scale);
         const uint32_t lut_saddr = (uint32_t)__cvta_generic_to_shared(s_lut);
-#pragma unroll 1
-        for (uint64_t i = 0; i < nw; i++) {
-            if (sink.f.rd + PF_WORDS >= pf_next) prefetch_to(sink.f.rd + 2 * PF_WORDS);
-            fill.round(sink.f);
-            rg = rpt << fp.s;  // checkpoint in the generic form (low s bits never matter)
-            const DecLaneState chk = snapshot();
-            uint32_t acc = 0;
-            bool bad = false;
+        // Four symbols, straight-line and speculative; `bad` = some symbol needs the exact path.
+        auto decode_word = [&](uint32_t& acc, bool& bad) {
+            acc = 0;
+            bad = false;
 #pragma unroll
-            for (uint32_t b = 0; b < PER; b++) {  // speculative: straight-line, no branch
+            for (uint32_t b = 0; b < PER; b++) {
                 const uint64_t data = sink.data();
                 const uint32_t off = lut_offset16(sink.dh - hi32(lo), rinv16);
                 const LutEntry e = lds_lut(lut_saddr + off);
@@ -342,13 +370,46 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
                 acc |= r.sym << (SYM_BITS * b);
                 bad |= !r.ok;
             }
-            if (RCB_UNLIKELY(bad)) {  // restore the checkpoint and decode the word exactly
-                const DecLaneState r = dec_exact<CHECKED>(chk, tab, K, div, 1u, PER, SYM_BITS, lut_saddr, lut_scale);
-                restore(r);
-                acc = r.syms;
-                rpt = rg >> fp.s;
-                rinv16 = lut_rinv16(hi32(rg), lut_scale);
-            }
+        };
+        auto redo_word = [&](const DecLaneState& chk) -> uint32_t {  // restore the checkpoint, decode exactly
+            fill.drain();
+            const DecLaneState r = dec_exact<CHECKED>(chk, tab, K, div, 1u, PER, SYM_BITS, lut_saddr, lut_scale);
+            restore(r);
+            rpt = rg >> fp.s;
+            rinv16 = lut_rinv16(hi32(rg), lut_scale);
+            return r.syms;
+        };
+        // Main loop: the words every live lane of the warp has (all of them, except in a warp holding the
+        // ragged last chunk).  Its only branch in the common case is the back edge, and that branch is
+        // warp-uniform (vote): a taken branch costs ~35 cycles on this one-warp-per-scheduler kernel, and a
+        // per-lane exit would park the lane at the reconvergence point until its whole warp left the loop.
+        const uint32_t nw_warp = __reduce_min_sync(live, (uint32_t)(nw < 0xFFFFFFFFull ? nw : 0xFFFFFFFFull));
+        uint64_t i = 0;
+        while (i < nw_warp) {
+            DecLaneState chk;
+            uint32_t acc;
+            bool bad, leave;
+#pragma unroll 1
+            do {
+                fill.round(sink.f);
+                rg = rpt << fp.s;  // checkpoint in the generic form (low s bits never matter)
+                chk = snapshot();
+                decode_word(acc, bad);
+                dw[i] = acc;  // speculative as well: rewritten below when the word was not clean
+                ++i;
+                leave = __any_sync(live, bad) | (i >= nw_warp);
+            } while (!leave);
+            if (bad) dw[i - 1] = redo_word(chk);
+        }
+#pragma unroll 1
+        for (; i < nw; i++) {  // ragged warp only
+            fill.round(sink.f);
+            rg = rpt << fp.s;
+            const DecLaneState chk = snapshot();
+            uint32_t acc;
+            bool bad;
+            decode_word(acc, bad);
+            if (RCB_UNLIKELY(bad)) acc = redo_word(chk);
             dw[i] = acc;
         }
         done = nw * PER;
@@ -376,6 +437,7 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
                 return sym;
             }
             // table miss (rare): exact search, out of line
+            fill.drain();
             const DecLaneState r = dec_exact<CHECKED>(snapshot(), tab, K, div, pow2 ? 1u : 0u, 1u, 0u, 0u, 0.0f);
             restore(r);
             return r.syms;
@@ -386,7 +448,6 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
     if (!FUSED) {
 #pragma unroll 1
         for (uint64_t i = 0; i < nw; i++) {
-            if (sink.f.rd + PF_WORDS >= pf_next) prefetch_to(sink.f.rd + 2 * PF_WORDS);
             fill.round(sink.f);
             uint32_t acc = 0;
 #pragma unroll

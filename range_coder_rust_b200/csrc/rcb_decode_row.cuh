@@ -41,7 +41,8 @@ struct DecodeRowArgs {
 // domain over cum[1..K-1], c = cum[s+1] - cum[s], generic renormalisation.
 __device__ __noinline__ DecLaneState dec_exact_row(DecLaneState s, const uint32_t* row, uint32_t K, DivParams div,
                                                    uint32_t pow2, uint32_t n_syms, uint32_t sym_bits) {
-    GlobalFetch gf{s.base, s.rd, s.last};
+    GlobalFetch gf(s.base, s.rd, s.last, s.ring, s.ring_hi > RING_PIECES * 4 ? s.ring_hi - RING_PIECES * 4 : 0u,
+                   s.ring_hi);
     DecSink<GlobalFetch> sink(gf);
     sink.dh = s.dh;
     sink.dl = s.dl;
@@ -163,7 +164,6 @@ __global__ void __launch_bounds__(512, 1) decode_row_kernel(DecodeRowArgs a) {
     fill.pbase = a.stream + pb;
     fill.wr = 0;
     fill.npieces = readable > (0xFFFFFFF0ull << 4) ? 0xFFFFFFF0u : (uint32_t)(readable >> 4);
-    fill.pend = 0;
     RingFetch rf;
     rf.ring = (uint32_t)__cvta_generic_to_shared(s_ring + (size_t)threadIdx.x * RING_STRIDE);
     rf.rd = rd0;
@@ -240,8 +240,10 @@ __global__ void __launch_bounds__(512, 1) decode_row_kernel(DecodeRowArgs a) {
                 return sym;
             }
             rg = MODE == FUSE_GEN ? rpt * (uint64_t)div.total : rpt << fp.s;
+            fill.drain();  // everything requested has landed: the exact path reads the ring
             const DecLaneState st{lo, rg, sink.dh, sink.dl, sink.wh, sink.wl, sink.cnt,
-                                  reinterpret_cast<const uint32_t*>(fill.pbase), sink.f.rd, last_word, err, 0u};
+                                  reinterpret_cast<const uint32_t*>(fill.pbase), sink.f.rd, last_word, err, 0u,
+                                  sink.f.ring, fill.wr * 4};
             const DecLaneState x = dec_exact_row(st, row, K, div, pow2 ? 1u : 0u, 1u, 0u);
             lo = x.lo;
             rg = x.rg;
@@ -252,14 +254,13 @@ __global__ void __launch_bounds__(512, 1) decode_row_kernel(DecodeRowArgs a) {
             sink.cnt = x.cnt;
             sink.f.rd = x.rd;
             err = x.err;
-            fill.resync(sink.f);
+            fill.after_exact(sink.f);
             rpt = fused_rpt<MODE>(rg, fp);
             rinv = fast_rcp((float)hi32(rg)) * fnb;
             return x.syms;
         };
 #pragma unroll 1
         for (uint64_t i = 0; i < nw; i++) {
-            if (sink.f.rd + PF_WORDS >= pf_next) prefetch_to(sink.f.rd + 2 * PF_WORDS);
             fill.round(sink.f);
             uint32_t acc = 0;
 #pragma unroll
