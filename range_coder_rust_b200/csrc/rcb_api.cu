@@ -718,7 +718,11 @@ static DecPlan plan_decode(const rcb_ctx* c, const rcb_model* m, uint64_t n_chun
             if (fat_ok) {
                 p.kind = 0;
                 p.fmode = FM_BIG;
-                p.smem = (size_t)p.threads * RING_STRIDE + (size_t)LUT_CAP * sizeof(LutEntry) + (size_t)m->K * sizeof(uint2);
+                // FUSED kernel: 32-byte entries (candidates + reciprocals of their frequencies)
+                const size_t fixed = (size_t)LUT_CAP * 2 * sizeof(LutEntry) + (size_t)m->K * sizeof(uint2);
+                while (p.threads > 32 && (size_t)p.threads * RING_STRIDE + fixed > budget) p.threads >>= 1;
+                p.lanes = (uint32_t)p.threads;
+                p.smem = (size_t)p.threads * RING_STRIDE + fixed;
                 return p;
             }
             // thin LUT over the cum row: smallest power of two with bucket width <= min c (<= 65536 buckets)

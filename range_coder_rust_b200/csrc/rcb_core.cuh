@@ -508,9 +508,47 @@ RCB_HD float lut_rinv16(uint32_t rg_hi, float scale) {
     return fast_rcp((float)rg_hi) * (16.0f * scale);
 }
 
+// ---------------------------------------------------------------------------
+// Shift-free bucket estimate for the next symbol (decode hot loop).  After symbol n (interval
+// [nlo, nlo + rpt_n*c_n) chosen, data unshifted) the next rfreq is
+//   (data' - lower') / rpt_{n+1}  ~=  (data - nlo) * total / (rpt_n * c_n)
+// because both sides of the division are shifted by the same bytes.  So the estimate needs neither
+// the renormalisation shift nor a reciprocal of the new range: with q_n = 1/float(rpt_n >> sr)
+// (computed while the table load of symbol n is in flight) and rc = 32*lut_scale*2^-sr / c_n stored
+// next to the candidates (32-byte shared-memory entries),
+//   bf = float(data - nlo) * (q_n * rc)        = byte offset of the next entry, fractional.
+// Error: rpt_n >> sr keeps >= 16 bits (estimate <= 1/16 bucket high), floor in rpt_{n+1} (<= 1/32 low):
+// inside the 1/8-bucket margin the table is built with; the choice is verified exactly anyway.
+// ---------------------------------------------------------------------------
+RCB_HD float u64_to_float(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn((float)hi32(x), 4294967296.0f, (float)lo32(x));
+#else
+    return (float)hi32(x) * 4294967296.0f + (float)lo32(x);
+#endif
+}
+RCB_HD uint32_t fused_sr(const FusedParams& fp) { return fp.s < 32u ? 32u - fp.s : 0u; }
+RCB_HD float lut_rc32(uint32_t c, float lut_scale, uint32_t sr) {
+    return c ? (32.0f * lut_scale / (float)(1u << sr)) / (float)c : 0.0f;
+}
+RCB_HD float lut_q(uint64_t rpt, uint32_t sr) { return fast_rcp((float)(uint32_t)(rpt >> sr)); }
+// estimate from scratch (loop entry, after the exact path): d = data - lower, range = rpt << s
+RCB_HD float lut_bf32_init(uint64_t d, uint64_t rg, float lut_scale) {
+    return u64_to_float(d) * (fast_rcp(u64_to_float(rg)) * (32.0f * lut_scale));
+}
+RCB_HD uint32_t lut_offset32(float bf) {  // byte offset of a 32-byte entry, 4096 entries
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(__fadd_rz(bf, 8388608.0f)) & 0x1FFE0u;  // see lut_offset16
+#else
+    if (!(bf < 131071.0f)) return 0x1FFE0u;
+    return (uint32_t)bf & 0x1FFE0u;
+#endif
+}
+
 struct FusedDec {
     uint64_t nlo, rgp, nrpt;
     uint32_t sym, sh;
+    bool takeB;   // second candidate of the entry chosen
     bool inside;  // symbol verified: lower' <= data < upper'
     bool ok;      // ... and the fast renormalisation applies
 };
@@ -539,6 +577,7 @@ RCB_HD FusedDec fused_decode_step(uint64_t lo, uint64_t rpt, uint64_t data, cons
         r.nrpt = fused_rpt<MODE>(r.rgp << r.sh, fp);
     }
     const uint32_t need = p2 ? 1u : (p1 ? (1u << 8) : (1u << 16));  // see fused_step
+    r.takeB = takeB;
     r.inside = inside;
     r.ok = inside & (hi32(r.rgp) >= need);
     return r;

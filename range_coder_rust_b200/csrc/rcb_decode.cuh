@@ -167,6 +167,12 @@ __device__ __forceinline__ LutEntry lds_lut(uint32_t saddr) {
     return e;
 }
 
+__device__ __forceinline__ float2 lds_f2(uint32_t saddr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr));
+    return v;
+}
+
 // Lane state that travels by value through the exact (out-of-line) path.
 struct DecLaneState {
     uint64_t lo, rg;
@@ -201,7 +207,7 @@ __device__ __forceinline__ uint32_t dec_symbol_exact(uint64_t& lo, uint64_t& rg,
 }
 
 // n_syms symbols (<= 4) decoded exactly from a checkpoint; symbols packed sym_bits apart.
-// lut_saddr != 0 (FUSED callers): each symbol first tries the table; a verified symbol whose
+// lut_saddr != 0 (FUSED callers, 32-byte entries): each symbol first tries the table; a verified symbol whose
 // renormalisation needs the literal loops (loop 2, the common reason to be here) skips the search.
 template <bool CHECKED>
 __device__ __noinline__ DecLaneState dec_exact(DecLaneState s, const uint2* tab, uint32_t K, DivParams div,
@@ -224,7 +230,7 @@ __device__ __noinline__ DecLaneState dec_exact(DecLaneState s, const uint2* tab,
         if (lut_saddr) {
             const uint64_t rpt = s.rg >> fp.s;
             const uint32_t off = lut_offset16(sink.dh - hi32(s.lo), lut_rinv16(hi32(s.rg), lut_scale));
-            const FusedDec r = fused_decode_step(s.lo, rpt, sink.data(), lds_lut(lut_saddr + off), fp);
+            const FusedDec r = fused_decode_step(s.lo, rpt, sink.data(), lds_lut(lut_saddr + 2u * off), fp);
             if (r.inside) {
                 resolved = true;
                 sym = r.sym;
@@ -250,7 +256,8 @@ template <typename SYM, bool SHARED, bool POW2, bool CHECKED, bool FUSED>
 __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
     extern __shared__ __align__(16) uint8_t s_raw[];
     __shared__ ModelHdr s_hdr;
-    // shared layout: rings[blockDim.x][RING_STRIDE] | LutEntry[nb or 4096] | uint2[K]
+    constexpr uint32_t LUT_STRIDE = FUSED ? 2u : 1u;  // in 16-byte units
+    // shared layout: rings[blockDim.x][RING_STRIDE] | LutEntry[nb] (FUSED: 4096 x {LutEntry, rcA, rcB, -, -}) | uint2[K]
     uint8_t* s_ring = s_raw;
     LutEntry* s_lut = reinterpret_cast<LutEntry*>(s_raw + (size_t)blockDim.x * RING_STRIDE);
     uint2* s_tab = nullptr;
@@ -259,12 +266,19 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
         __syncthreads();
         const uint32_t nb = (s_hdr.flags & MODEL_REGULAR) ? s_hdr.nb : 0u;
         const uint32_t nb_pad = FUSED ? 4096u : nb;  // FUSED indexes any of 4096 entries
-        s_tab = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(s_lut) + (size_t)nb_pad * sizeof(LutEntry));
+        s_tab = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(s_lut) +
+                                         (size_t)nb_pad * sizeof(LutEntry) * LUT_STRIDE);
         const uint4* gl = reinterpret_cast<const uint4*>(a.lut);
         uint4* sl = reinterpret_cast<uint4*>(s_lut);
         const uint32_t total = s_hdr.div.total;
-        for (uint32_t i = threadIdx.x; i < nb_pad; i += blockDim.x)
-            sl[i] = i < nb ? gl[i] : make_uint4(total, total, total, 0u);  // empty interval: never verifies
+        const uint32_t sr = fused_sr(make_fused(s_hdr.div));
+        for (uint32_t i = threadIdx.x; i < nb_pad; i += blockDim.x) {
+            const uint4 e = i < nb ? gl[i] : make_uint4(total, total, total, 0u);  // empty interval: never verifies
+            sl[i * LUT_STRIDE] = e;
+            if (FUSED)  // reciprocals of the candidates' frequencies for the shift-free estimate (rcb_core.cuh)
+                sl[i * 2 + 1] = make_uint4(__float_as_uint(lut_rc32(e.y - e.x, s_hdr.lut_scale, sr)),
+                                           __float_as_uint(lut_rc32(e.z - e.y, s_hdr.lut_scale, sr)), 0u, 0u);
+        }
         for (uint32_t i = threadIdx.x; i < a.K; i += blockDim.x) s_tab[i] = a.tabs[i];
         __syncthreads();
     }
@@ -351,7 +365,9 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
     if constexpr (FUSED) {
         const FusedParams fp = make_fused(div);
         uint64_t rpt = rg >> fp.s;
-        float rinv16 = lut_rinv16(hi32(rg), lut_scale);
+        const uint32_t sr = fused_sr(fp);
+        float q = lut_q(rpt, sr);                                      // 1 / float(rpt >> sr)
+        float bf = lut_bf32_init(sink.data() - lo, rg, lut_scale);     // byte offset of the next entry
         const uint32_t lut_saddr = (uint32_t)__cvta_generic_to_shared(s_lut);
         // Four symbols, straight-line and speculative; `bad` = some symbol needs the exact path.
         auto decode_word = [&](uint32_t& acc, bool& bad) {
@@ -360,13 +376,16 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
 #pragma unroll
             for (uint32_t b = 0; b < PER; b++) {
                 const uint64_t data = sink.data();
-                const uint32_t off = lut_offset16(sink.dh - hi32(lo), rinv16);
+                const uint32_t off = lut_offset32(bf);
                 const LutEntry e = lds_lut(lut_saddr + off);
+                const float2 rc = lds_f2(lut_saddr + off + 16u);
                 const FusedDec r = fused_decode_step(lo, rpt, data, e, fp);
+                // next symbol's entry from the unshifted residue: no dependence on the shift (rcb_core.cuh)
+                bf = u64_to_float(data - r.nlo) * (q * (r.takeB ? rc.y : rc.x));
                 sink.put(0u, r.sh);
                 lo = r.nlo << r.sh;
                 rpt = r.nrpt;
-                rinv16 = lut_rinv16(hi32(r.rgp << r.sh), lut_scale);
+                q = lut_q(rpt, sr);
                 acc |= r.sym << (SYM_BITS * b);
                 bad |= !r.ok;
             }
@@ -376,7 +395,8 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
             const DecLaneState r = dec_exact<CHECKED>(chk, tab, K, div, 1u, PER, SYM_BITS, lut_saddr, lut_scale);
             restore(r);
             rpt = rg >> fp.s;
-            rinv16 = lut_rinv16(hi32(rg), lut_scale);
+            q = lut_q(rpt, sr);
+            bf = lut_bf32_init(sink.data() - lo, rg, lut_scale);
             return r.syms;
         };
         // Main loop: the words every live lane of the warp has (all of them, except in a warp holding the
@@ -421,7 +441,7 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
             const uint64_t rpt = pow2 ? range_par_total<true>(rg, div) : range_par_total<false>(rg, div);
             const uint64_t d = sink.data() - lo;  // examples/sample_impl.rs:29
             const uint32_t b = lut_bucket(d, rg, lut_scale, max_bucket);
-            const LutEntry e = s_lut[b];
+            const LutEntry e = s_lut[b * LUT_STRIDE];
             uint32_t sym;
             uint64_t P, rgn;
             if (RCB_LIKELY(lut_resolve(e, d, rpt, sym, P, rgn))) {
