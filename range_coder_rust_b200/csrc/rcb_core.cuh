@@ -105,6 +105,21 @@ RCB_HD uint32_t lo32(uint64_t x) {
 #endif
 }
 
+// a * b + c (low 64 bits), a 64-bit, b 32-bit: two multiply-adds (the second one carries the high
+// word), not the three instructions (wide multiply-add, multiply, add) the compiler emits on its own.
+RCB_HD uint64_t mad64x32(uint64_t a, uint32_t b, uint64_t c) {
+#if defined(__CUDA_ARCH__)
+    const uint64_t t = (uint64_t)lo32(a) * (uint64_t)b + c;  // IMAD.WIDE with the 64-bit addend
+    uint32_t h;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(h) : "r"(hi32(a)), "r"(b), "r"(hi32(t)));
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo32(t)), "r"(h));
+    return r;
+#else
+    return a * (uint64_t)b + c;
+#endif
+}
+
 RCB_HD uint32_t bswap32(uint32_t x) {
 #if defined(__CUDA_ARCH__)
     return __byte_perm(x, 0u, 0x0123);
@@ -324,9 +339,9 @@ RCB_HD uint64_t fused_rpt(uint64_t range, const FusedParams& fp) {
 template <int MODE = FUSE_BIG>
 RCB_HD bool fused_step(uint64_t lo, uint64_t rpt, uint32_t cum, uint32_t c, const FusedParams& fp,
                        uint64_t& nlo, uint64_t& rgp, uint64_t& nrpt, uint32_t& sh) {
-    nlo = lo + rpt * (uint64_t)cum;
-    const uint64_t up = lo + rpt * (uint64_t)(cum + c);
-    rgp = rpt * (uint64_t)c;
+    nlo = mad64x32(rpt, cum, lo);
+    const uint64_t up = mad64x32(rpt, cum + c, lo);
+    rgp = mad64x32(rpt, c, 0ull);
     const uint32_t xh = hi32(nlo) ^ hi32(up);
     const bool p1 = xh < (1u << 24), p2 = xh < (1u << 16), p3 = xh < (1u << 8);
     if (MODE == FUSE_BIG) {
@@ -557,14 +572,15 @@ template <int MODE = FUSE_BIG>
 RCB_HD FusedDec fused_decode_step(uint64_t lo, uint64_t rpt, uint64_t data, const LutEntry& e,
                                   const FusedParams& fp) {
     FusedDec r;
-    const uint64_t loA = lo + rpt * (uint64_t)e.cumA;
-    const uint64_t loB = lo + rpt * (uint64_t)e.cumB;
-    const uint64_t loC = lo + rpt * (uint64_t)e.cumC;
+    const uint64_t loA = mad64x32(rpt, e.cumA, lo);
+    const uint64_t loB = mad64x32(rpt, e.cumB, lo);
+    const uint64_t loC = mad64x32(rpt, e.cumC, lo);
     const bool takeB = data >= loB;
     r.nlo = takeB ? loB : loA;
     const uint64_t up = takeB ? loC : loB;
     r.sym = takeB ? (e.syms >> 16) : (e.syms & 0xFFFFu);
-    const bool inside = (data >= r.nlo) & (data < up);
+    // lower' <= data < upper'  <=>  data - lower' < range' (unsigned: data < lower' wraps to a huge value)
+    const bool inside = (data - r.nlo) < (up - r.nlo);
     r.rgp = up - r.nlo;
     const uint32_t xh = hi32(r.nlo) ^ hi32(up);
     const bool p1 = xh < (1u << 24), p2 = xh < (1u << 16), p3 = xh < (1u << 8);

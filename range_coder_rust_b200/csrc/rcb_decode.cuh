@@ -231,12 +231,18 @@ __device__ __noinline__ DecLaneState dec_exact(DecLaneState s, const uint2* tab,
             const uint64_t rpt = s.rg >> fp.s;
             const uint32_t off = lut_offset16(sink.dh - hi32(s.lo), lut_rinv16(hi32(s.rg), lut_scale));
             const FusedDec r = fused_decode_step(s.lo, rpt, sink.data(), lds_lut(lut_saddr + 2u * off), fp);
-            if (r.inside) {
+            if (r.ok) {  // the usual case for the clean symbols of the word: same step as the hot loop
+                resolved = true;
+                sym = r.sym;
+                sink.put(0u, r.sh);
+                s.lo = r.nlo << r.sh;
+                s.rg = r.nrpt << fp.s;  // generic form; the low s bits of range never matter
+            } else if (r.inside) {  // verified symbol, renormalisation needs the literal loops
                 resolved = true;
                 sym = r.sym;
                 s.lo = r.nlo;
                 s.rg = r.rgp;
-                renorm<CHECKED>(s.lo, s.rg, sink, s.err);
+                renorm_slow<CHECKED>(s.lo, s.rg, sink, s.err);
             }
         }
         if (!resolved) sym = dec_symbol_exact<CHECKED>(s.lo, s.rg, sink, s.err, tab, K, div, pow2 != 0);
