@@ -496,13 +496,14 @@ static EncPlan plan_encode(const rcb_ctx* c, const rcb_model* m, uint64_t n_chun
         const bool pow2 = (m->h_hdr0.flags & MODEL_POW2) != 0;
         p.fmode = p.checked ? FM_GENERIC : (pow2 ? (m->h_hdr0.div.shift >= 24 ? FM_BIG : FM_POW2) : FM_GEN);
         p.lanes = (uint32_t)p.threads;
-        p.smem = (size_t)m->K * sizeof(uint2);
+        p.smem = (((size_t)m->K * sizeof(uint2) + 15) & ~(size_t)15);
+        if (p.fmode != FM_GENERIC) p.smem += (size_t)p.threads * ENC_RING_STRIDE;  // per-lane input rings
         return p;
     }
-    // per-chunk models: each lane's cum[K+1] in its own shared-memory row when it fits
+    // per-chunk models: each lane's cum[K+1] in its own shared-memory row (+ its input ring) when it fits
     const size_t row = ((size_t)m->K + 1) * sizeof(uint32_t);
-    const size_t budget = 220 * 1024;
-    const uint32_t lmax = (uint32_t)(budget / row);
+    const size_t budget = 216 * 1024;
+    const uint32_t lmax = (uint32_t)(budget / (row + ENC_RING_STRIDE));
     if (!p.checked && regular && lmax >= 32) {
         p.table = TAB_LANE;
         p.fmode = FM_LANE;
@@ -513,7 +514,7 @@ static EncPlan plan_encode(const rcb_ctx* c, const rcb_model* m, uint64_t n_chun
         if (c->enc_threads && (uint32_t)c->enc_threads < L) L = (uint32_t)c->enc_threads;
         p.lanes = L;
         p.threads = (int)((L + 31) / 32 * 32);
-        p.smem = (size_t)L * row;
+        p.smem = (((size_t)L * row + 15) & ~(size_t)15) + (size_t)p.threads * ENC_RING_STRIDE;
         return p;
     }
     p.table = TAB_GLOBAL;

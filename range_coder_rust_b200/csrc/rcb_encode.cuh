@@ -78,6 +78,28 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) 
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
+// Symbol input of the fused loops: a private ring of 16-byte pieces per lane in shared memory, filled
+// by cp.async (LDGSTS) several vectors ahead.  No register is the destination of a global load, so
+// nothing on the symbol path -- and no CALL into the exact re-code path -- ever waits on the memory
+// system (the register scoreboard is per warp; a load in flight stalls the warp at every call
+// boundary).  Each piece carries a 256-byte L2 prefetch hint: no separate prefetch instruction.
+constexpr uint32_t ENC_RING_PIECES = 8;
+constexpr uint32_t ENC_RING_STRIDE = ENC_RING_PIECES * 16 + 16;  // 144: 16-byte aligned, spreads banks
+constexpr uint32_t ENC_RING_AHEAD = 6;                           // pieces requested ahead of the one in use
+
+__device__ __forceinline__ void enc_ring_issue(bool p, uint32_t saddr, const void* g) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q cp.async.cg.shared.global.L2::256B [%0], [%1], 16;\n\t}"
+        :
+        : "r"(saddr), "l"(g), "r"((uint32_t)p)
+        : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t saddr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr) : "memory");
+    return r;
+}
+
 template <int SPW>
 struct EncEntries {
     uint2 e[SPW];  // {cum, c}
@@ -98,7 +120,7 @@ template <int SPW, int MODE>
 __device__ __noinline__ EncWordState enc_word_exact(EncWordState s, EncEntries<SPW> en, FusedParams fp,
                                                     uint8_t* row, uint32_t cap) {
     RowStore rs{row};
-    EncSink<RowStore, true> sink(rs, cap);
+    EncSink<RowStore, false> sink(rs, cap);  // the caller checked room for a whole vector (see the guard)
     sink.pend = s.pend;
     sink.nb = s.nb;
     sink.pos = s.pos;
@@ -134,6 +156,10 @@ __global__ void __launch_bounds__(512, 1) encode_kernel(EncodeArgs a) {
     const uint32_t K = a.K;
     const uint32_t L = a.lanes_per_block;
     const uint64_t block_first = (uint64_t)blockIdx.x * L;
+    // shared layout: table (TAB_SHARED: uint2[K]; TAB_LANE: u32[L][K+1]) | input rings[blockDim.x] (fused loops)
+    const uint32_t ring_off = TABLE == TAB_SHARED ? ((K * 8u + 15u) & ~15u)
+                              : TABLE == TAB_LANE ? ((L * (K + 1u) * 4u + 15u) & ~15u)
+                                                  : 0u;
     if (TABLE == TAB_SHARED) {
         uint2* s_tab = reinterpret_cast<uint2*>(s_raw);
         for (uint32_t i = threadIdx.x; i < K; i += blockDim.x) s_tab[i] = a.tabs[i];
@@ -223,11 +249,19 @@ __global__ void __launch_bounds__(512, 1) encode_kernel(EncodeArgs a) {
             }
         };
         if (nvec) {
-            prefetch_l2_bulk(v, (uint32_t)(nvec < PF_VECS ? nvec * 16 : PF_VECS * 16));
-            uint4 cur = ldg_stream_v4(v);
-            Entries eA = lookup(cur.x);
             uint64_t i = 0;
             if constexpr (FMODE != FM_GENERIC) {
+                // ring prologue: pieces 0 .. AHEAD-1, one commit group each
+                const uint32_t ring =
+                    (uint32_t)__cvta_generic_to_shared(s_raw + ring_off + (size_t)threadIdx.x * ENC_RING_STRIDE);
+#pragma unroll
+                for (uint32_t q = 0; q < ENC_RING_AHEAD; q++) {
+                    enc_ring_issue(q < nvec, ring + q * 16, v + q);
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                }
+                asm volatile("cp.async.wait_group %0;" ::"n"(ENC_RING_AHEAD - 1) : "memory");
+                uint4 cur = lds_v4(ring);
+                Entries eA = lookup(cur.x);
                 // fast sink: no capacity test per store; room for a whole vector is checked once
                 // per vector (16 symbols x at most 15 bytes + the deferred emission < 320 bytes)
                 EncSink<RowStore, false> fs(rs, cap);
@@ -268,15 +302,20 @@ __global__ void __launch_bounds__(512, 1) encode_kernel(EncodeArgs a) {
 #pragma unroll 1
                     for (; i < nvec; i++) {
                         if (fs.pos + 320u > cap) break;  // finish this chunk on the capacity-checked path
-                        prefetch_block(i);
-                        const uint4 nxt = (i + 1 < nvec) ? ldg_stream_v4(v + i + 1) : make_uint4(0, 0, 0, 0);
+                        // request piece i+AHEAD (its slot held piece i-2), retire all but the newest AHEAD-1
+                        // groups: pieces <= i+1 have landed
+                        const uint64_t q = i + ENC_RING_AHEAD;
+                        enc_ring_issue(q < nvec, ring + ((uint32_t)q & (ENC_RING_PIECES - 1)) * 16, v + q);
+                        asm volatile("cp.async.commit_group;" ::: "memory");
+                        asm volatile("cp.async.wait_group %0;" ::"n"(ENC_RING_AHEAD - 1) : "memory");
+                        const uint4 nxt = lds_v4(ring + (((uint32_t)i + 1u) & (ENC_RING_PIECES - 1)) * 16);
                         Entries eB = lookup(cur.y);
                         code(eA);
                         eA = lookup(cur.z);
                         code(eB);
                         eB = lookup(cur.w);
                         code(eA);
-                        eA = lookup(nxt.x);  // word 0 of the next vector (zeros past the end: unused)
+                        eA = lookup(i + 1 < nvec ? nxt.x : 0u);  // word 0 of the next vector (unused past the end)
                         code(eB);
                         cur = nxt;
                     }
@@ -290,12 +329,16 @@ __global__ void __launch_bounds__(512, 1) encode_kernel(EncodeArgs a) {
                 } else {
                     run(std::integral_constant<int, FMODE>{});
                 }
+                asm volatile("cp.async.wait_all;" ::: "memory");
                 sink.pend = fs.pend;
                 sink.nb = fs.nb;
                 sink.pos = fs.pos;
                 sink.put(em_hi, em_sh);
                 done = i * PER;  // anything left runs through the scalar, capacity-checked loop below
             } else {
+                prefetch_l2_bulk(v, (uint32_t)(nvec < PF_VECS ? nvec * 16 : PF_VECS * 16));
+                uint4 cur = ldg_stream_v4(v);
+                Entries eA = lookup(cur.x);
                 auto code = [&](const Entries& en) {
 #pragma unroll
                     for (int b = 0; b < SPW; b++) generic_symbol(en.e[b]);
