@@ -130,12 +130,12 @@ __device__ __noinline__ EncWordState enc_word_exact(EncWordState s, EncEntries<S
         uint32_t sh;
         const bool ok = fused_step<MODE>(s.lo, s.rpt, en.e[b].x, en.e[b].y, fp, nlo, rgp, nrpt, sh);
         sink.put(s.em_hi, s.em_sh);
-        if (ok) {
-            s.em_hi = hi32(nlo);
-            s.em_sh = sh;
-            s.lo = nlo << sh;
-            s.rpt = nrpt;
-        } else {
+        // fast results unconditionally; only the symbol that needs the literal loops branches
+        s.em_hi = hi32(nlo);
+        s.em_sh = sh;
+        s.lo = nlo << sh;
+        s.rpt = nrpt;
+        if (RCB_UNLIKELY(!ok)) {
             s.em_sh = 0;
             uint64_t lo = nlo, rg = rgp;
             renorm_slow<false>(lo, rg, sink, s.err);

@@ -79,16 +79,27 @@ def main():
     p.add_argument("--reps", type=int, default=3)
     p.add_argument("--gib", type=float, default=1.0)
     p.add_argument("--big", action="store_true", help="also an 8 GiB many-lane batch (config 5's per-GPU shard)")
+    p.add_argument("--only", default="", help="comma-separated config tags to run (2,3-16,3-64,3-256,4,2b,2c)")
     a = p.parse_args()
+    only = set(x for x in a.only.split(",") if x)
+
+    def want(tag):
+        return not only or tag in only
     ctx = rcb.Context(0)
     nb = int(a.gib * (1 << 30))
-    run(ctx, "2: static global table, Zipf 1.1, K=256", nb, 256, 65536, "static", 1.1, a.reps)
+    if want("2"):
+        run(ctx, "2: static global table, Zipf 1.1, K=256", nb, 256, 65536, "static", 1.1, a.reps)
     for chunk in (16384, 65536, 262144):
-        run(ctx, f"3: adaptive per-chunk, mixed entropy, K=256, chunk {chunk // 1024} KiB", nb, 256, chunk,
-            "adaptive", None, a.reps)
-    run(ctx, "4: K=4096 (u16), Zipf 1.1, static global table", nb, 4096, 32768, "static", 1.1, a.reps)
-    run(ctx, "2b: static table with a non-power-of-two total", nb, 256, 65536, "static", 1.1, a.reps, odd_total=True)
-    run(ctx, "2c: static global table, 16 KiB chunks (65536 lanes)", nb, 256, 16384, "static", 1.1, a.reps)
+        if want(f"3-{chunk // 1024}"):
+            run(ctx, f"3: adaptive per-chunk, mixed entropy, K=256, chunk {chunk // 1024} KiB", nb, 256, chunk,
+                "adaptive", None, a.reps)
+    if want("4"):
+        run(ctx, "4: K=4096 (u16), Zipf 1.1, static global table", nb, 4096, 32768, "static", 1.1, a.reps)
+    if want("2b"):
+        run(ctx, "2b: static table with a non-power-of-two total", nb, 256, 65536, "static", 1.1, a.reps,
+            odd_total=True)
+    if want("2c"):
+        run(ctx, "2c: static global table, 16 KiB chunks (65536 lanes)", nb, 256, 16384, "static", 1.1, a.reps)
     if a.big:
         run(ctx, "5: 8 GiB per-GPU shard, static table, 64 KiB chunks (131072 lanes)", 8 << 30, 256, 65536, "static",
             1.1, max(1, a.reps - 1))
