@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <new>
 
@@ -47,6 +48,14 @@ struct rcb_ctx {
     const uint64_t* pending_offsets = nullptr;
     // host-buffer pipeline: slices of one batch on their own streams (copies overlap the coder kernels)
     cudaStream_t slice_stream[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // all host->device copies of a batch go through one stream and all device->host copies through
+    // another, in slice order: copies issued on several streams share the bus and every slice would
+    // arrive late; in order, slice k is complete after (k+1)/S of the transfer time
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    DecResume* d_resume = nullptr;  // lane states between the segment launches of rcb_decode_host
+    size_t resume_cap = 0;
+    cudaEvent_t in_ready[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t out_ready[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     unsigned long long* d_slice_summary = nullptr;  // [8][8]
     unsigned long long* h_slice_summary = nullptr;  // pinned mirror
     bool timing = false;
@@ -175,8 +184,14 @@ extern "C" int rcb_ctx_destroy(rcb_ctx* c) {
     cudaFree(c->h2d);
     for (int i = 0; i < 7; i++)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < 8; i++) {
         if (c->slice_stream[i]) cudaStreamDestroy(c->slice_stream[i]);
+        if (c->in_ready[i]) cudaEventDestroy(c->in_ready[i]);
+        if (c->out_ready[i]) cudaEventDestroy(c->out_ready[i]);
+    }
+    cudaFree(c->d_resume);
+    if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     cudaFree(c->d_slice_summary);
     cudaFreeHost(c->h_slice_summary);
     delete c;
@@ -820,10 +835,13 @@ static void launch_decode_row(rcb_ctx* c, const DecodeRowArgs& a, const DecPlan&
 // encode_issue).  d_offsets points at the run's first entry; offsets stay relative to d_stream.
 static int decode_issue(rcb_ctx* c, const uint8_t* d_stream, const uint64_t* d_offsets, uint64_t n_syms,
                         int sym_bytes, uint64_t chunk_syms, const rcb_model* m, uint64_t model_first,
-                        void* d_syms_out, uint32_t* status, unsigned long long* d_summary, bool timed) {
+                        void* d_syms_out, uint32_t* status, unsigned long long* d_summary, bool timed,
+                        const DecSegment* seg = nullptr) {
     const uint64_t n_chunks = (n_syms + chunk_syms - 1) / chunk_syms;
     const bool shared = m->n_models == 1;
     DecodeArgs a;
+    if (seg) a.seg = *seg;
+    else a.seg = DecSegment{0, 0, nullptr, 0u, 0u};
     a.stream = d_stream;
     a.offsets = d_offsets;
     a.n_syms = n_syms;
@@ -857,6 +875,7 @@ static int decode_issue(rcb_ctx* c, const uint8_t* d_stream, const uint64_t* d_o
         ra.nb = plan.nb;
         ra.out = a.out;
         ra.status = a.status;
+        ra.seg = a.seg;
         if (sym_bytes == 1) {
             if (plan.lut16) launch_decode_row<uint8_t, uint16_t>(c, ra, plan, blocks);
             else launch_decode_row<uint8_t, uint8_t>(c, ra, plan, blocks);
@@ -867,6 +886,7 @@ static int decode_issue(rcb_ctx* c, const uint8_t* d_stream, const uint64_t* d_o
     }
     CK_LAUNCH(c);
     if (timed) EV(c, 5);
+    if (seg && seg->state && seg->save) return RCB_OK;  // statuses exist after the last segment only
     status_summary_kernel<<<1, 1024, 0, c->stream>>>(status, n_chunks, d_summary);
     CK_LAUNCH(c);
     if (timed) EV(c, 6);
@@ -924,13 +944,38 @@ extern "C" int rcb_decode_chunks(rcb_ctx* c, const uint8_t* d_stream, const uint
 // slices' kernels run side by side (a slice of the lanes takes as long as all of them: the coder is
 // latency-bound per lane, so the kernels must overlap rather than queue).
 static int ensure_slices(rcb_ctx* c, int n) {
-    for (int i = 0; i < n; i++)
+    for (int i = 0; i < n; i++) {
         if (!c->slice_stream[i]) CK(c, cudaStreamCreateWithFlags(&c->slice_stream[i], cudaStreamNonBlocking));
+        if (!c->in_ready[i]) CK(c, cudaEventCreateWithFlags(&c->in_ready[i], cudaEventDisableTiming));
+        if (!c->out_ready[i]) CK(c, cudaEventCreateWithFlags(&c->out_ready[i], cudaEventDisableTiming));
+    }
+    if (!c->h2d_stream) CK(c, cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+    if (!c->d2h_stream) CK(c, cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
     if (!c->d_slice_summary) {
         CK(c, cudaMalloc(&c->d_slice_summary, 64 * sizeof(unsigned long long)));
         CK(c, cudaMallocHost(&c->h_slice_summary, 64 * sizeof(unsigned long long)));
     }
     return RCB_OK;
+}
+
+// Writes a slice's summary (4 words) and its byte count into (mapped, pinned) host memory.
+__global__ void publish_slice_kernel(unsigned long long* h_dst, const unsigned long long* d_sum,
+                                     const unsigned long long* d_bytes) {
+    for (int i = 0; i < 4; i++) h_dst[i] = d_sum[i];
+    h_dst[4] = *d_bytes;
+    __threadfence_system();
+}
+
+// RCB_TRACE=1: host timestamps of the pipeline stages on stderr (debugging aid)
+static bool trace_on() {
+    static int v = -1;
+    if (v < 0) v = getenv("RCB_TRACE") ? 1 : 0;
+    return v == 1;
+}
+static double now_ms() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
 static int pick_slices(uint64_t n_chunks, uint64_t bytes) {
@@ -989,7 +1034,9 @@ extern "C" int rcb_encode_host(rcb_ctx* c, const void* h_syms, uint64_t n_syms, 
         const uint64_t s0 = c0 * chunk_syms, s1 = c1 * chunk_syms < n_syms ? c1 * chunk_syms : n_syms;
         c->stream = c->slice_stream[k];
         cudaError_t e = cudaMemcpyAsync(d_in + s0 * sym_bytes, (const uint8_t*)h_syms + s0 * sym_bytes,
-                                        (s1 - s0) * sym_bytes, cudaMemcpyHostToDevice, c->stream);
+                                        (s1 - s0) * sym_bytes, cudaMemcpyHostToDevice, c->h2d_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(c->in_ready[k], c->h2d_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(c->slice_stream[k], c->in_ready[k], 0);
         if (e != cudaSuccess) {
             c->last_err = e;
             rc = RCB_ERR_CUDA;
@@ -1000,11 +1047,12 @@ extern "C" int rcb_encode_host(rcb_ctx* c, const void* h_syms, uint64_t n_syms, 
                           pitch, c->lens + c0, c->status + c0, d_out + c0 * pitch, nk * pitch, d_off + c0 + k,
                           c->d_slice_summary + 8 * k, false);
         if (rc) break;
-        e = cudaMemcpyAsync(c->h_slice_summary + 8 * k, c->d_slice_summary + 8 * k, 4 * sizeof(unsigned long long),
-                            cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess)
-            e = cudaMemcpyAsync(c->h_slice_summary + 8 * k + 4, d_off + c0 + k + nk, sizeof(unsigned long long),
-                                cudaMemcpyDeviceToHost, c->stream);
+        // the slice's status summary and byte count go straight into pinned host memory from a one-thread
+        // kernel: a tiny device->host copy would queue behind the bulk copies on the copy engines
+        publish_slice_kernel<<<1, 1, 0, c->stream>>>(c->h_slice_summary + 8 * k, c->d_slice_summary + 8 * k,
+                                                     (const unsigned long long*)(d_off + c0 + k + nk));
+        c->launches++;
+        e = cudaGetLastError();
         if (e != cudaSuccess) {
             c->last_err = e;
             rc = RCB_ERR_CUDA;
@@ -1013,9 +1061,12 @@ extern "C" int rcb_encode_host(rcb_ctx* c, const void* h_syms, uint64_t n_syms, 
     uint64_t base = 0;
     uint64_t bases[8];
     bool staging_overflow = false;
+    const double t_issue = now_ms();
+    if (trace_on()) fprintf(stderr, "[rcb] encode_host: %d slices issued\n", S);
     for (int k = 0; k < S && rc == RCB_OK; k++) {
         const uint64_t c0 = first[k], nk = first[k + 1] - c0;
         cudaError_t e = cudaStreamSynchronize(c->slice_stream[k]);
+        if (trace_on()) fprintf(stderr, "[rcb]   slice %d coded at +%.2f ms\n", k, now_ms() - t_issue);
         if (e != cudaSuccess) {
             c->last_err = e;
             rc = RCB_ERR_CUDA;
@@ -1030,11 +1081,12 @@ extern "C" int rcb_encode_host(rcb_ctx* c, const void* h_syms, uint64_t n_syms, 
         const uint64_t bytes = sum[4];
         bases[k] = base;
         if (base + bytes <= out_cap) {
-            e = cudaMemcpyAsync(h_out + base, d_out + c0 * pitch, bytes, cudaMemcpyDeviceToHost, c->slice_stream[k]);
+            // slice k's kernels are done (synchronised above): its bytes leave on the in-order D2H stream
+            e = cudaMemcpyAsync(h_out + base, d_out + c0 * pitch, bytes, cudaMemcpyDeviceToHost, c->d2h_stream);
             if (e == cudaSuccess)
                 // the slice's last entry is the next slice's first: only the final slice copies it
                 e = cudaMemcpyAsync(h_offsets + c0, d_off + c0 + k, (nk + (k == S - 1 ? 1 : 0)) * sizeof(uint64_t),
-                                    cudaMemcpyDeviceToHost, c->slice_stream[k]);
+                                    cudaMemcpyDeviceToHost, c->d2h_stream);
             if (e != cudaSuccess) {
                 c->last_err = e;
                 rc = RCB_ERR_CUDA;
@@ -1044,6 +1096,9 @@ extern "C" int rcb_encode_host(rcb_ctx* c, const void* h_syms, uint64_t n_syms, 
         base += bytes;
     }
     for (int k = 0; k < S; k++) cudaStreamSynchronize(c->slice_stream[k]);
+    cudaStreamSynchronize(c->h2d_stream);
+    cudaStreamSynchronize(c->d2h_stream);
+    if (trace_on()) fprintf(stderr, "[rcb]   all copies done at +%.2f ms\n", now_ms() - t_issue);
     c->stream = user_stream;
     if (staging_overflow) {
         // a staging row was too small for this data (rare): the one-shot path sizes it exactly and reruns
@@ -1109,10 +1164,33 @@ extern "C" int rcb_decode_host(rcb_ctx* c, const uint8_t* h_stream, const uint64
     if (r) return r;
     CK(c, cudaMemcpyAsync(d_off, h_offsets, (n_chunks + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
+    // segments per chunk: 4 when a chunk is big enough for the split to pay (>= 32 KiB, quarter a multiple
+    // of 16 symbols so that every segment starts on a word of output)
+    const int P = (chunk_syms * sym_bytes >= (32u << 10) && chunk_syms % 64 == 0) ? 4 : 1;
+    const uint64_t seg_syms = chunk_syms / P;
+    if (P > 1 && c->resume_cap < n_chunks) {
+        cudaFree(c->d_resume);
+        c->d_resume = nullptr;
+        c->resume_cap = 0;
+        CK(c, cudaMalloc(&c->d_resume, n_chunks * sizeof(DecResume)));
+        c->resume_cap = n_chunks;
+    }
     cudaStream_t user_stream = c->stream;
     int rc = RCB_OK;
     uint64_t first[9];
     for (int k = 0; k <= S; k++) first[k] = n_chunks * k / S;
+    cudaEvent_t tr_start = nullptr, tr_k[8][4], tr_c[8][4], tr_in[8];
+    if (trace_on()) {
+        cudaEventCreate(&tr_start);
+        for (int k = 0; k < 8; k++) {
+            cudaEventCreate(&tr_in[k]);
+            for (int q = 0; q < 4; q++) {
+                cudaEventCreate(&tr_k[k][q]);
+                cudaEventCreate(&tr_c[k][q]);
+            }
+        }
+        cudaEventRecord(tr_start, c->h2d_stream);
+    }
     for (int k = 0; k < S && rc == RCB_OK; k++) {
         const uint64_t c0 = first[k], c1 = first[k + 1];
         const uint64_t s0 = c0 * chunk_syms, s1 = c1 * chunk_syms < n_syms ? c1 * chunk_syms : n_syms;
@@ -1123,33 +1201,91 @@ extern "C" int rcb_decode_host(rcb_ctx* c, const uint8_t* h_stream, const uint64
         }
         c->stream = c->slice_stream[k];
         cudaError_t e = cudaSuccess;
-        if (b1 > b0) e = cudaMemcpyAsync(d_st + b0, h_stream + b0, b1 - b0, cudaMemcpyHostToDevice, c->stream);
+        if (b1 > b0) e = cudaMemcpyAsync(d_st + b0, h_stream + b0, b1 - b0, cudaMemcpyHostToDevice, c->h2d_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(c->in_ready[k], c->h2d_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(c->slice_stream[k], c->in_ready[k], 0);
+        if (trace_on()) cudaEventRecord(tr_in[k], c->h2d_stream);
         if (e != cudaSuccess) {
             c->last_err = e;
             rc = RCB_ERR_CUDA;
             break;
         }
-        rc = decode_issue(c, d_st, d_off + c0, s1 - s0, sym_bytes, chunk_syms, m, c0, d_out + s0 * sym_bytes,
-                          c->status + c0, c->d_slice_summary + 8 * k, false);
+        // each chunk is decoded in P launches so that the copy-out of its first symbols starts after 1/P of
+        // the (per-chunk, latency-bound) decode time instead of all of it
+        const uint64_t chunk_bytes = chunk_syms * sym_bytes;
+        const uint64_t full = (s1 - s0) / chunk_syms;            // complete chunks of this slice
+        const uint64_t tail_syms = (s1 - s0) - full * chunk_syms;  // ragged last chunk (0: none)
+        for (int ph = 0; ph < P && rc == RCB_OK; ph++) {
+            const uint64_t f0 = seg_syms * ph;
+            DecSegment seg{f0, seg_syms, P > 1 ? c->d_resume + c0 : nullptr, ph > 0 ? 1u : 0u, ph < P - 1 ? 1u : 0u};
+            rc = decode_issue(c, d_st, d_off + c0, s1 - s0, sym_bytes, chunk_syms, m, c0, d_out + s0 * sym_bytes,
+                              c->status + c0, c->d_slice_summary + 8 * k, false, &seg);
+            if (rc) break;
+            if (trace_on()) cudaEventRecord(tr_k[k][ph], c->stream);
+            e = cudaEventRecord(c->out_ready[k], c->stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(c->d2h_stream, c->out_ready[k], 0);
+            const uint64_t w_syms = ph < P - 1 ? seg_syms : chunk_syms - f0;  // this segment's width
+            uint8_t* hdst = (uint8_t*)h_syms_out + (s0 + f0) * sym_bytes;
+            const uint8_t* dsrc = d_out + (s0 + f0) * sym_bytes;
+            if (e == cudaSuccess && full) {
+                if (P == 1)
+                    e = cudaMemcpyAsync(hdst, dsrc, full * chunk_bytes, cudaMemcpyDeviceToHost, c->d2h_stream);
+                else
+                    e = cudaMemcpy2DAsync(hdst, chunk_bytes, dsrc, chunk_bytes, w_syms * sym_bytes, full,
+                                          cudaMemcpyDeviceToHost, c->d2h_stream);
+            }
+            if (e == cudaSuccess && tail_syms > f0) {  // the ragged chunk's part of this segment
+                const uint64_t n_t = (tail_syms - f0 < w_syms ? tail_syms - f0 : w_syms) * sym_bytes;
+                e = cudaMemcpyAsync(hdst + full * chunk_bytes, dsrc + full * chunk_bytes, n_t, cudaMemcpyDeviceToHost,
+                                    c->d2h_stream);
+            }
+            if (trace_on()) cudaEventRecord(tr_c[k][ph], c->d2h_stream);
+            if (e != cudaSuccess) {
+                c->last_err = e;
+                rc = RCB_ERR_CUDA;
+            }
+        }
         if (rc) break;
-        e = cudaMemcpyAsync((uint8_t*)h_syms_out + s0 * sym_bytes, d_out + s0 * sym_bytes, (s1 - s0) * sym_bytes,
-                            cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess)
-            e = cudaMemcpyAsync(c->h_slice_summary + 8 * k, c->d_slice_summary + 8 * k,
-                                4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream);
+        // status summary straight into pinned host memory (see rcb_encode_host)
+        publish_slice_kernel<<<1, 1, 0, c->stream>>>(c->h_slice_summary + 8 * k, c->d_slice_summary + 8 * k,
+                                                     c->d_slice_summary + 8 * k);
+        c->launches++;
+        e = cudaGetLastError();
         if (e != cudaSuccess) {
             c->last_err = e;
             rc = RCB_ERR_CUDA;
         }
     }
-    for (int k = 0; k < S; k++) {
-        cudaError_t e = cudaStreamSynchronize(c->slice_stream[k]);
+    for (int k = 0; k < S + 2; k++) {
+        cudaError_t e = cudaStreamSynchronize(k < S ? c->slice_stream[k] : (k == S ? c->h2d_stream : c->d2h_stream));
         if (e != cudaSuccess && rc == RCB_OK) {
             c->last_err = e;
             rc = RCB_ERR_CUDA;
         }
     }
     c->stream = user_stream;
+    if (trace_on()) {
+        for (int k = 0; k < S; k++) {
+            float t_in = 0;
+            cudaEventElapsedTime(&t_in, tr_start, tr_in[k]);
+            fprintf(stderr, "[rcb] decode_host slice %d: in %.2f |", k, t_in);
+            for (int q = 0; q < P; q++) {
+                float a = 0, b = 0;
+                cudaEventElapsedTime(&a, tr_start, tr_k[k][q]);
+                cudaEventElapsedTime(&b, tr_start, tr_c[k][q]);
+                fprintf(stderr, " seg%d kernel %.2f copied %.2f |", q, a, b);
+            }
+            fprintf(stderr, "\n");
+        }
+        cudaEventDestroy(tr_start);
+        for (int k = 0; k < 8; k++) {
+            cudaEventDestroy(tr_in[k]);
+            for (int q = 0; q < 4; q++) {
+                cudaEventDestroy(tr_k[k][q]);
+                cudaEventDestroy(tr_c[k][q]);
+            }
+        }
+    }
     if (rc) return rc;
     for (int k = 0; k < S; k++)
         if (c->h_slice_summary[8 * k]) return status_to_error((uint32_t)c->h_slice_summary[8 * k + 2]);

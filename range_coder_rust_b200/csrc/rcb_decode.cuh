@@ -27,6 +27,20 @@
 
 namespace rcb {
 
+// Lane state between two segment launches of one chunk (host-buffer pipeline: a chunk is decoded in
+// a few launches so that the device->host copy of its first symbols starts before its last ones exist).
+struct DecResume {
+    uint64_t lo, rg;
+    uint32_t dh, dl, wh, wl, cnt, rd, err, pad;
+};
+struct DecSegment {
+    uint64_t first;    // first symbol of every chunk decoded by this launch
+    uint64_t syms;     // symbols per chunk in this launch (used when save != 0; else: to the chunk's end)
+    DecResume* state;  // [n_chunks]; nullptr: the launch decodes whole chunks
+    uint32_t load;     // continue from state (not the first segment)
+    uint32_t save;     // store state at the end (not the last segment)
+};
+
 struct DecodeArgs {
     const uint8_t* stream;
     const uint64_t* offsets;  // [n_chunks+1]
@@ -40,6 +54,7 @@ struct DecodeArgs {
     uint32_t per_chunk;
     void* out;
     uint32_t* status;
+    DecSegment seg;
 };
 
 constexpr uint32_t RING_PIECES = 8;                   // 16-byte pieces per lane
@@ -292,8 +307,14 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
     const unsigned live = __ballot_sync(0xFFFFFFFFu, chunk < a.n_chunks);  // lanes of this warp that hold a chunk
     if (chunk >= a.n_chunks) return;
     const uint64_t first = chunk * a.chunk_syms;
-    const uint64_t cnt = (a.n_syms - first < a.chunk_syms) ? (a.n_syms - first) : a.chunk_syms;
-    SYM* dst = reinterpret_cast<SYM*>(a.out) + first;
+    const uint64_t chunk_cnt = (a.n_syms - first < a.chunk_syms) ? (a.n_syms - first) : a.chunk_syms;
+    // this launch's part of the chunk (the whole chunk unless the host pipeline segments it)
+    const bool seg_load = a.seg.state && a.seg.load, seg_save = a.seg.state && a.seg.save;
+    const uint64_t seg_begin = a.seg.state ? (a.seg.first < chunk_cnt ? a.seg.first : chunk_cnt) : 0;
+    const uint64_t seg_end =
+        seg_save ? (a.seg.first + a.seg.syms < chunk_cnt ? a.seg.first + a.seg.syms : chunk_cnt) : chunk_cnt;
+    const uint64_t cnt = seg_end - seg_begin;
+    SYM* dst = reinterpret_cast<SYM*>(a.out) + first + seg_begin;
 
     const uint2* tab = SHARED ? s_tab : a.tabs + chunk * a.K;
     ModelHdr hdr = SHARED ? s_hdr : a.hdrs[chunk];
@@ -317,14 +338,14 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
     fill.npieces = readable > (0xFFFFFFF0ull << 4) ? 0xFFFFFFF0u : (uint32_t)(readable >> 4);
     RingFetch rf;
     rf.ring = (uint32_t)__cvta_generic_to_shared(s_ring + (size_t)threadIdx.x * RING_STRIDE);
-    rf.rd = rd0;
+    rf.rd = seg_load ? a.seg.state[chunk].rd : rd0;
     rf.cur = 0;
     const uint32_t last_word = fill.npieces * 4 - 1;
 
-    // L2 prefetch of the first 2 KiB of this lane's code bytes; afterwards every ring piece carries a
+    // L2 prefetch of the next 2 KiB of this lane's code bytes; afterwards every ring piece carries a
     // 256-byte L2 prefetch hint (no per-word prefetch branch in the loops)
     constexpr uint32_t PF_WORDS = 256;
-    uint32_t pf_next = 0;  // next granule (in words from pbase) to request
+    uint32_t pf_next = rf.rd & ~3u;  // next granule (in words from pbase) to request
     auto prefetch_to = [&](uint32_t upto_words) {
         while (pf_next < upto_words) {
             const uint64_t o = (uint64_t)pf_next * 4;
@@ -335,13 +356,25 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
             pf_next += PF_WORDS;
         }
     };
-    prefetch_to(2 * PF_WORDS);
-    fill.resync(rf);  // initial fill: RING_PIECES pieces, wait, load word rd0
+    prefetch_to(pf_next + 2 * PF_WORDS);
+    fill.resync(rf);  // fill the ring from the read position, wait, load the current word
     DecSink<RingFetch> sink(rf);
-    sink.prime(skip);  // src/decoder.rs:14-23
 
     uint64_t lo = 0, rg = ~0ull;
     uint32_t err = 0;
+    if (seg_load) {
+        const DecResume st = a.seg.state[chunk];
+        lo = st.lo;
+        rg = st.rg;
+        sink.dh = st.dh;
+        sink.dl = st.dl;
+        sink.wh = st.wh;
+        sink.wl = st.wl;
+        sink.cnt = st.cnt;
+        err = st.err;
+    } else {
+        sink.prime(skip);  // src/decoder.rs:14-23
+    }
 
     constexpr uint32_t PER = 4 / sizeof(SYM);  // symbols per 32-bit store
     constexpr uint32_t SYM_BITS = 8 * sizeof(SYM);
@@ -489,6 +522,10 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
     }
 
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (seg_save) {  // the chunk continues in the next launch
+        a.seg.state[chunk] = DecResume{lo, rg, sink.dh, sink.dl, sink.wh, sink.wl, sink.cnt, sink.f.rd, err, 0u};
+        return;
+    }
     const uint32_t used = sink.used(sink.f.rd - rd0, skip);
     if (!err && (uint64_t)used > off1 - off0) err = ST_TRUNCATED;  // src/decoder.rs:33
     a.status[chunk] = err;

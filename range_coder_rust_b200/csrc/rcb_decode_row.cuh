@@ -35,6 +35,7 @@ struct DecodeRowArgs {
     uint32_t nb;              // LUT buckets (per lane or per block)
     void* out;
     uint32_t* status;
+    DecSegment seg;           // rcb_decode.cuh
 };
 
 // Exact path for row tables (rare, out of line): the reference's binary search in the product
@@ -144,8 +145,13 @@ __global__ void __launch_bounds__(512, 1) decode_row_kernel(DecodeRowArgs a) {
     const uint64_t chunk = block_first + threadIdx.x;
     if (chunk >= a.n_chunks) return;
     const uint64_t first = chunk * a.chunk_syms;
-    const uint64_t cnt = (a.n_syms - first < a.chunk_syms) ? (a.n_syms - first) : a.chunk_syms;
-    SYM* dst = reinterpret_cast<SYM*>(a.out) + first;
+    const uint64_t chunk_cnt = (a.n_syms - first < a.chunk_syms) ? (a.n_syms - first) : a.chunk_syms;
+    const bool seg_load = a.seg.state && a.seg.load, seg_save = a.seg.state && a.seg.save;
+    const uint64_t seg_begin = a.seg.state ? (a.seg.first < chunk_cnt ? a.seg.first : chunk_cnt) : 0;
+    const uint64_t seg_end =
+        seg_save ? (a.seg.first + a.seg.syms < chunk_cnt ? a.seg.first + a.seg.syms : chunk_cnt) : chunk_cnt;
+    const uint64_t cnt = seg_end - seg_begin;
+    SYM* dst = reinterpret_cast<SYM*>(a.out) + first + seg_begin;
 
     const uint32_t* row = s_rows + (TABLE == TAB_LANE ? (size_t)threadIdx.x * row_words : 0);
     const LUT_T* lut = s_luts + (TABLE == TAB_LANE ? (size_t)threadIdx.x * nb : 0);
@@ -166,12 +172,12 @@ __global__ void __launch_bounds__(512, 1) decode_row_kernel(DecodeRowArgs a) {
     fill.npieces = readable > (0xFFFFFFF0ull << 4) ? 0xFFFFFFF0u : (uint32_t)(readable >> 4);
     RingFetch rf;
     rf.ring = (uint32_t)__cvta_generic_to_shared(s_ring + (size_t)threadIdx.x * RING_STRIDE);
-    rf.rd = rd0;
+    rf.rd = seg_load ? a.seg.state[chunk].rd : rd0;
     rf.cur = 0;
     const uint32_t last_word = fill.npieces * 4 - 1;
 
     constexpr uint32_t PF_WORDS = 256;
-    uint32_t pf_next = 0;
+    uint32_t pf_next = rf.rd & ~3u;
     auto prefetch_to = [&](uint32_t upto_words) {
         while (pf_next < upto_words) {
             const uint64_t o = (uint64_t)pf_next * 4;
@@ -182,13 +188,25 @@ __global__ void __launch_bounds__(512, 1) decode_row_kernel(DecodeRowArgs a) {
             pf_next += PF_WORDS;
         }
     };
-    prefetch_to(2 * PF_WORDS);
+    prefetch_to(pf_next + 2 * PF_WORDS);
     fill.resync(rf);
     DecSink<RingFetch> sink(rf);
-    sink.prime(skip);  // src/decoder.rs:14-23
 
     uint64_t lo = 0, rg = ~0ull;
     uint32_t err = 0;
+    if (seg_load) {
+        const DecResume st = a.seg.state[chunk];
+        lo = st.lo;
+        rg = st.rg;
+        sink.dh = st.dh;
+        sink.dl = st.dl;
+        sink.wh = st.wh;
+        sink.wl = st.wl;
+        sink.cnt = st.cnt;
+        err = st.err;
+    } else {
+        sink.prime(skip);  // src/decoder.rs:14-23
+    }
     constexpr uint32_t PER = 4 / sizeof(SYM);
     constexpr uint32_t SYM_BITS = 8 * sizeof(SYM);
     const FusedParams fp = make_fused(div);
@@ -273,6 +291,7 @@ __global__ void __launch_bounds__(512, 1) decode_row_kernel(DecodeRowArgs a) {
             fill.round(sink.f);
             dst[i] = (SYM)step();
         }
+        rg = MODE == FUSE_GEN ? rpt * (uint64_t)div.total : rpt << fp.s;  // generic form (segment hand-over)
     };
     if constexpr (FMODE == FM_LANE) {
         if (pow2) run(std::integral_constant<int, FUSE_POW2>{});
@@ -282,6 +301,10 @@ __global__ void __launch_bounds__(512, 1) decode_row_kernel(DecodeRowArgs a) {
     }
 
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (seg_save) {  // the chunk continues in the next launch
+        a.seg.state[chunk] = DecResume{lo, rg, sink.dh, sink.dl, sink.wh, sink.wl, sink.cnt, sink.f.rd, err, 0u};
+        return;
+    }
     const uint32_t used = sink.used(sink.f.rd - rd0, skip);
     if (!err && (uint64_t)used > off1 - off0) err = ST_TRUNCATED;  // src/decoder.rs:33
     a.status[chunk] = err;

@@ -352,6 +352,41 @@ def test_host_buffer_pipeline_slices(ctx, oracle):
     assert np.array_equal(back2, syms)
 
 
+@pytest.mark.parametrize("K,chunk,kind", [(256, 65536, "static"), (256, 65536, "adaptive"), (4096, 32768, "static"),
+                                          (256, 32768, "odd_total")])
+def test_host_buffer_pipeline_segments(ctx, oracle, K, chunk, kind):
+    """decode_host decodes big chunks in several launches per chunk (lane state handed over through
+    device memory) so that copy-out overlaps decoding: every kernel family, ragged last chunk."""
+    sb = 1 if K <= 256 else 2
+    n = 600 * chunk + 12345  # 601 chunks -> slices x 4 segments per chunk, last chunk ragged
+    thr = oracle.zipf_thresholds(K, 1.1)
+    if kind == "adaptive":
+        thr = np.stack([oracle.zipf_thresholds(K, s) for s in (0.0, 0.8, 1.1, 2.0, 5.0)])
+        syms = oracle.generate(n, K, 0x5EED0002, thr, sym_bytes=sb, chunk_syms=chunk)
+    else:
+        syms = oracle.generate(n, K, 0x5EED0001, thr, sym_bytes=sb)
+    d = to_dev(ctx, syms)
+    if kind == "adaptive":
+        model = ctx.model_from_counts(ctx.histogram(d, K, chunk_syms=chunk))
+    else:
+        counts = ctx.histogram(d, K)
+        if kind == "odd_total":
+            counts[0] += 12345
+        model = ctx.model_from_counts(counts)
+    stream, offsets, nbytes = ctx.encode_chunks(d, chunk, model)
+    h_stream = np.zeros((nbytes + 15) // 16 * 16 + 16, dtype=np.uint8)
+    h_stream[:nbytes] = dev_to_np(stream, nbytes)
+    h_offsets = dev_to_np(offsets).astype(np.uint64)
+    back = ctx.decode_host(h_stream, h_offsets, syms.size, chunk, model, sym_bytes=sb)
+    assert np.array_equal(back, syms)
+    # and the oracle agrees on a few chunks of that stream (first, middle, ragged last)
+    for j in (0, 300, 600):
+        c, cum, total, _ = model.tables(j if kind == "adaptive" else 0)
+        code = h_stream[int(h_offsets[j]):int(h_offsets[j + 1])]
+        ref, _ = oracle.decode(code, min(chunk, n - j * chunk), c, cum, total, sb)
+        assert np.array_equal(ref, syms[j * chunk:(j + 1) * chunk])
+
+
 # ------------------------------------------------ full-size properties (1 GiB)
 def test_full_size_round_trip_and_sampled_parity(ctx, oracle):
     """BASELINE.json configs[1] at full size: 1 GiB Zipf(1.1), 64 KiB chunks.
