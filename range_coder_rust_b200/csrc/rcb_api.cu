@@ -339,7 +339,27 @@ static int launch_hist(rcb_ctx* c, const void* d_syms, uint64_t n, uint32_t K, u
                        void* d_counts) {
     const int threads = K <= 4096 ? 256 : 64;  // private copy of the K bins per warp
     const size_t smem = (size_t)(threads / 32) * K * sizeof(uint32_t);
-    if (chunk_syms == 0) {
+    if (chunk_syms == 0 && sizeof(SYM) == 1 && K <= 256) {
+        // byte symbols: replicated bins (rcb_kernels.cuh), 3 blocks of 8 warps per SM
+        CK(c, cudaMemsetAsync(d_counts, 0, (size_t)K * sizeof(unsigned long long), c->stream));
+        const size_t smem8 = (size_t)(threads / 32) * K * HIST_REP * sizeof(uint32_t);
+        const uint64_t nvec = n / 16;
+        const uint64_t want = (nvec + threads * 8 - 1) / (threads * 8);
+        const uint64_t maxb = (uint64_t)c->sm_count * 3;
+        const int blocks = (int)(want < 1 ? 1 : (want > maxb ? maxb : want));
+        if (K == 256) {
+            auto kern = hist_global_u8_kernel<true>;
+            CK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+            kern<<<blocks, threads, smem8, c->stream>>>((const uint8_t*)d_syms, n, K, (unsigned long long*)d_counts,
+                                                        c->d_words + 2);
+        } else {
+            auto kern = hist_global_u8_kernel<false>;
+            CK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+            kern<<<blocks, threads, smem8, c->stream>>>((const uint8_t*)d_syms, n, K, (unsigned long long*)d_counts,
+                                                        c->d_words + 2);
+        }
+        CK_LAUNCH(c);
+    } else if (chunk_syms == 0) {
         CK(c, cudaMemsetAsync(d_counts, 0, (size_t)K * sizeof(unsigned long long), c->stream));
         auto kern = hist_global_kernel<SYM>;
         CK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
