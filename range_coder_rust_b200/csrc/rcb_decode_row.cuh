@@ -230,24 +230,24 @@ __global__ void __launch_bounds__(512, 1) decode_row_kernel(DecodeRowArgs a) {
             b = b < nbm1 ? b : nbm1;
             uint32_t sym = lut[b];
             // two candidates: sym and sym + 1 (zero-width neighbours fail the test and get scanned)
-            const uint64_t loA = lo + rpt * (uint64_t)row[sym];
-            const uint64_t loB = lo + rpt * (uint64_t)row[sym + 1u];
-            const uint64_t loC = lo + rpt * (uint64_t)row[sym + 2u < K ? sym + 2u : K];
+            const uint64_t loA = mad64x32(rpt, row[sym], lo);
+            const uint64_t loB = mad64x32(rpt, row[sym + 1u], lo);
+            const uint64_t loC = mad64x32(rpt, row[sym + 2u < K ? sym + 2u : K], lo);
             const bool takeB = data >= loB;
             uint64_t nlo = takeB ? loB : loA;
             uint64_t up = takeB ? loC : loB;
             sym += takeB ? 1u : 0u;
-            if (RCB_UNLIKELY(!((data >= nlo) & (data < up)))) {
+            if (RCB_UNLIKELY(!((data - nlo) < (up - nlo)))) {  // not lower' <= data < upper' 
                 // several symbols in this bucket (or the estimate was off): short exact scan in the
                 // product domain -- the reference's search result is the largest s with
                 // lower + rpt * cum[s] <= data, clamped to K-1 (examples/sample_impl.rs:33-44)
                 sym = sym < K - 1u ? sym : K - 1u;
 #pragma unroll 1
-                while (sym > 0u && lo + rpt * (uint64_t)row[sym] > data) sym--;
+                while (sym > 0u && mad64x32(rpt, row[sym], lo) > data) sym--;
 #pragma unroll 1
-                while (sym < K - 1u && lo + rpt * (uint64_t)row[sym + 1u] <= data) sym++;
-                nlo = lo + rpt * (uint64_t)row[sym];
-                up = lo + rpt * (uint64_t)row[sym + 1u];
+                while (sym < K - 1u && mad64x32(rpt, row[sym + 1u], lo) <= data) sym++;
+                nlo = mad64x32(rpt, row[sym], lo);
+                up = mad64x32(rpt, row[sym + 1u], lo);
             }
             const FusedRenorm r = fused_renorm<MODE>(nlo, up, fp);
             if (RCB_LIKELY(r.ok)) {
