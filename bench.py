@@ -46,6 +46,7 @@ def parse_args():
     p.add_argument("--e2e-steps", type=int, default=2)
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--trace-steps", action="store_true", help="per-step phase times of this rank on stderr")
     p.add_argument("--enc-threads", type=int, default=0)
     p.add_argument("--dec-threads", type=int, default=0)
     return p.parse_args()
@@ -81,13 +82,20 @@ class ClockSampler:
         self.samples = []
         self.reasons = set()
         self.stop_flag = threading.Event()
+        self.recording = False  # NVML is initialised (start) before warm-up; samples count from arm() on
         self.thread = None
         self.max_mhz = None
         self.error = None
 
+    def arm(self):
+        self.recording = True
+
     def _sample(self, pynvml, h):
-        self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+        mhz = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
         r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+        if not self.recording:
+            return
+        self.samples.append(mhz)
         for bit, name in ((pynvml.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"),
                           (pynvml.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
                           (pynvml.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"),
@@ -295,11 +303,12 @@ def run_ours(a):
                 kern[k].append(t[k])
 
     ctx.enable_timing(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()  # NVML start-up happens here, outside the timed region (it can stall other ranks' launches)
     for _ in range(a.warmup):
         step(False)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.arm()
     launches0 = ctx.launch_count
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
@@ -317,6 +326,13 @@ def run_ours(a):
 
     def phase(a_, b_):
         return sum(x.elapsed_time(y) for x, y in zip(ev[a_], ev[b_])) / len(ev[a_])
+
+    if a.trace_steps:
+        for i in range(len(ev["start"])):
+            print(f"[rank {rank}] step {i}: " + " ".join(
+                f"{nm}={ev[p0][i].elapsed_time(ev[p1][i]):.3f}" for nm, p0, p1 in
+                (("hist", "start", "hist"), ("model", "hist", "model"), ("enc", "model", "enc"), ("dec", "enc", "dec"))),
+                file=sys.stderr, flush=True)
 
     ms = {"histogram": phase("start", "hist"), "model": phase("hist", "model"), "encode": phase("model", "enc"),
           "decode": phase("enc", "dec")}
