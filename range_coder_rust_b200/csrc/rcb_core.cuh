@@ -504,25 +504,8 @@ RCB_HD bool lut_resolve(const LutEntry& e, uint64_t d, uint64_t rpt, uint32_t& s
 // the candidates' new lower bounds lower + rpt * cum{A,B,C} come straight out of
 // multiply-adds, `data >= lower + rpt*cumB` picks the candidate, and
 // lower' <= data < upper' is the exact verification (d - P < rpt*c in disguise).
-// rinv16 = 16 * lut_scale / float(range >> 32) turns the high word of
-// data - lower into a byte offset into the 16-byte LUT entries.
+// The byte offset of the entry comes from the shift-free estimate below.
 // ---------------------------------------------------------------------------
-RCB_HD uint32_t lut_offset16(uint32_t d_hi, float rinv16) {
-    float bf = (float)d_hi * rinv16;  // >= 0, in sixteenths of a bucket
-#if defined(__CUDA_ARCH__)
-    // round-toward-zero add of 2^23 leaves floor(bf) in the mantissa; no clamp: a huge estimate
-    // (garbage stream) lands on some in-bounds entry that fails verification (exact fallback)
-    return __float_as_uint(__fadd_rz(bf, 8388608.0f)) & 0xFFF0u;
-#else
-    if (!(bf < 65535.0f)) return 0xFFF0u;
-    return (uint32_t)bf & 0xFFF0u;
-#endif
-}
-
-RCB_HD float lut_rinv16(uint32_t rg_hi, float scale) {
-    return fast_rcp((float)rg_hi) * (16.0f * scale);
-}
-
 // ---------------------------------------------------------------------------
 // Shift-free bucket estimate for the next symbol (decode hot loop).  After symbol n (interval
 // [nlo, nlo + rpt_n*c_n) chosen, data unshifted) the next rfreq is
@@ -553,7 +536,9 @@ RCB_HD float lut_bf32_init(uint64_t d, uint64_t rg, float lut_scale) {
 }
 RCB_HD uint32_t lut_offset32(float bf) {  // byte offset of a 32-byte entry, 4096 entries
 #if defined(__CUDA_ARCH__)
-    return __float_as_uint(__fadd_rz(bf, 8388608.0f)) & 0x1FFE0u;  // see lut_offset16
+    // round-toward-zero add of 2^23 leaves floor(bf) in the mantissa; no clamp: a huge estimate
+    // (garbage stream) lands on some in-bounds entry that fails verification (exact fallback)
+    return __float_as_uint(__fadd_rz(bf, 8388608.0f)) & 0x1FFE0u;
 #else
     if (!(bf < 131071.0f)) return 0x1FFE0u;
     return (uint32_t)bf & 0x1FFE0u;

@@ -221,13 +221,11 @@ __device__ __forceinline__ uint32_t dec_symbol_exact(uint64_t& lo, uint64_t& rg,
     return sym;
 }
 
-// n_syms symbols (<= 4) decoded exactly from a checkpoint; symbols packed sym_bits apart.
-// lut_saddr != 0 (FUSED callers, 32-byte entries): each symbol first tries the table; a verified symbol whose
-// renormalisation needs the literal loops (loop 2, the common reason to be here) skips the search.
+// n_syms symbols (<= 4) decoded exactly from a checkpoint (the reference's search + the generic
+// renormalisation), symbols packed sym_bits apart.  Out of line: the generic kernels' table-miss path.
 template <bool CHECKED>
 __device__ __noinline__ DecLaneState dec_exact(DecLaneState s, const uint2* tab, uint32_t K, DivParams div,
-                                               uint32_t pow2, uint32_t n_syms, uint32_t sym_bits,
-                                               uint32_t lut_saddr, float lut_scale) {
+                                               uint32_t pow2, uint32_t n_syms, uint32_t sym_bits) {
     GlobalFetch gf(s.base, s.rd, s.last, s.ring, s.ring_hi > RING_PIECES * 4 ? s.ring_hi - RING_PIECES * 4 : 0u,
                    s.ring_hi);
     DecSink<GlobalFetch> sink(gf);
@@ -236,31 +234,10 @@ __device__ __noinline__ DecLaneState dec_exact(DecLaneState s, const uint2* tab,
     sink.wh = s.wh;
     sink.wl = s.wl;
     sink.cnt = s.cnt;
-    const FusedParams fp = make_fused(div);
     uint32_t acc = 0;
 #pragma unroll 1
     for (uint32_t b = 0; b < n_syms; b++) {
-        uint32_t sym;
-        bool resolved = false;
-        if (lut_saddr) {
-            const uint64_t rpt = s.rg >> fp.s;
-            const uint32_t off = lut_offset16(sink.dh - hi32(s.lo), lut_rinv16(hi32(s.rg), lut_scale));
-            const FusedDec r = fused_decode_step(s.lo, rpt, sink.data(), lds_lut(lut_saddr + 2u * off), fp);
-            if (r.ok) {  // the usual case for the clean symbols of the word: same step as the hot loop
-                resolved = true;
-                sym = r.sym;
-                sink.put(0u, r.sh);
-                s.lo = r.nlo << r.sh;
-                s.rg = r.nrpt << fp.s;  // generic form; the low s bits of range never matter
-            } else if (r.inside) {  // verified symbol, renormalisation needs the literal loops
-                resolved = true;
-                sym = r.sym;
-                s.lo = r.nlo;
-                s.rg = r.rgp;
-                renorm_slow<CHECKED>(s.lo, s.rg, sink, s.err);
-            }
-        }
-        if (!resolved) sym = dec_symbol_exact<CHECKED>(s.lo, s.rg, sink, s.err, tab, K, div, pow2 != 0);
+        const uint32_t sym = dec_symbol_exact<CHECKED>(s.lo, s.rg, sink, s.err, tab, K, div, pow2 != 0);
         acc |= sym << (sym_bits * b);
     }
     s.syms = acc;
@@ -429,14 +406,50 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
                 bad |= !r.ok;
             }
         };
-        auto redo_word = [&](const DecLaneState& chk) -> uint32_t {  // restore the checkpoint, decode exactly
+        // The word was not clean for this lane: back to the checkpoint (register moves) and through the
+        // word one symbol at a time, inline and on the same ring -- the table step where it verifies, the
+        // reference's literal loops / search where it does not.  A word consumes at most ~52 bytes and
+        // the ring holds >= 90 completed bytes at a checkpoint once drained.
+        auto redo_word = [&](const DecLaneState& chk) -> uint32_t {
             fill.drain();
-            const DecLaneState r = dec_exact<CHECKED>(chk, tab, K, div, 1u, PER, SYM_BITS, lut_saddr, lut_scale);
-            restore(r);
-            rpt = rg >> fp.s;
+            lo = chk.lo;
+            rpt = chk.rg >> fp.s;
+            sink.dh = chk.dh;
+            sink.dl = chk.dl;
+            sink.wh = chk.wh;
+            sink.wl = chk.wl;
+            sink.cnt = chk.cnt;
+            sink.f.rd = chk.rd;
+            sink.f.reload();
+            uint32_t acc = 0;
+#pragma unroll 1
+            for (uint32_t b = 0; b < PER; b++) {
+                const uint64_t data = sink.data();
+                const uint32_t off = lut_offset32(lut_bf32_init(data - lo, rpt << fp.s, lut_scale));
+                const FusedDec r = fused_decode_step(lo, rpt, data, lds_lut(lut_saddr + off), fp);
+                uint32_t sym = r.sym;
+                if (RCB_LIKELY(r.ok)) {
+                    sink.put(0u, r.sh);
+                    lo = r.nlo << r.sh;
+                    rpt = r.nrpt;
+                } else {
+                    uint64_t l2 = r.nlo, g2 = r.rgp;
+                    if (!r.inside) {  // table miss: the reference's search (examples/sample_impl.rs:27-45)
+                        sym = find_index_exact(data - lo, rpt, K, [&](uint32_t j) { return tab[j].x; });
+                        const uint2 t = tab[sym];
+                        l2 = lo + rpt * (uint64_t)t.x;  // src/decoder.rs:42-50
+                        g2 = rpt * (uint64_t)t.y;
+                    }
+                    renorm_slow<CHECKED>(l2, g2, sink, err);  // src/range_coder.rs:83-89, bytes from the ring
+                    lo = l2;
+                    rpt = g2 >> fp.s;
+                }
+                acc |= sym << (SYM_BITS * b);
+            }
+            rg = rpt << fp.s;
             q = lut_q(rpt, sr);
             bf = lut_bf32_init(sink.data() - lo, rg, lut_scale);
-            return r.syms;
+            return acc;
         };
         // Main loop: the words every live lane of the warp has (all of them, except in a warp holding the
         // ragged last chunk).  Its only branch in the common case is the back edge, and that branch is
@@ -497,7 +510,7 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
             }
             // table miss (rare): exact search, out of line
             fill.drain();
-            const DecLaneState r = dec_exact<CHECKED>(snapshot(), tab, K, div, pow2 ? 1u : 0u, 1u, 0u, 0u, 0.0f);
+            const DecLaneState r = dec_exact<CHECKED>(snapshot(), tab, K, div, pow2 ? 1u : 0u, 1u, 0u);
             restore(r);
             return r.syms;
         }

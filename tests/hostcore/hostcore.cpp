@@ -203,18 +203,25 @@ extern "C" int64_t hc_decode(const uint8_t* stream, uint64_t off0, uint64_t off1
             else pad[b] = LutEntry{total, total, total, 0};
         }
         uint64_t rpt = rg >> fp.s;
-        float rinv16 = lut_rinv16(hi32(rg), h.lut_scale);
+        // shift-free estimate, as in decode_kernel: q = 1/float(rpt >> sr), rc = const / c of the candidate
+        const uint32_t sr = fused_sr(fp);
+        float q = lut_q(rpt, sr);
+        float bf = lut_bf32_init(sink.data() - lo, rg, h.lut_scale);
         for (uint64_t i = 0; i < n_syms; i++) {
             const uint64_t data = sink.data();
-            const uint32_t off = lut_offset16(hi32(data) - hi32(lo), rinv16);
-            FusedDec r = fused_decode_step(lo, rpt, data, pad[off >> 4], fp);
+            const uint32_t off = lut_offset32(bf);
+            const LutEntry e = pad[off >> 5];
+            const float rcA = lut_rc32(e.cumB - e.cumA, h.lut_scale, sr);
+            const float rcB = lut_rc32(e.cumC - e.cumB, h.lut_scale, sr);
+            FusedDec r = fused_decode_step(lo, rpt, data, e, fp);
             uint32_t sym;
             if (r.ok) {
                 sym = r.sym;
+                bf = u64_to_float(data - r.nlo) * (q * (r.takeB ? rcB : rcA));
                 sink.put(0, r.sh);
                 lo = r.nlo << r.sh;
                 rpt = r.nrpt;
-                rinv16 = lut_rinv16(hi32(r.rgp << r.sh), h.lut_scale);
+                q = lut_q(rpt, sr);
             } else {
                 fallbacks++;
                 sym = find_index_exact(data - lo, rpt, K, [&](uint32_t j) { return cum[j]; });
@@ -222,7 +229,8 @@ extern "C" int64_t hc_decode(const uint8_t* stream, uint64_t off0, uint64_t off1
                 rg = rpt * (uint64_t)c[sym];
                 renorm<false>(lo, rg, sink, err);
                 rpt = rg >> fp.s;
-                rinv16 = lut_rinv16(hi32(rg), h.lut_scale);
+                q = lut_q(rpt, sr);
+                bf = lut_bf32_init(sink.data() - lo, rg, h.lut_scale);
             }
             store_sym(out, i, sym_bytes, sym);
         }
