@@ -740,7 +740,7 @@ static DecPlan plan_decode(const rcb_ctx* c, const rcb_model* m, uint64_t n_chun
     p.threads = pick_threads(c, c->dec_threads, n_chunks);
     p.lanes = (uint32_t)p.threads;
     const size_t budget = 216 * 1024;
-    const size_t row = ((size_t)m->K + 1) * sizeof(uint32_t);
+    const size_t row = ((size_t)m->K + ROW_PAD) * sizeof(uint32_t);  // rcb_decode_row.cuh
     p.lut16 = m->K > 256;
     const size_t lut_elem = p.lut16 ? 2 : 1;
     if (shared) {

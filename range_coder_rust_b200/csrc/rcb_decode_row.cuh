@@ -22,6 +22,8 @@
 
 namespace rcb {
 
+constexpr uint32_t ROW_PAD = 4;  // row entries K .. K+3 hold total
+
 struct DecodeRowArgs {
     const uint8_t* stream;
     const uint64_t* offsets;  // [n_chunks+1]
@@ -38,10 +40,9 @@ struct DecodeRowArgs {
     DecSegment seg;           // rcb_decode.cuh
 };
 
-// Exact path for row tables (rare, out of line): the reference's binary search in the product
-// domain over cum[1..K-1], c = cum[s+1] - cum[s], generic renormalisation.
-__device__ __noinline__ DecLaneState dec_exact_row(DecLaneState s, const uint32_t* row, uint32_t K, DivParams div,
-                                                   uint32_t pow2, uint32_t n_syms, uint32_t sym_bits) {
+// Literal renormalisation loops for a symbol that is already chosen (s.lo / s.rg hold lower' and
+// range'): src/range_coder.rs:83-89 through the exact-path byte source.  Rare, out of line.
+__device__ __noinline__ DecLaneState dec_renorm_exact(DecLaneState s) {
     GlobalFetch gf(s.base, s.rd, s.last, s.ring, s.ring_hi > RING_PIECES * 4 ? s.ring_hi - RING_PIECES * 4 : 0u,
                    s.ring_hi);
     DecSink<GlobalFetch> sink(gf);
@@ -50,19 +51,7 @@ __device__ __noinline__ DecLaneState dec_exact_row(DecLaneState s, const uint32_
     sink.wh = s.wh;
     sink.wl = s.wl;
     sink.cnt = s.cnt;
-    uint32_t acc = 0;
-#pragma unroll 1
-    for (uint32_t b = 0; b < n_syms; b++) {
-        const uint64_t rpt = pow2 ? range_par_total<true>(s.rg, div) : range_par_total<false>(s.rg, div);
-        const uint64_t d = sink.data() - s.lo;  // examples/sample_impl.rs:29
-        const uint32_t sym = find_index_exact(d, rpt, K, [&](uint32_t i) { return row[i]; });
-        const uint32_t cum = row[sym], c = row[sym + 1] - cum;
-        s.lo = s.lo + rpt * (uint64_t)cum;  // src/decoder.rs:42-50
-        s.rg = rpt * (uint64_t)c;
-        renorm<false>(s.lo, s.rg, sink, s.err);
-        acc |= sym << (sym_bits * b);
-    }
-    s.syms = acc;
+    renorm_slow<false>(s.lo, s.rg, sink, s.err);
     s.dh = sink.dh;
     s.dl = sink.dl;
     s.wh = sink.wh;
@@ -72,23 +61,13 @@ __device__ __noinline__ DecLaneState dec_exact_row(DecLaneState s, const uint32_
     return s;
 }
 
-// symbol whose interval contains v (the reference's search on plain cum values)
-__device__ __forceinline__ uint32_t row_symbol_at(const uint32_t* row, uint32_t K, uint64_t v) {
-    uint32_t left = 0, right = K - 1;
-    while (left < right) {
-        const uint32_t mid = (left + right) >> 1;
-        if ((uint64_t)row[mid + 1] <= v) left = mid + 1; else right = mid;
-    }
-    return left;
-}
-
 template <typename SYM, int TABLE, int FMODE, typename LUT_T>
 __global__ void __launch_bounds__(512, 1) decode_row_kernel(DecodeRowArgs a) {
     extern __shared__ __align__(16) uint8_t s_raw[];
     __shared__ ModelHdr s_hdr;
     const uint32_t K = a.K, L = a.lanes_per_block, nb = a.nb;
     const uint64_t block_first = (uint64_t)blockIdx.x * L;
-    const uint32_t row_words = K + 1;
+    const uint32_t row_words = K + ROW_PAD;  // cum[0..K-1], then total ROW_PAD times: candidates past K never verify
     const uint32_t n_rows = TABLE == TAB_LANE ? L : 1u;
     // shared layout: rings[blockDim.x][RING_STRIDE] | rows[n_rows][K+1] u32 | luts[n_rows][nb] LUT_T
     uint8_t* s_ring = s_raw;
@@ -103,7 +82,7 @@ __global__ void __launch_bounds__(512, 1) decode_row_kernel(DecodeRowArgs a) {
             const uint64_t model = TABLE == TAB_LANE ? block_first + l : 0;
             const uint2* t = a.tabs + model * K;
             for (uint32_t i = threadIdx.x; i < K; i += blockDim.x) s_rows[l * row_words + i] = t[i].x;
-            if (threadIdx.x == 0) s_rows[l * row_words + K] = a.hdrs[model].div.total;
+            if (threadIdx.x < ROW_PAD) s_rows[l * row_words + K + threadIdx.x] = a.hdrs[model].div.total;
         }
         if (TABLE == TAB_SHARED && threadIdx.x == 0) s_hdr = a.hdrs[0];
         __syncthreads();
@@ -116,10 +95,17 @@ __global__ void __launch_bounds__(512, 1) decode_row_kernel(DecodeRowArgs a) {
             for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) {
                 uint64_t v0 = nb_pow2 ? ((uint64_t)b * total) >> nb_shift : (uint64_t)b * total / nb;
                 v0 = v0 > margin ? v0 - margin : 0;
-                s_luts[b] = (LUT_T)row_symbol_at(s_rows, K, v0);
+                uint32_t lft = 0, rgt = K - 1;  // symbol whose interval contains v0
+                while (lft < rgt) {
+                    const uint32_t mid = (lft + rgt) >> 1;
+                    if ((uint64_t)s_rows[mid + 1] <= v0) lft = mid + 1; else rgt = mid;
+                }
+                s_luts[b] = (LUT_T)lft;
             }
         } else if (threadIdx.x < lanes) {
-            // each lane walks its own row and its buckets together (both monotone)
+            // each lane walks its own row and its buckets together (both monotone).  (Dropping the
+            // zero-frequency symbols from the row was measured: the position -> symbol map costs more
+            // LUT buckets than the compaction saves in scans.)
             const uint32_t* row = s_rows + threadIdx.x * row_words;
             LUT_T* lut = s_luts + (size_t)threadIdx.x * nb;
             const uint64_t total = row[K];
@@ -228,27 +214,45 @@ __global__ void __launch_bounds__(512, 1) decode_row_kernel(DecodeRowArgs a) {
             const float bf = (float)(sink.dh - hi32(lo)) * rinv;
             uint32_t b = __float_as_uint(__fadd_rz(bf, 8388608.0f)) & 0x7FFFFFu;
             b = b < nbm1 ? b : nbm1;
-            uint32_t sym = lut[b];
-            // two candidates: sym and sym + 1 (zero-width neighbours fail the test and get scanned)
-            const uint64_t loA = mad64x32(rpt, row[sym], lo);
-            const uint64_t loB = mad64x32(rpt, row[sym + 1u], lo);
-            const uint64_t loC = mad64x32(rpt, row[sym + 2u < K ? sym + 2u : K], lo);
-            const bool takeB = data >= loB;
-            uint64_t nlo = takeB ? loB : loA;
-            uint64_t up = takeB ? loC : loB;
-            sym += takeB ? 1u : 0u;
-            if (RCB_UNLIKELY(!((data - nlo) < (up - nlo)))) {  // not lower' <= data < upper' 
-                // several symbols in this bucket (or the estimate was off): short exact scan in the
+            uint32_t j = lut[b];  // first candidate symbol
+            uint64_t nlo, up;
+            if constexpr (TABLE == TAB_LANE) {
+                // per-lane tables have coarse LUTs (a few hundred buckets): four candidates j .. j+3 with
+                // bounds row[j .. j+4] (monotone: three compares pick one; more than four symbols in a
+                // bucket get scanned below)
+                const uint32_t* r4 = row + j;
+                const uint32_t c0 = r4[0], c1 = r4[1], c2 = r4[2], c3 = r4[3], c4 = r4[4];
+                const bool g1 = data >= mad64x32(rpt, c1, lo);
+                const bool g2 = data >= mad64x32(rpt, c2, lo);
+                const bool g3 = data >= mad64x32(rpt, c3, lo);
+                const uint32_t cl = g2 ? (g3 ? c3 : c2) : (g1 ? c1 : c0);
+                const uint32_t cu = g2 ? (g3 ? c4 : c3) : (g1 ? c2 : c1);
+                j += (g1 ? 1u : 0u) + (g2 ? 1u : 0u) + (g3 ? 1u : 0u);
+                nlo = mad64x32(rpt, cl, lo);
+                up = mad64x32(rpt, cu, lo);
+            } else {
+                // block-wide tables afford a fine LUT (bucket <= smallest frequency): two candidates
+                const uint64_t loA = mad64x32(rpt, row[j], lo);
+                const uint64_t loB = mad64x32(rpt, row[j + 1u], lo);
+                const uint64_t loC = mad64x32(rpt, row[j + 2u], lo);
+                const bool takeB = data >= loB;
+                nlo = takeB ? loB : loA;
+                up = takeB ? loC : loB;
+                j += takeB ? 1u : 0u;
+            }
+            if (RCB_UNLIKELY(!((data - nlo) < (up - nlo)))) {  // not lower' <= data < upper'
+                // more symbols in this bucket than candidates (or the estimate was off): short scan in the
                 // product domain -- the reference's search result is the largest s with
                 // lower + rpt * cum[s] <= data, clamped to K-1 (examples/sample_impl.rs:33-44)
-                sym = sym < K - 1u ? sym : K - 1u;
+                j = j < K - 1u ? j : K - 1u;
 #pragma unroll 1
-                while (sym > 0u && mad64x32(rpt, row[sym], lo) > data) sym--;
+                while (j > 0u && mad64x32(rpt, row[j], lo) > data) j--;
 #pragma unroll 1
-                while (sym < K - 1u && mad64x32(rpt, row[sym + 1u], lo) <= data) sym++;
-                nlo = mad64x32(rpt, row[sym], lo);
-                up = mad64x32(rpt, row[sym + 1u], lo);
+                while (j < K - 1u && mad64x32(rpt, row[j + 1u], lo) <= data) j++;
+                nlo = mad64x32(rpt, row[j], lo);
+                up = mad64x32(rpt, row[j + 1u], lo);
             }
+            const uint32_t sym = j;
             const FusedRenorm r = fused_renorm<MODE>(nlo, up, fp);
             if (RCB_LIKELY(r.ok)) {
                 sink.put(0u, r.sh);
@@ -257,12 +261,12 @@ __global__ void __launch_bounds__(512, 1) decode_row_kernel(DecodeRowArgs a) {
                 rinv = fast_rcp((float)hi32(r.rgp << r.sh)) * fnb;
                 return sym;
             }
-            rg = MODE == FUSE_GEN ? rpt * (uint64_t)div.total : rpt << fp.s;
+            // the symbol is known, its renormalisation needs the literal loops (out of line)
             fill.drain();  // everything requested has landed: the exact path reads the ring
-            const DecLaneState st{lo, rg, sink.dh, sink.dl, sink.wh, sink.wl, sink.cnt,
+            const DecLaneState st{nlo, r.rgp, sink.dh, sink.dl, sink.wh, sink.wl, sink.cnt,
                                   reinterpret_cast<const uint32_t*>(fill.pbase), sink.f.rd, last_word, err, 0u,
                                   sink.f.ring, fill.wr * 4};
-            const DecLaneState x = dec_exact_row(st, row, K, div, pow2 ? 1u : 0u, 1u, 0u);
+            const DecLaneState x = dec_renorm_exact(st);
             lo = x.lo;
             rg = x.rg;
             sink.dh = x.dh;
@@ -275,7 +279,7 @@ __global__ void __launch_bounds__(512, 1) decode_row_kernel(DecodeRowArgs a) {
             fill.after_exact(sink.f);
             rpt = fused_rpt<MODE>(rg, fp);
             rinv = fast_rcp((float)hi32(rg)) * fnb;
-            return x.syms;
+            return sym;
         };
 #pragma unroll 1
         for (uint64_t i = 0; i < nw; i++) {
