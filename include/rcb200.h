@@ -167,7 +167,14 @@ int rcb_decode_chunks_async(rcb_ctx *ctx, const uint8_t *d_stream, const uint64_
 int rcb_decode_result(rcb_ctx *ctx);
 
 /* ---- host-buffer convenience (H2D, encode/decode, D2H inside the call) -----
- * What a Rust `gpu::encode_chunks(&pmodel, K, &symbols, chunk_syms)` binds. */
+ * What a Rust `gpu::encode_chunks(&pmodel, K, &symbols, chunk_syms)` binds.
+ * Large batches run as a pipeline of up to 8 slices of whole chunks (copies in
+ * and out overlap the kernels; rcb_decode_host additionally decodes chunks of
+ * >= 32 KiB in four resumable launches) -- results do not depend on that.
+ * Pinned (page-locked) host buffers let the copies run asynchronously; pageable
+ * ones work and are slower.  Exactly h_offsets[n_chunks] bytes of h_stream are
+ * read (the padding the device reader wants is added on the device side).
+ * RCB_TRACE=1 in the environment prints the pipeline's timeline on stderr. */
 int rcb_encode_host(rcb_ctx *ctx, const void *h_syms, uint64_t n_syms, int sym_bytes,
                     uint64_t chunk_syms, const rcb_model *m, uint8_t *h_out, uint64_t out_cap,
                     uint64_t *h_offsets, uint64_t *h_out_bytes);
