@@ -252,12 +252,18 @@ extern "C" int rcb_ctx_get_timings(rcb_ctx* c, float* ms, int n) {
 // Threads per block of the coder kernels.  One lane per chunk: with few lanes (<= 128 per SM) small
 // blocks spread the warps over all SMs (latency-bound regime, one warp per scheduler); with many
 // lanes bigger blocks share one copy of the shared-memory tables (throughput regime).
+// Lanes per block: the coder kernels keep one block per SM busy (the decoder's tables fill shared memory),
+// so the lanes are spread evenly over as few full waves of SM-count blocks as 512-thread blocks allow --
+// 16384 lanes: 128 threads, one wave; 65536 lanes: 448 threads, one wave (not 256 blocks of 256 = 1.7 waves).
 static int pick_threads(const rcb_ctx* c, int user, uint64_t n_chunks) {
     if (user) return user;
     const uint64_t sms = (uint64_t)(c->sm_count > 0 ? c->sm_count : 148);
-    if (n_chunks > sms * 512) return 512;
-    if (n_chunks > sms * 128) return 256;
-    return 128;
+    const uint64_t waves = (n_chunks + sms * 512 - 1) / (sms * 512);
+    const uint64_t per_block = (n_chunks + waves * sms - 1) / (waves ? waves * sms : 1);
+    uint64_t t = (per_block + 31) / 32 * 32;
+    if (t < 128) t = 128;
+    if (t > 512) t = 512;
+    return (int)t;
 }
 
 static int ensure_chunks(rcb_ctx* c, uint64_t n_chunks) {
@@ -754,8 +760,8 @@ static DecPlan plan_decode(const rcb_ctx* c, const rcb_model* m, uint64_t n_chun
             if (fat_ok) {
                 p.kind = 0;
                 p.fmode = FM_BIG;
-                // FUSED kernel: 32-byte entries (candidates + reciprocals of their frequencies)
-                const size_t fixed = (size_t)LUT_CAP * 2 * sizeof(LutEntry) + (size_t)m->K * sizeof(uint2);
+                // FUSED kernel: candidates (16 bytes) + reciprocals of their frequencies (8 bytes) per bucket
+                const size_t fixed = (size_t)LUT_CAP * (sizeof(LutEntry) + 8) + (size_t)m->K * sizeof(uint2);
                 while (p.threads > 32 && (size_t)p.threads * RING_STRIDE + fixed > budget) p.threads >>= 1;
                 p.lanes = (uint32_t)p.threads;
                 p.smem = (size_t)p.threads * RING_STRIDE + fixed;

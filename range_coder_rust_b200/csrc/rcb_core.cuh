@@ -512,8 +512,8 @@ RCB_HD bool lut_resolve(const LutEntry& e, uint64_t d, uint64_t rpt, uint32_t& s
 //   (data' - lower') / rpt_{n+1}  ~=  (data - nlo) * total / (rpt_n * c_n)
 // because both sides of the division are shifted by the same bytes.  So the estimate needs neither
 // the renormalisation shift nor a reciprocal of the new range: with q_n = 1/float(rpt_n >> sr)
-// (computed while the table load of symbol n is in flight) and rc = 32*lut_scale*2^-sr / c_n stored
-// next to the candidates (32-byte shared-memory entries),
+// (computed while the table load of symbol n is in flight) and rc = 16*lut_scale*2^-sr / c_n stored
+// in a second shared-memory array (one float pair per 16-byte entry),
 //   bf = float(data - nlo) * (q_n * rc)        = byte offset of the next entry, fractional.
 // Error: rpt_n >> sr keeps >= 16 bits (estimate <= 1/16 bucket high), floor in rpt_{n+1} (<= 1/32 low):
 // inside the 1/8-bucket margin the table is built with; the choice is verified exactly anyway.
@@ -526,22 +526,22 @@ RCB_HD float u64_to_float(uint64_t x) {
 #endif
 }
 RCB_HD uint32_t fused_sr(const FusedParams& fp) { return fp.s < 32u ? 32u - fp.s : 0u; }
-RCB_HD float lut_rc32(uint32_t c, float lut_scale, uint32_t sr) {
-    return c ? (32.0f * lut_scale / (float)(1u << sr)) / (float)c : 0.0f;
+RCB_HD float lut_rc16(uint32_t c, float lut_scale, uint32_t sr) {
+    return c ? (16.0f * lut_scale / (float)(1u << sr)) / (float)c : 0.0f;
 }
 RCB_HD float lut_q(uint64_t rpt, uint32_t sr) { return fast_rcp((float)(uint32_t)(rpt >> sr)); }
 // estimate from scratch (loop entry, after the exact path): d = data - lower, range = rpt << s
-RCB_HD float lut_bf32_init(uint64_t d, uint64_t rg, float lut_scale) {
-    return u64_to_float(d) * (fast_rcp(u64_to_float(rg)) * (32.0f * lut_scale));
+RCB_HD float lut_bf16_init(uint64_t d, uint64_t rg, float lut_scale) {
+    return u64_to_float(d) * (fast_rcp(u64_to_float(rg)) * (16.0f * lut_scale));
 }
-RCB_HD uint32_t lut_offset32(float bf) {  // byte offset of a 32-byte entry, 4096 entries
+RCB_HD uint32_t lut_offset16(float bf) {  // byte offset of a 16-byte entry, 4096 entries
 #if defined(__CUDA_ARCH__)
     // round-toward-zero add of 2^23 leaves floor(bf) in the mantissa; no clamp: a huge estimate
     // (garbage stream) lands on some in-bounds entry that fails verification (exact fallback)
-    return __float_as_uint(__fadd_rz(bf, 8388608.0f)) & 0x1FFE0u;
+    return __float_as_uint(__fadd_rz(bf, 8388608.0f)) & 0xFFF0u;
 #else
-    if (!(bf < 131071.0f)) return 0x1FFE0u;
-    return (uint32_t)bf & 0x1FFE0u;
+    if (!(bf < 65535.0f)) return 0xFFF0u;
+    return (uint32_t)bf & 0xFFF0u;
 #endif
 }
 

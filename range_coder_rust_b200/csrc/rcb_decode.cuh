@@ -254,8 +254,9 @@ template <typename SYM, bool SHARED, bool POW2, bool CHECKED, bool FUSED>
 __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
     extern __shared__ __align__(16) uint8_t s_raw[];
     __shared__ ModelHdr s_hdr;
-    constexpr uint32_t LUT_STRIDE = FUSED ? 2u : 1u;  // in 16-byte units
-    // shared layout: rings[blockDim.x][RING_STRIDE] | LutEntry[nb] (FUSED: 4096 x {LutEntry, rcA, rcB, -, -}) | uint2[K]
+    // shared layout: rings[blockDim.x][RING_STRIDE] | LutEntry[nb or 4096] | (FUSED) float2 rc[4096] | uint2[K]
+    // (entries and reciprocals in separate arrays: 16- and 8-byte strides spread random lookups over all
+    // banks; one 32-byte record per bucket doubled the bank conflicts once several warps share an SM)
     uint8_t* s_ring = s_raw;
     LutEntry* s_lut = reinterpret_cast<LutEntry*>(s_raw + (size_t)blockDim.x * RING_STRIDE);
     uint2* s_tab = nullptr;
@@ -264,18 +265,17 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
         __syncthreads();
         const uint32_t nb = (s_hdr.flags & MODEL_REGULAR) ? s_hdr.nb : 0u;
         const uint32_t nb_pad = FUSED ? 4096u : nb;  // FUSED indexes any of 4096 entries
-        s_tab = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(s_lut) +
-                                         (size_t)nb_pad * sizeof(LutEntry) * LUT_STRIDE);
+        float2* s_rc = reinterpret_cast<float2*>(s_lut + nb_pad);
+        s_tab = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(s_rc) + (FUSED ? 4096u * sizeof(float2) : 0u));
         const uint4* gl = reinterpret_cast<const uint4*>(a.lut);
         uint4* sl = reinterpret_cast<uint4*>(s_lut);
         const uint32_t total = s_hdr.div.total;
         const uint32_t sr = fused_sr(make_fused(s_hdr.div));
         for (uint32_t i = threadIdx.x; i < nb_pad; i += blockDim.x) {
             const uint4 e = i < nb ? gl[i] : make_uint4(total, total, total, 0u);  // empty interval: never verifies
-            sl[i * LUT_STRIDE] = e;
+            sl[i] = e;
             if (FUSED)  // reciprocals of the candidates' frequencies for the shift-free estimate (rcb_core.cuh)
-                sl[i * 2 + 1] = make_uint4(__float_as_uint(lut_rc32(e.y - e.x, s_hdr.lut_scale, sr)),
-                                           __float_as_uint(lut_rc32(e.z - e.y, s_hdr.lut_scale, sr)), 0u, 0u);
+                s_rc[i] = make_float2(lut_rc16(e.y - e.x, s_hdr.lut_scale, sr), lut_rc16(e.z - e.y, s_hdr.lut_scale, sr));
         }
         for (uint32_t i = threadIdx.x; i < a.K; i += blockDim.x) s_tab[i] = a.tabs[i];
         __syncthreads();
@@ -383,8 +383,9 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
         uint64_t rpt = rg >> fp.s;
         const uint32_t sr = fused_sr(fp);
         float q = lut_q(rpt, sr);                                      // 1 / float(rpt >> sr)
-        float bf = lut_bf32_init(sink.data() - lo, rg, lut_scale);     // byte offset of the next entry
+        float bf = lut_bf16_init(sink.data() - lo, rg, lut_scale);     // byte offset of the next entry
         const uint32_t lut_saddr = (uint32_t)__cvta_generic_to_shared(s_lut);
+        const uint32_t rc_saddr = lut_saddr + 4096u * (uint32_t)sizeof(LutEntry);
         // Four symbols, straight-line and speculative; `bad` = some symbol needs the exact path.
         auto decode_word = [&](uint32_t& acc, bool& bad) {
             acc = 0;
@@ -392,9 +393,9 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
 #pragma unroll
             for (uint32_t b = 0; b < PER; b++) {
                 const uint64_t data = sink.data();
-                const uint32_t off = lut_offset32(bf);
+                const uint32_t off = lut_offset16(bf);
                 const LutEntry e = lds_lut(lut_saddr + off);
-                const float2 rc = lds_f2(lut_saddr + off + 16u);
+                const float2 rc = lds_f2(rc_saddr + (off >> 1));
                 const FusedDec r = fused_decode_step(lo, rpt, data, e, fp);
                 // next symbol's entry from the unshifted residue: no dependence on the shift (rcb_core.cuh)
                 bf = u64_to_float(data - r.nlo) * (q * (r.takeB ? rc.y : rc.x));
@@ -425,7 +426,7 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
 #pragma unroll 1
             for (uint32_t b = 0; b < PER; b++) {
                 const uint64_t data = sink.data();
-                const uint32_t off = lut_offset32(lut_bf32_init(data - lo, rpt << fp.s, lut_scale));
+                const uint32_t off = lut_offset16(lut_bf16_init(data - lo, rpt << fp.s, lut_scale));
                 const FusedDec r = fused_decode_step(lo, rpt, data, lds_lut(lut_saddr + off), fp);
                 uint32_t sym = r.sym;
                 if (RCB_LIKELY(r.ok)) {
@@ -448,7 +449,7 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
             }
             rg = rpt << fp.s;
             q = lut_q(rpt, sr);
-            bf = lut_bf32_init(sink.data() - lo, rg, lut_scale);
+            bf = lut_bf16_init(sink.data() - lo, rg, lut_scale);
             return acc;
         };
         // Main loop: the words every live lane of the warp has (all of them, except in a warp holding the
@@ -493,7 +494,7 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
             const uint64_t rpt = pow2 ? range_par_total<true>(rg, div) : range_par_total<false>(rg, div);
             const uint64_t d = sink.data() - lo;  // examples/sample_impl.rs:29
             const uint32_t b = lut_bucket(d, rg, lut_scale, max_bucket);
-            const LutEntry e = s_lut[b * LUT_STRIDE];
+            const LutEntry e = s_lut[b];
             uint32_t sym;
             uint64_t P, rgn;
             if (RCB_LIKELY(lut_resolve(e, d, rpt, sym, P, rgn))) {

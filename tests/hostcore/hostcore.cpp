@@ -206,13 +206,13 @@ extern "C" int64_t hc_decode(const uint8_t* stream, uint64_t off0, uint64_t off1
         // shift-free estimate, as in decode_kernel: q = 1/float(rpt >> sr), rc = const / c of the candidate
         const uint32_t sr = fused_sr(fp);
         float q = lut_q(rpt, sr);
-        float bf = lut_bf32_init(sink.data() - lo, rg, h.lut_scale);
+        float bf = lut_bf16_init(sink.data() - lo, rg, h.lut_scale);
         for (uint64_t i = 0; i < n_syms; i++) {
             const uint64_t data = sink.data();
-            const uint32_t off = lut_offset32(bf);
-            const LutEntry e = pad[off >> 5];
-            const float rcA = lut_rc32(e.cumB - e.cumA, h.lut_scale, sr);
-            const float rcB = lut_rc32(e.cumC - e.cumB, h.lut_scale, sr);
+            const uint32_t off = lut_offset16(bf);
+            const LutEntry e = pad[off >> 4];
+            const float rcA = lut_rc16(e.cumB - e.cumA, h.lut_scale, sr);
+            const float rcB = lut_rc16(e.cumC - e.cumB, h.lut_scale, sr);
             FusedDec r = fused_decode_step(lo, rpt, data, e, fp);
             uint32_t sym;
             if (r.ok) {
@@ -230,7 +230,7 @@ extern "C" int64_t hc_decode(const uint8_t* stream, uint64_t off0, uint64_t off1
                 renorm<false>(lo, rg, sink, err);
                 rpt = rg >> fp.s;
                 q = lut_q(rpt, sr);
-                bf = lut_bf32_init(sink.data() - lo, rg, h.lut_scale);
+                bf = lut_bf16_init(sink.data() - lo, rg, h.lut_scale);
             }
             store_sym(out, i, sym_bytes, sym);
         }
