@@ -22,7 +22,7 @@
 
 namespace rcb {
 
-constexpr uint32_t ROW_PAD = 4;  // row entries K .. K+3 hold total
+constexpr uint32_t ROW_PAD = 5;  // row entries K .. K+4 hold total (odd row pitch for even K: lanes on distinct banks)
 
 struct DecodeRowArgs {
     const uint8_t* stream;
