@@ -142,6 +142,24 @@ def test_generator_matches_oracle(ctx, oracle):
     assert np.array_equal(dev_to_np(got), ref)
 
 
+def test_histogram_small_alphabets_and_range_check(ctx, oracle):
+    """Byte histogram kernel (replicated bins): K < 256 takes the range-checked flavour; vector loop,
+    two-loads-per-trip loop and the scalar tail are all exercised; a symbol >= K is reported."""
+    from range_coder_rust_b200 import _lib
+
+    rng = np.random.default_rng(11)
+    for K, n in ((100, (1 << 20) + 7), (2, 12345), (255, 3 * 4096 + 16)):
+        syms = rng.integers(0, K, size=n).astype(np.uint8)
+        d = to_dev(ctx, syms)
+        counts = ctx.histogram(d, K)
+        assert np.array_equal(dev_to_np(counts).astype(np.uint64), oracle.histogram(syms, K))
+    syms = rng.integers(0, 100, size=1 << 16).astype(np.uint8)
+    syms[40000] = 100  # out of range, inside the vector loop
+    with pytest.raises(_lib.RcbError) as e:
+        ctx.histogram(to_dev(ctx, syms), 100)
+    assert e.value.code == _lib.RCB_ERR_SYMBOL_OUT_OF_RANGE
+
+
 # ------------------------- config 3: per-chunk adaptive histograms, chunk sweep
 S_CYCLE = (0.0, 0.25, 0.5, 0.8, 1.1, 1.5, 2.0, 3.0, 5.0)
 
