@@ -409,10 +409,8 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
         };
         // The word was not clean for this lane: back to the checkpoint (register moves) and through the
         // word one symbol at a time, inline and on the same ring -- the table step where it verifies, the
-        // reference's literal loops / search where it does not.  A word consumes at most ~52 bytes and
-        // the ring holds >= 90 completed bytes at a checkpoint once drained.
+        // reference's literal loops / search where it does not.
         auto redo_word = [&](const DecLaneState& chk) -> uint32_t {
-            fill.drain();
             lo = chk.lo;
             rpt = chk.rg >> fp.s;
             sink.dh = chk.dh;
@@ -421,7 +419,10 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
             sink.wl = chk.wl;
             sink.cnt = chk.cnt;
             sink.f.rd = chk.rd;
-            sink.f.reload();
+            // ring filled to the brim and landed (>= 112 bytes from the checkpoint; this word consumes at
+            // most ~52), current word reloaded: the invariant of round() holds again however many unclean
+            // words follow each other
+            fill.resync(sink.f);
             uint32_t acc = 0;
 #pragma unroll 1
             for (uint32_t b = 0; b < PER; b++) {
