@@ -113,6 +113,14 @@ struct RingFill {
         issue_if(p2, f.ring);
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
+    // One piece per call: enough for the fused word loop (a clean word consumes <= 12 bytes, an unclean
+    // one refills the ring completely before it is re-decoded).
+    __device__ __forceinline__ void round1(RingFetch& f) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        const uint32_t occ = wr * 16 - f.rd * 4;
+        issue_if((occ <= RING_PIECES * 16 - 16) & (wr < npieces), f.ring);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     // Before the exact out-of-line path: everything requested has landed, so that path can read the ring.
     __device__ __forceinline__ void drain() {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -465,7 +473,7 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
             bool bad, leave;
 #pragma unroll 1
             do {
-                fill.round(sink.f);
+                fill.round1(sink.f);
                 rg = rpt << fp.s;  // checkpoint in the generic form (low s bits never matter)
                 chk = snapshot();
                 decode_word(acc, bad);
@@ -477,7 +485,7 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
         }
 #pragma unroll 1
         for (; i < nw; i++) {  // ragged warp only
-            fill.round(sink.f);
+            fill.round1(sink.f);
             rg = rpt << fp.s;
             const DecLaneState chk = snapshot();
             uint32_t acc;
