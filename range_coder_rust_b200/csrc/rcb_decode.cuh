@@ -418,9 +418,16 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
         // The word was not clean for this lane: back to the checkpoint (register moves) and through the
         // word one symbol at a time, inline and on the same ring -- the table step where it verifies, the
         // reference's literal loops / search where it does not.
-        auto redo_word = [&](const DecLaneState& chk) -> uint32_t {
+        struct WordChk {  // lane state at the start of a word: what the re-decode restarts from
+            uint64_t lo, rpt;
+            uint32_t dh, dl, wh, wl, cnt, rd;
+        };
+        auto checkpoint = [&]() -> WordChk {
+            return WordChk{lo, rpt, sink.dh, sink.dl, sink.wh, sink.wl, sink.cnt, sink.f.rd};
+        };
+        auto redo_word = [&](const WordChk& chk) -> uint32_t {
             lo = chk.lo;
-            rpt = chk.rg >> fp.s;
+            rpt = chk.rpt;
             sink.dh = chk.dh;
             sink.dl = chk.dl;
             sink.wh = chk.wh;
@@ -468,14 +475,13 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
         const uint32_t nw_warp = __reduce_min_sync(live, (uint32_t)(nw < 0xFFFFFFFFull ? nw : 0xFFFFFFFFull));
         uint64_t i = 0;
         while (i < nw_warp) {
-            DecLaneState chk;
+            WordChk chk;
             uint32_t acc;
             bool bad, leave;
 #pragma unroll 1
             do {
                 fill.round1(sink.f);
-                rg = rpt << fp.s;  // checkpoint in the generic form (low s bits never matter)
-                chk = snapshot();
+                chk = checkpoint();
                 decode_word(acc, bad);
                 dw[i] = acc;  // speculative as well: rewritten below when the word was not clean
                 ++i;
@@ -486,8 +492,7 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
 #pragma unroll 1
         for (; i < nw; i++) {  // ragged warp only
             fill.round1(sink.f);
-            rg = rpt << fp.s;
-            const DecLaneState chk = snapshot();
+            const WordChk chk = checkpoint();
             uint32_t acc;
             bool bad;
             decode_word(acc, bad);
