@@ -53,8 +53,11 @@ def parse_args():
 
 
 def workload_name(a):
+    std = a.alphabet == 256 and a.zipf == 1.1 and a.chunk == 65536
+    which = ("BASELINE.json configs[1]" if std and a.bytes == 1 << 30 else
+             "BASELINE.json configs[4] shard" if std and a.bytes == 8 << 30 else "custom shape")
     return (f"{a.bytes / 2**30:g} GiB/GPU synthetic Zipf(s={a.zipf}) bytes, {a.alphabet}-symbol static global "
-            f"freq table, {a.chunk // 1024} KiB chunks (BASELINE.json configs[1])")
+            f"freq table, {a.chunk // 1024} KiB chunks ({which})")
 
 
 # ----------------------------------------------------------------- clocks
