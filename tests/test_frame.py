@@ -1,6 +1,7 @@
 """RCB2 container: the checker-side writer/reader on CPU, and -- on a GPU --
 frames written by the library decoded by the oracle and the reverse, byte for byte."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -105,3 +106,24 @@ def test_gpu_frame_empty_and_capacity(ctx, oracle):
                                        out.ctypes.data_as(ctypes.c_void_p), out.nbytes, ctypes.byref(n))
     assert rc == -8  # RCB_ERR_OUT_CAPACITY
     assert n.value == 7
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("adaptive", [False, True])
+def test_file_front_end_round_trip(tmp_path, oracle, adaptive):
+    """python -m range_coder_rust_b200 compress / decompress: the frame on disk decodes with the checker too."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    data = _data(oracle, 300_007, 256, s=1.3, seed=0x5EED0007)
+    src, frm, dst = tmp_path / "in.bin", tmp_path / "in.rcb2", tmp_path / "out.bin"
+    data.tofile(src)
+    cmd = [sys.executable, "-m", "range_coder_rust_b200"]
+    subprocess.run(cmd + ["compress", str(src), str(frm), "--chunk", "32768"] + (["--adaptive"] if adaptive else []),
+                   check=True, cwd=root)
+    subprocess.run(cmd + ["decompress", str(frm), str(dst)], check=True, cwd=root)
+    assert np.array_equal(np.fromfile(dst, dtype=np.uint8), data)
+    assert np.array_equal(frame_ref.decode_frame(np.fromfile(frm, dtype=np.uint8)), data)
+    out = subprocess.run(cmd + ["info", str(frm)], check=True, cwd=root, capture_output=True, text=True).stdout
+    assert "300007 symbols" in out and ("per-chunk tables" in out) == adaptive
