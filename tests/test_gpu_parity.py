@@ -320,6 +320,40 @@ def test_error_statuses(ctx, oracle):
     assert e.value.code == _lib.RCB_ERR_OUT_CAPACITY
 
 
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("kind", ["static_pow2", "static_odd", "adaptive", "k4096"])
+def test_garbage_streams_terminate(ctx, oracle, kind):
+    """Corrupt input must never hang or fault the decoder (the reference would panic or spin): random
+    bytes in place of the code stream, through every kernel family.  Any status is acceptable; the call
+    has to return and the context has to stay usable."""
+    import range_coder_rust_b200 as rcb
+
+    K = 4096 if kind == "k4096" else 256
+    sb = 2 if K > 256 else 1
+    chunk, n = 4096, 64 * 4096 + 123
+    syms = oracle.generate(n, K, 0x5EED0001, oracle.zipf_thresholds(K, 1.1), sym_bytes=sb)
+    d = to_dev(ctx, syms)
+    if kind == "adaptive":
+        model = ctx.model_from_counts(ctx.histogram(d, K, chunk_syms=chunk))
+    else:
+        counts = ctx.histogram(d, K)
+        if kind == "static_odd":
+            counts[0] += 999
+        model = ctx.model_from_counts(counts)
+    stream, offsets, nbytes = ctx.encode_chunks(d, chunk, model)
+    rng = np.random.default_rng(3)
+    for trial in range(3):
+        junk = torch.from_numpy(rng.integers(0, 256, size=stream.numel(), dtype=np.uint8)).to(ctx.device)
+        if trial == 2:
+            junk.fill_(0xFF)  # lower ends in ones everywhere: the worst case for loop 2
+        try:
+            ctx.decode_chunks(junk, offsets, n, chunk, model, sym_bytes=sb)
+        except rcb.RcbError:
+            pass
+    back = ctx.decode_chunks(stream, offsets, n, chunk, model, sym_bytes=sb)  # still works afterwards
+    assert np.array_equal(dev_to_np(back, dtype=syms.dtype), syms)
+
+
 def test_staging_overflow_retry(ctx, oracle):
     """A model whose rarest symbol dominates the data needs more than the default
     staging estimate only in pathological cases; force one via a tiny estimate."""
