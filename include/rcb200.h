@@ -51,7 +51,8 @@ typedef enum rcb_error {
                                       src/decoder.rs:33 */
     RCB_ERR_INVALID_MODEL = -10,   /* table has cum_freq > total_freq (outside the path) */
     RCB_ERR_UNSUPPORTED = -11,
-    RCB_ERR_NO_DEVICE = -12        /* no CUDA device: there is no CPU fallback */
+    RCB_ERR_NO_DEVICE = -12,       /* no CUDA device: there is no CPU fallback */
+    RCB_ERR_NCCL = -13             /* an NCCL call failed or libnccl.so.2 is missing; see rcb_comm_last_error */
 } rcb_error;
 
 /* per-chunk status words written to d_status (0 = ok) */
@@ -83,6 +84,7 @@ int rcb_last_cuda_error(const rcb_ctx *ctx, const char **msg);
 /* ---- context --------------------------------------------------------------
  * Replaces nothing in the reference (it has no runtime); owns the stream and
  * scratch.  `stream` is a cudaStream_t (NULL = the default stream). */
+int rcb_device_count(void); /* CUDA devices visible to this process (0 when there is none) */
 int rcb_ctx_create(int device, void *stream, rcb_ctx **out);
 int rcb_ctx_destroy(rcb_ctx *ctx);
 int rcb_ctx_set_stream(rcb_ctx *ctx, void *stream);
@@ -97,6 +99,15 @@ uint64_t rcb_ctx_launch_count(const rcb_ctx *ctx);
  * status summary of the most recent encode / decode issued with timing on. */
 int rcb_ctx_enable_timing(rcb_ctx *ctx, int on);
 int rcb_ctx_get_timings(rcb_ctx *ctx, float *ms, int n);
+
+/* ---- device memory for hosts that carry no CUDA binding of their own (a Rust
+ * caller sharding over several GPUs needs device-resident shards for
+ * rcb_histogram / rcb_encode_chunks).  16-byte aligned; the copies run on the
+ * ctx's stream and synchronise it. */
+int rcb_device_alloc(rcb_ctx *ctx, uint64_t bytes, void **d_out);
+int rcb_device_free(rcb_ctx *ctx, void *d_ptr);
+int rcb_copy_to_device(rcb_ctx *ctx, void *d_dst, const void *h_src, uint64_t bytes);
+int rcb_copy_to_host(rcb_ctx *ctx, void *h_dst, const void *d_src, uint64_t bytes);
 
 /* ---- frequency model ------------------------------------------------------
  * Dense snapshot of a `PModel` (src/pmodel.rs:4-13): c_freq(i), cum_freq(i)
@@ -239,6 +250,32 @@ int rcb_frame_encode_host(rcb_ctx *ctx, const void *h_syms, uint64_t n_syms, int
                           uint64_t *h_frame_bytes);
 int rcb_frame_decode_host(rcb_ctx *ctx, const uint8_t *h_frame, uint64_t len, void *h_syms_out,
                           uint64_t out_cap_bytes, uint64_t *h_n_syms);
+
+/* ---- multi-GPU: the path's only exchange step -----------------
+ * Chunks shard over GPUs with no data-path collective.  A static model shared by
+ * chunks on several GPUs needs the sum of the per-GPU count tables -- in the
+ * reference the caller owns that loop (FreqTable::add_alphabet_freq over all the
+ * data, examples/sample_impl.rs:77-81) -- which is ONE ncclAllReduce(sum) of
+ * uint64[K] over NVLink; every rank then runs the same deterministic
+ * rcb_model_from_counts and holds an identical table.  NCCL is bound at run time
+ * (dlopen libnccl.so.2, or $RCB_NCCL_LIB), so hosts that never shard need none.
+ *   one process / thread per GPU:  rank 0 calls rcb_comm_unique_id and ships the
+ *     128 bytes to the others out of band; every rank calls rcb_comm_init_rank.
+ *   one thread driving all GPUs:   rcb_comm_init_all + rcb_allreduce_counts_multi. */
+#define RCB_UNIQUE_ID_BYTES 128
+typedef struct rcb_comm rcb_comm;
+int rcb_comm_unique_id(uint8_t *id /*[RCB_UNIQUE_ID_BYTES]*/);
+int rcb_comm_init_rank(rcb_ctx *ctx, const uint8_t *id, int n_ranks, int rank, rcb_comm **out);
+int rcb_comm_init_all(rcb_ctx *const *ctxs, int n_ctx, rcb_comm **out /*[n_ctx]*/);
+int rcb_comm_destroy(rcb_comm *comm);
+int rcb_comm_info(const rcb_comm *comm, int *n_ranks, int *rank, int *nccl_version);
+const char *rcb_comm_last_error(const rcb_comm *comm);
+/* d_counts = uint64[K] as written by rcb_histogram(chunk_syms == 0): summed over
+ * the communicator's ranks, in place, on the ctx's stream; does not synchronise
+ * (rcb_model_from_counts on the same ctx is ordered after it). */
+int rcb_allreduce_counts(rcb_ctx *ctx, rcb_comm *comm, void *d_counts, uint32_t K);
+int rcb_allreduce_counts_multi(rcb_ctx *const *ctxs, rcb_comm *const *comms, void *const *d_counts,
+                               uint32_t K, int n_ctx);
 
 /* ---- synthetic data (benchmark inputs; not in the reference)
  * symbol j = #{ i < K-1 : thr[t][i] <= mix64(seed + j*GOLDEN) >> 32 },

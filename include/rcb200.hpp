@@ -17,6 +17,7 @@
 // types throw; where it would never return (a coded symbol with c_freq == 0)
 // they throw RangeCoderPanic("zero frequency").
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <deque>
@@ -265,6 +266,107 @@ std::vector<Sym> decode_chunks(Context& ctx, const ModelSnapshot& snap, const En
           "gpu::decode_chunks");
     return out;
 }
+
+// A static table shared by chunks that live on several GPUs, one host thread driving all
+// of them: GPU g owns the chunks [n_chunks*g/G, n_chunks*(g+1)/G).  The frequency table is what the
+// reference's caller builds with FreqTable::add_alphabet_freq over ALL the data + calc_cum
+// (examples/sample_impl.rs:77-81): per-GPU histograms of the local chunks, ONE all-reduce of the K
+// counts over NVLink (rcb_allreduce_counts_multi), then the same deterministic table on every GPU.
+// No payload byte crosses GPUs; the per-GPU streams concatenate in chunk order.
+class MultiGpu {
+public:
+    explicit MultiGpu(int n_gpus) {
+        if (n_gpus < 1 || n_gpus > rcb_device_count()) throw RangeCoderPanic(RCB_ERR_INVALID_ARGUMENT, "MultiGpu");
+        ctx_.resize(n_gpus, nullptr);
+        comm_.resize(n_gpus, nullptr);
+        model_.resize(n_gpus, nullptr);
+        for (int g = 0; g < n_gpus; g++) check(rcb_ctx_create(g, nullptr, &ctx_[g]), "rcb_ctx_create");
+        check(rcb_comm_init_all(ctx_.data(), n_gpus, comm_.data()), "rcb_comm_init_all");
+    }
+    ~MultiGpu() {
+        for (auto m : model_) rcb_model_destroy(m);
+        for (auto k : comm_) rcb_comm_destroy(k);
+        for (auto c : ctx_) rcb_ctx_destroy(c);
+    }
+    MultiGpu(const MultiGpu&) = delete;
+    MultiGpu& operator=(const MultiGpu&) = delete;
+    int gpus() const { return (int)ctx_.size(); }
+
+    // histogram (sharded) -> all-reduce -> table -> encode, every chunk on its own GPU
+    template <class Sym>
+    Encoded encode_chunks(const std::vector<Sym>& syms, uint32_t K, uint64_t chunk_syms) {
+        const int G = gpus();
+        const uint64_t n = syms.size(), n_chunks = (n + chunk_syms - 1) / chunk_syms;
+        std::vector<void*> d_syms(G, nullptr), d_counts(G, nullptr);
+        std::vector<uint64_t> first(G + 1);
+        for (int g = 0; g <= G; g++) first[g] = std::min<uint64_t>(n, n_chunks * g / G * chunk_syms);
+        for (int g = 0; g < G; g++) {
+            const uint64_t cnt = first[g + 1] - first[g];
+            check(rcb_device_alloc(ctx_[g], cnt * sizeof(Sym), &d_syms[g]), "rcb_device_alloc");
+            check(rcb_device_alloc(ctx_[g], (uint64_t)K * 8, &d_counts[g]), "rcb_device_alloc");
+            check(rcb_copy_to_device(ctx_[g], d_syms[g], syms.data() + first[g], cnt * sizeof(Sym)), "rcb_copy_to_device");
+            check(rcb_histogram(ctx_[g], d_syms[g], cnt, (int)sizeof(Sym), K, 0, d_counts[g]), "rcb_histogram");
+        }
+        check(rcb_allreduce_counts_multi(ctx_.data(), comm_.data(), d_counts.data(), K, G), "rcb_allreduce_counts_multi");
+        Encoded e;
+        e.offsets.assign(1, 0);
+        for (int g = 0; g < G; g++) {
+            if (model_[g]) rcb_model_destroy(model_[g]);
+            model_[g] = nullptr;
+            check(rcb_model_create(ctx_[g], K, 1, &model_[g]), "rcb_model_create");
+            check(rcb_model_from_counts(ctx_[g], model_[g], d_counts[g], 8), "rcb_model_from_counts");
+            const uint64_t cnt = first[g + 1] - first[g], chunks = (cnt + chunk_syms - 1) / chunk_syms;
+            const uint64_t cap = rcb_encode_bound(ctx_[g], model_[g], cnt, (int)sizeof(Sym), chunk_syms) + 16;
+            void *d_out = nullptr, *d_off = nullptr;
+            check(rcb_device_alloc(ctx_[g], cap, &d_out), "rcb_device_alloc");
+            check(rcb_device_alloc(ctx_[g], (chunks + 1) * 8, &d_off), "rcb_device_alloc");
+            uint64_t bytes = 0;
+            check(rcb_encode_chunks(ctx_[g], d_syms[g], cnt, (int)sizeof(Sym), chunk_syms, model_[g], (uint8_t*)d_out,
+                                    cap, (uint64_t*)d_off, nullptr, &bytes),
+                  "rcb_encode_chunks");
+            const uint64_t base = e.stream.size(), k0 = e.offsets.size() - 1;
+            e.stream.resize(base + bytes);
+            e.offsets.resize(k0 + chunks + 1);
+            check(rcb_copy_to_host(ctx_[g], e.stream.data() + base, d_out, bytes), "rcb_copy_to_host");
+            check(rcb_copy_to_host(ctx_[g], e.offsets.data() + k0, d_off, (chunks + 1) * 8), "rcb_copy_to_host");
+            for (uint64_t i = 0; i <= chunks; i++) e.offsets[k0 + i] += base;  // local -> global offsets
+            rcb_device_free(ctx_[g], d_out);
+            rcb_device_free(ctx_[g], d_off);
+            rcb_device_free(ctx_[g], d_syms[g]);
+            rcb_device_free(ctx_[g], d_counts[g]);
+        }
+        return e;
+    }
+
+    // every GPU decodes its own chunks under the table of the last encode_chunks
+    template <class Sym>
+    std::vector<Sym> decode_chunks(const Encoded& e, uint64_t n_syms, uint64_t chunk_syms) {
+        const int G = gpus();
+        const uint64_t n_chunks = (n_syms + chunk_syms - 1) / chunk_syms;
+        std::vector<Sym> out(n_syms);
+        for (int g = 0; g < G; g++) {
+            const uint64_t c0 = n_chunks * g / G, c1 = n_chunks * (g + 1) / G;
+            const uint64_t s0 = std::min(n_syms, c0 * chunk_syms), s1 = std::min(n_syms, c1 * chunk_syms);
+            if (s1 == s0) continue;
+            std::vector<uint64_t> offs(e.offsets.begin() + c0, e.offsets.begin() + c1 + 1);
+            const uint64_t base = offs[0];
+            for (auto& o : offs) o -= base;
+            std::vector<uint8_t> part(e.stream.begin() + base, e.stream.begin() + base + offs.back());
+            part.resize((part.size() + 31) & ~size_t(15));
+            check(rcb_decode_host(ctx_[g], part.data(), offs.data(), s1 - s0, (int)sizeof(Sym), chunk_syms, model_[g],
+                                  out.data() + s0),
+                  "rcb_decode_host");
+        }
+        return out;
+    }
+    const rcb_model* model(int g) const { return model_[g]; }
+    rcb_ctx* context(int g) const { return ctx_[g]; }
+
+private:
+    std::vector<rcb_ctx*> ctx_;
+    std::vector<rcb_comm*> comm_;
+    std::vector<rcb_model*> model_;
+};
 }  // namespace gpu
 
 }  // namespace range_coder

@@ -6,13 +6,13 @@ the C ABI in include/rcb200.h.  This package only binds that ABI.
 """
 from ._lib import LIB_PATH, RcbError, load  # noqa: F401
 
-__all__ = ["Context", "Model", "RcbError", "zipf_thresholds", "load", "LIB_PATH"]
+__all__ = ["Context", "Model", "Comm", "RcbError", "zipf_thresholds", "load", "LIB_PATH"]
 
 
 def __getattr__(name):
     # torch is imported lazily so that `import range_coder_rust_b200` (and the
     # ABI symbol checks) work without initialising CUDA.
-    if name in ("Context", "Model", "zipf_thresholds"):
+    if name in ("Context", "Model", "Comm", "zipf_thresholds"):
         from . import api
 
         return getattr(api, name)

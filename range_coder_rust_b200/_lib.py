@@ -24,6 +24,7 @@ SIGNATURES = {
     "rcb_strerror": (ctypes.c_char_p, [ci]),
     "rcb_version": (ci, []),
     "rcb_last_cuda_error": (ci, [vp, ctypes.POINTER(ctypes.c_char_p)]),
+    "rcb_device_count": (ci, []),
     "rcb_ctx_create": (ci, [ci, vp, ctypes.POINTER(vp)]),
     "rcb_ctx_destroy": (ci, [vp]),
     "rcb_ctx_set_stream": (ci, [vp, vp]),
@@ -32,6 +33,10 @@ SIGNATURES = {
     "rcb_ctx_launch_count": (u64, [vp]),
     "rcb_ctx_enable_timing": (ci, [vp, ci]),
     "rcb_ctx_get_timings": (ci, [vp, ctypes.POINTER(ctypes.c_float), ci]),
+    "rcb_device_alloc": (ci, [vp, u64, ctypes.POINTER(vp)]),
+    "rcb_device_free": (ci, [vp, vp]),
+    "rcb_copy_to_device": (ci, [vp, vp, vp, u64]),
+    "rcb_copy_to_host": (ci, [vp, vp, vp, u64]),
     "rcb_model_create": (ci, [vp, u32, u64, ctypes.POINTER(vp)]),
     "rcb_model_destroy": (ci, [vp]),
     "rcb_histogram": (ci, [vp, vp, u64, ci, u32, u64, vp]),
@@ -57,6 +62,14 @@ SIGNATURES = {
     "rcb_frame_encode_host": (ci, [vp, vp, u64, ci, u64, vp, vp, u64, u64p]),
     "rcb_frame_decode_host": (ci, [vp, vp, u64, vp, u64, u64p]),
     "rcb_generate": (ci, [vp, vp, u64, u64, ci, u32, u64, vp, u32, u64]),
+    "rcb_comm_unique_id": (ci, [vp]),
+    "rcb_comm_init_rank": (ci, [vp, vp, ci, ci, ctypes.POINTER(vp)]),
+    "rcb_comm_init_all": (ci, [ctypes.POINTER(vp), ci, ctypes.POINTER(vp)]),
+    "rcb_comm_destroy": (ci, [vp]),
+    "rcb_comm_info": (ci, [vp, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci)]),
+    "rcb_comm_last_error": (ctypes.c_char_p, [vp]),
+    "rcb_allreduce_counts": (ci, [vp, vp, vp, u32]),
+    "rcb_allreduce_counts_multi": (ci, [ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp), u32, ci]),
 }
 
 _lib = None
@@ -107,6 +120,7 @@ RCB_ERR_TRUNCATED_STREAM = -9
 RCB_ERR_INVALID_MODEL = -10
 RCB_ERR_UNSUPPORTED = -11
 RCB_ERR_NO_DEVICE = -12
+RCB_ERR_NCCL = -13
 
 RCB_MODEL_POW2 = 1
 RCB_MODEL_CONSISTENT = 2

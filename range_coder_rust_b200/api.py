@@ -67,6 +67,41 @@ class Model:
         return c, cum, total.value, flags.value
 
 
+class Comm:
+    """An NCCL communicator owned by the library (include/rcb200.h, multi-GPU section): the path's only
+    exchange step is `Context.allreduce_counts` over it."""
+
+    def __init__(self, ctx, h, n_ranks, rank):
+        self.ctx, self.h, self.n_ranks, self.rank = ctx, h, n_ranks, rank
+
+    @staticmethod
+    def unique_id(lib=None):
+        """128 opaque bytes from rank 0 (ncclGetUniqueId); ship them to the other ranks out of band."""
+        lib = lib or _lib.load()
+        buf = (ctypes.c_uint8 * 128)()
+        rc = lib.rcb_comm_unique_id(buf)
+        if rc:
+            raise RcbError(rc, "rcb_comm_unique_id", (lib.rcb_comm_last_error(None) or b"").decode())
+        return bytes(buf)
+
+    @property
+    def nccl_version(self):
+        v = ctypes.c_int()
+        self.ctx.lib.rcb_comm_info(self.h, None, None, ctypes.byref(v))
+        return v.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.rcb_comm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Context:
     """One context per GPU (include/rcb200.h); issues work on the torch stream
     that is current when it is created (or on `stream`)."""
@@ -186,6 +221,50 @@ class Context:
         self._check(self.lib.rcb_model_from_tables(self.h, m.h, _np_ptr(c), _np_ptr(cum), _np_ptr(total)),
                     "rcb_model_from_tables")
         return m
+
+    # ------------------------------------------------------------ multi-GPU
+    def comm_init_rank(self, unique_id, n_ranks, rank):
+        """One process (or thread) per GPU: every rank calls this with rank 0's `Comm.unique_id()`."""
+        assert len(unique_id) == 128
+        buf = (ctypes.c_uint8 * 128).from_buffer_copy(unique_id)
+        h = ctypes.c_void_p()
+        rc = self.lib.rcb_comm_init_rank(self.h, buf, n_ranks, rank, ctypes.byref(h))
+        if rc:
+            raise RcbError(rc, "rcb_comm_init_rank", (self.lib.rcb_comm_last_error(None) or b"").decode())
+        return Comm(self, h, n_ranks, rank)
+
+    @staticmethod
+    def comm_init_all(ctxs):
+        """One thread driving several GPUs (ncclCommInitAll): one Comm per context, same order."""
+        lib = ctxs[0].lib
+        n = len(ctxs)
+        hs = (ctypes.c_void_p * n)(*[c.h for c in ctxs])
+        out = (ctypes.c_void_p * n)()
+        rc = lib.rcb_comm_init_all(hs, n, out)
+        if rc:
+            raise RcbError(rc, "rcb_comm_init_all", (lib.rcb_comm_last_error(None) or b"").decode())
+        return [Comm(c, ctypes.c_void_p(out[i]), n, i) for i, c in enumerate(ctxs)]
+
+    def allreduce_counts(self, counts, comm):
+        """Sum the ranks' u64 count tables in place (one ncclAllReduce on this context's stream)."""
+        assert counts.dtype == torch.int64 and counts.dim() == 1 and counts.is_contiguous()
+        rc = self.lib.rcb_allreduce_counts(self.h, comm.h, _ptr(counts), counts.numel())
+        if rc:
+            raise RcbError(rc, "rcb_allreduce_counts", (self.lib.rcb_comm_last_error(comm.h) or b"").decode())
+        return counts
+
+    @staticmethod
+    def allreduce_counts_multi(ctxs, comms, counts_list):
+        lib = ctxs[0].lib
+        n = len(ctxs)
+        K = counts_list[0].numel()
+        assert all(t.dtype == torch.int64 and t.numel() == K and t.is_contiguous() for t in counts_list)
+        hs = (ctypes.c_void_p * n)(*[c.h for c in ctxs])
+        ks = (ctypes.c_void_p * n)(*[k.h for k in comms])
+        ps = (ctypes.c_void_p * n)(*[t.data_ptr() for t in counts_list])
+        rc = lib.rcb_allreduce_counts_multi(hs, ks, ps, K, n)
+        if rc:
+            raise RcbError(rc, "rcb_allreduce_counts_multi", (lib.rcb_comm_last_error(comms[0].h) or b"").decode())
 
     # -------------------------------------------------------- encode/decode
     def encode_bound(self, model, n_syms, sym_bytes, chunk_syms):

@@ -92,6 +92,35 @@ struct rcb_model {
         }                                              \
     } while (0)
 
+// Every entry point runs on its ctx's device and leaves the calling thread's current device as it found
+// it (a multi-GPU host -- torch, a Rust thread pool -- must not see its device change under it).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) {
+            err = cudaSetDevice(dev);
+            switched = err == cudaSuccess;
+        }
+    }
+    ~DeviceGuard() {
+        if (switched && prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+#define ON_DEVICE(ctx)                                 \
+    DeviceGuard dg__((ctx)->device);                   \
+    do {                                               \
+        if (dg__.err != cudaSuccess) {                 \
+            (ctx)->last_err = dg__.err;                \
+            return RCB_ERR_CUDA;                       \
+        }                                              \
+    } while (0)
+
 #define CK_LAUNCH(ctx)                                 \
     do {                                               \
         (ctx)->launches++;                             \
@@ -117,6 +146,7 @@ extern "C" const char* rcb_strerror(int err) {
         case RCB_ERR_INVALID_MODEL: return "invalid model table (cum_freq > total_freq)";
         case RCB_ERR_UNSUPPORTED: return "unsupported configuration";
         case RCB_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+        case RCB_ERR_NCCL: return "NCCL error (or libnccl.so.2 not found)";
         default: return "unknown error";
     }
 }
@@ -143,6 +173,12 @@ static int status_to_error(uint32_t st) {
 }
 
 // ------------------------------------------------------------------ context
+extern "C" int rcb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
 extern "C" int rcb_ctx_create(int device, void* stream, rcb_ctx** out) {
     if (!out) return RCB_ERR_INVALID_ARGUMENT;
     *out = nullptr;
@@ -152,7 +188,8 @@ extern "C" int rcb_ctx_create(int device, void* stream, rcb_ctx** out) {
     rcb_ctx* c = new (std::nothrow) rcb_ctx();
     if (!c) return RCB_ERR_INVALID_ARGUMENT;
     c->device = device;
-    if (cudaSetDevice(device) != cudaSuccess) {
+    DeviceGuard dg(device);
+    if (dg.err != cudaSuccess) {
         delete c;
         return RCB_ERR_CUDA;
     }
@@ -172,7 +209,7 @@ extern "C" int rcb_ctx_create(int device, void* stream, rcb_ctx** out) {
 
 extern "C" int rcb_ctx_destroy(rcb_ctx* c) {
     if (!c) return RCB_OK;
-    cudaSetDevice(c->device);
+    DeviceGuard dg(c->device);
     cudaStreamSynchronize(c->stream);
     cudaFree(c->staging);
     cudaFree(c->lens);
@@ -224,7 +261,7 @@ extern "C" uint64_t rcb_ctx_launch_count(const rcb_ctx* c) { return c ? c->launc
 
 extern "C" int rcb_ctx_enable_timing(rcb_ctx* c, int on) {
     if (!c) return RCB_ERR_INVALID_ARGUMENT;
-    CK(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     if (on && !c->ev[0])
         for (int i = 0; i < 7; i++) CK(c, cudaEventCreate(&c->ev[i]));
     c->timing = on != 0;
@@ -302,12 +339,46 @@ static int ensure_h2d(rcb_ctx* c, size_t bytes) {
     return RCB_OK;
 }
 
+// ------------------------------------------------------------ device memory
+extern "C" int rcb_device_alloc(rcb_ctx* c, uint64_t bytes, void** d_out) {
+    if (!c || !d_out) return RCB_ERR_INVALID_ARGUMENT;
+    *d_out = nullptr;
+    ON_DEVICE(c);
+    CK(c, cudaMalloc(d_out, bytes ? (size_t)bytes : 16));
+    return RCB_OK;
+}
+
+extern "C" int rcb_device_free(rcb_ctx* c, void* d_ptr) {
+    if (!c) return RCB_ERR_INVALID_ARGUMENT;
+    if (!d_ptr) return RCB_OK;
+    ON_DEVICE(c);
+    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, cudaFree(d_ptr));
+    return RCB_OK;
+}
+
+extern "C" int rcb_copy_to_device(rcb_ctx* c, void* d_dst, const void* h_src, uint64_t bytes) {
+    if (!c || (bytes && (!d_dst || !h_src))) return RCB_ERR_INVALID_ARGUMENT;
+    ON_DEVICE(c);
+    if (bytes) CK(c, cudaMemcpyAsync(d_dst, h_src, (size_t)bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return RCB_OK;
+}
+
+extern "C" int rcb_copy_to_host(rcb_ctx* c, void* h_dst, const void* d_src, uint64_t bytes) {
+    if (!c || (bytes && (!h_dst || !d_src))) return RCB_ERR_INVALID_ARGUMENT;
+    ON_DEVICE(c);
+    if (bytes) CK(c, cudaMemcpyAsync(h_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return RCB_OK;
+}
+
 // -------------------------------------------------------------------- model
 extern "C" int rcb_model_create(rcb_ctx* c, uint32_t K, uint64_t n_models, rcb_model** out) {
     if (!c || !out || K == 0 || K > MAX_K || n_models == 0) return RCB_ERR_INVALID_ARGUMENT;
     *out = nullptr;
     if (n_models == 1 && K > MAX_K_SHARED) return RCB_ERR_UNSUPPORTED;
-    CK(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     rcb_model* m = new (std::nothrow) rcb_model();
     if (!m) return RCB_ERR_INVALID_ARGUMENT;
     m->ctx = c;
@@ -328,10 +399,8 @@ extern "C" int rcb_model_create(rcb_ctx* c, uint32_t K, uint64_t n_models, rcb_m
 
 extern "C" int rcb_model_destroy(rcb_model* m) {
     if (!m) return RCB_OK;
-    if (m->ctx) {
-        cudaSetDevice(m->ctx->device);
-        cudaStreamSynchronize(m->ctx->stream);
-    }
+    DeviceGuard dg(m->ctx ? m->ctx->device : 0);
+    if (m->ctx) cudaStreamSynchronize(m->ctx->stream);
     cudaFree(m->d_tab);
     cudaFree(m->d_total);
     cudaFree(m->d_hdr);
@@ -395,7 +464,7 @@ extern "C" int rcb_histogram(rcb_ctx* c, const void* d_syms, uint64_t n_syms, in
     if (sym_bytes != 1 && sym_bytes != 2) return RCB_ERR_UNSUPPORTED;
     if (K > 16384) return RCB_ERR_UNSUPPORTED;  // per-warp private bins must fit shared memory
     if (reinterpret_cast<uintptr_t>(d_syms) & 15u) return RCB_ERR_INVALID_ARGUMENT;
-    CK(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     CK(c, cudaMemsetAsync(c->d_words + 2, 0, sizeof(uint32_t), c->stream));
     int r = sym_bytes == 1 ? launch_hist<uint8_t>(c, d_syms, n_syms, K, chunk_syms, d_counts)
                            : launch_hist<uint16_t>(c, d_syms, n_syms, K, chunk_syms, d_counts);
@@ -436,7 +505,7 @@ extern "C" int rcb_model_from_counts(rcb_ctx* c, rcb_model* m, const void* d_cou
     if (!c || !m || !d_counts || m->ctx != c) return RCB_ERR_INVALID_ARGUMENT;
     if (count_bytes != 4 && count_bytes != 8) return RCB_ERR_INVALID_ARGUMENT;
     if (m->n_models > 0x7FFFFFFFull) return RCB_ERR_UNSUPPORTED;
-    CK(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     if (count_bytes == 8)
         counts_to_tables_kernel<unsigned long long><<<(unsigned)m->n_models, 256, 0, c->stream>>>(
             (const unsigned long long*)d_counts, m->K, m->d_tab, m->d_total);
@@ -450,7 +519,7 @@ extern "C" int rcb_model_from_counts(rcb_ctx* c, rcb_model* m, const void* d_cou
 extern "C" int rcb_model_from_tables(rcb_ctx* c, rcb_model* m, const uint32_t* h_c, const uint32_t* h_cum,
                                      const uint32_t* h_total) {
     if (!c || !m || !h_c || !h_cum || !h_total || m->ctx != c) return RCB_ERR_INVALID_ARGUMENT;
-    CK(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     const size_t n = (size_t)m->n_models * m->K;
     uint2* tmp = (uint2*)malloc(n * sizeof(uint2));
     if (!tmp) return RCB_ERR_INVALID_ARGUMENT;
@@ -471,7 +540,7 @@ extern "C" int rcb_model_from_tables(rcb_ctx* c, rcb_model* m, const uint32_t* h
 extern "C" int rcb_model_get_tables(rcb_ctx* c, const rcb_model* m, uint64_t index, uint32_t* h_c,
                                     uint32_t* h_cum, uint32_t* h_total, uint32_t* h_flags) {
     if (!c || !m || index >= m->n_models) return RCB_ERR_INVALID_ARGUMENT;
-    CK(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     uint2* tmp = (uint2*)malloc((size_t)m->K * sizeof(uint2));
     if (!tmp) return RCB_ERR_INVALID_ARGUMENT;
     ModelHdr h;
@@ -647,7 +716,7 @@ static int encode_launch(rcb_ctx* c, const void* d_syms, uint64_t n_syms, int sy
     const uint64_t n_chunks = (n_syms + chunk_syms - 1) / chunk_syms;
     if (m->n_models != 1 && m->n_models != n_chunks) return RCB_ERR_INVALID_ARGUMENT;
     if (n_chunks > 0x7FFFFFFFull) return RCB_ERR_UNSUPPORTED;
-    CK(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     if (n_chunks == 0) {
         CK(c, cudaMemsetAsync(d_offsets, 0, sizeof(uint64_t), c->stream));
         CK(c, cudaMemsetAsync(c->d_summary, 0, 4 * sizeof(unsigned long long), c->stream));
@@ -928,10 +997,12 @@ extern "C" int rcb_decode_chunks_async(rcb_ctx* c, const uint8_t* d_stream, cons
     if ((reinterpret_cast<uintptr_t>(d_stream) & 15u) || (reinterpret_cast<uintptr_t>(d_syms_out) & 15u) ||
         (reinterpret_cast<uintptr_t>(d_offsets) & 7u))
         return RCB_ERR_INVALID_ARGUMENT;
+    if (chunk_syms > 0x40000000ull) return RCB_ERR_UNSUPPORTED;  // same limit as the encoder
+    if (n_syms > (1ull << 62)) return RCB_ERR_INVALID_ARGUMENT;  // n_syms * sym_bytes must not wrap
     const uint64_t n_chunks = (n_syms + chunk_syms - 1) / chunk_syms;
     if (m->n_models != 1 && m->n_models != n_chunks) return RCB_ERR_INVALID_ARGUMENT;
     if (n_chunks > 0x7FFFFFFFull) return RCB_ERR_UNSUPPORTED;
-    CK(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     if (n_chunks == 0) {
         CK(c, cudaMemsetAsync(c->d_summary + 4, 0, 4 * sizeof(unsigned long long), c->stream));
         return RCB_OK;
@@ -1021,7 +1092,7 @@ extern "C" int rcb_encode_host(rcb_ctx* c, const void* h_syms, uint64_t n_syms, 
     const uint64_t in_bytes = (n_syms * sym_bytes + 15) & ~15ull;
     const uint64_t pitch = staging_pitch(m, chunk_syms);
     const uint64_t bound = n_chunks * pitch + 32;
-    CK(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     const int S = pick_slices(n_chunks, n_syms * sym_bytes);
     const uint64_t off_bytes = ((n_chunks + 1 + S) * sizeof(uint64_t) + 15) & ~15ull;
     int r = ensure_h2d(c, in_bytes + bound + off_bytes + 64);
@@ -1159,13 +1230,20 @@ extern "C" int rcb_decode_host(rcb_ctx* c, const uint8_t* h_stream, const uint64
     if (!c || !m || !m->ready || chunk_syms == 0 || !h_offsets) return RCB_ERR_INVALID_ARGUMENT;
     if (sym_bytes != 1 && sym_bytes != 2) return RCB_ERR_UNSUPPORTED;
     if (n_syms && (!h_stream || !h_syms_out)) return RCB_ERR_INVALID_ARGUMENT;
+    if (chunk_syms > 0x40000000ull) return RCB_ERR_UNSUPPORTED;
+    if (n_syms > (1ull << 62)) return RCB_ERR_INVALID_ARGUMENT;
     const uint64_t n_chunks = (n_syms + chunk_syms - 1) / chunk_syms;
     if (m->n_models != 1 && m->n_models != n_chunks) return RCB_ERR_INVALID_ARGUMENT;
+    if (n_chunks > 0x7FFFFFFFull) return RCB_ERR_UNSUPPORTED;
     const uint64_t total = h_offsets[n_chunks];
+    // the offsets size the copies below: they must be monotone and end at `total`.  (A chunk shorter
+    // than the 8 bytes Decoder::new pops is reported per chunk by the kernels as a truncated stream.)
+    for (uint64_t i = 0; i < n_chunks; i++)
+        if (h_offsets[i] > h_offsets[i + 1]) return RCB_ERR_INVALID_ARGUMENT;
     const uint64_t st_bytes = (total + 47) & ~15ull;
     const uint64_t off_bytes = ((n_chunks + 1) * sizeof(uint64_t) + 15) & ~15ull;
     const uint64_t out_bytes = (n_syms * sym_bytes + 15) & ~15ull;
-    CK(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     int r = ensure_h2d(c, st_bytes + off_bytes + out_bytes + 64);
     if (r) return r;
     uint8_t* d_st = (uint8_t*)c->h2d;
@@ -1328,7 +1406,7 @@ extern "C" int rcb_generate(rcb_ctx* c, void* d_out, uint64_t first, uint64_t n,
     const size_t thr_bytes = (size_t)n_tables * (K - 1) * sizeof(uint32_t);
     if (thr_bytes > 200 * 1024) return RCB_ERR_UNSUPPORTED;
     if (n == 0) return RCB_OK;
-    CK(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     uint32_t* d_thr = nullptr;
     CK(c, cudaMalloc(&d_thr, thr_bytes ? thr_bytes : 4));
     cudaError_t e = cudaMemcpyAsync(d_thr, h_thr, thr_bytes, cudaMemcpyHostToDevice, c->stream);
@@ -1380,7 +1458,7 @@ extern "C" int rcb_encode_stream(rcb_ctx* c, rcb_stream_state* st, const void* h
     if (m && m->n_models != 1) return RCB_ERR_UNSUPPORTED;
     if (sym_bytes != 1 && sym_bytes != 2) return RCB_ERR_UNSUPPORTED;
     if ((n_syms && !h_syms) || (out_cap && !h_out)) return RCB_ERR_INVALID_ARGUMENT;
-    CK(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     const size_t sym_b = (size_t)((n_syms * sym_bytes + 15) & ~15ull);
     const size_t out_b = (size_t)((out_cap + 15) & ~15ull);
     const size_t per_b = (size_t)((n_syms * 4 + 15) & ~15ull);
@@ -1417,8 +1495,11 @@ extern "C" int rcb_decode_stream(rcb_ctx* c, rcb_stream_state* st, const uint8_t
     if (m->n_models != 1) return RCB_ERR_UNSUPPORTED;
     if (sym_bytes != 1 && sym_bytes != 2) return RCB_ERR_UNSUPPORTED;
     if ((code_len && !h_code) || (n_syms && !h_syms_out)) return RCB_ERR_INVALID_ARGUMENT;
-    CK(c, cudaSetDevice(c->device));
-    const size_t code_b = (size_t)((code_len + 15) & ~15ull);
+    ON_DEVICE(c);
+    // only the unread tail of the code travels (the caller's per-symbol loop would otherwise copy the
+    // whole stream once per symbol)
+    const uint64_t code_base = st->consumed < code_len ? st->consumed : code_len;
+    const size_t code_b = (size_t)((code_len - code_base + 15) & ~15ull);
     const size_t sym_b = (size_t)((n_syms * sym_bytes + 15) & ~15ull);
     int r = ensure_h2d(c, 64 + code_b + sym_b + 16);
     if (r) return r;
@@ -1427,9 +1508,10 @@ extern "C" int rcb_decode_stream(rcb_ctx* c, rcb_stream_state* st, const uint8_t
     uint8_t* d_code = base + 64;
     uint8_t* d_syms = d_code + code_b;
     CK(c, cudaMemcpyAsync(d_st, st, sizeof(StreamState), cudaMemcpyHostToDevice, c->stream));
-    if (code_len) CK(c, cudaMemcpyAsync(d_code, h_code, code_len, cudaMemcpyHostToDevice, c->stream));
-    decode_stream_kernel<<<1, 1, 0, c->stream>>>(d_st, d_code, code_len, n_syms, sym_bytes, m->d_tab, m->d_hdr, m->K,
-                                                  d_syms);
+    if (code_len > code_base)
+        CK(c, cudaMemcpyAsync(d_code, h_code + code_base, code_len - code_base, cudaMemcpyHostToDevice, c->stream));
+    decode_stream_kernel<<<1, 1, 0, c->stream>>>(d_st, d_code, code_base, code_len, n_syms, sym_bytes, m->d_tab,
+                                                  m->d_hdr, m->K, d_syms);
     CK_LAUNCH(c);
     CK(c, cudaMemcpyAsync(st, d_st, sizeof(StreamState), cudaMemcpyDeviceToHost, c->stream));
     if (n_syms)
@@ -1487,7 +1569,7 @@ extern "C" int rcb_frame_write(rcb_ctx* c, const rcb_model* m, int sym_bytes, ui
     put_le<uint64_t>(p + 40, n_chunks);
     put_le<uint64_t>(p + 48, payload);
     uint8_t* ms = p + FRAME_HDR;
-    CK(c, cudaSetDevice(c->device));
+    ON_DEVICE(c);
     const size_t n_ent = (size_t)m->n_models * m->K;
     uint2* tmp = (uint2*)malloc(n_ent * sizeof(uint2));
     if (!tmp) return RCB_ERR_INVALID_ARGUMENT;
@@ -1530,18 +1612,22 @@ extern "C" int rcb_frame_parse(const uint8_t* h_frame, uint64_t len, rcb_frame_i
     if (f.version != 1 || (f.sym_bytes != 1 && f.sym_bytes != 2) || f.K == 0 || f.K > MAX_K || f.model_mode > 1 ||
         f.chunk_syms == 0)
         return RCB_ERR_INVALID_ARGUMENT;
+    // untrusted header: bound everything before it enters any arithmetic (n_syms * sym_bytes and the
+    // ceil-division below must not wrap; chunk_syms has the coder's own limit)
+    if (f.n_syms > (1ull << 62) || f.chunk_syms > 0x40000000ull) return RCB_ERR_INVALID_ARGUMENT;
     if (f.n_chunks != (f.n_syms + f.chunk_syms - 1) / f.chunk_syms) return RCB_ERR_INVALID_ARGUMENT;
-    if (f.n_chunks > (1ull << 40) || f.payload_bytes > len) return RCB_ERR_INVALID_ARGUMENT;
+    if (f.n_chunks > 0x7FFFFFFFull || f.payload_bytes > len) return RCB_ERR_INVALID_ARGUMENT;
     f.model_off = FRAME_HDR;
     f.offsets_off = f.model_off + frame_model_bytes(f.K, f.n_chunks, (int)f.model_mode);
     f.payload_off = f.offsets_off + (f.n_chunks + 1) * 8;
     f.frame_bytes = f.payload_off + f.payload_bytes;
     if (f.frame_bytes > len) return RCB_ERR_TRUNCATED_STREAM;
-    // offsets must be monotone and end at payload_bytes
+    // offsets: start at 0, every chunk holds at least the 8 bytes of Encoder::finish
+    // (src/encoder.rs:40-46), end at payload_bytes
     uint64_t prev = 0;
     for (uint64_t i = 0; i <= f.n_chunks; i++) {
         const uint64_t o = get_le<uint64_t>(h_frame + f.offsets_off + 8 * i);
-        if (o < prev || o > f.payload_bytes) return RCB_ERR_INVALID_ARGUMENT;
+        if (o > f.payload_bytes || (i == 0 ? o != 0 : o < prev + 8)) return RCB_ERR_INVALID_ARGUMENT;
         prev = o;
     }
     if (prev != f.payload_bytes) return RCB_ERR_INVALID_ARGUMENT;
@@ -1627,7 +1713,7 @@ extern "C" int rcb_frame_decode_host(rcb_ctx* c, const uint8_t* h_frame, uint64_
     int r = rcb_frame_parse(h_frame, len, &f);
     if (r) return r;
     if (h_n_syms) *h_n_syms = f.n_syms;
-    if (f.n_syms * f.sym_bytes > out_cap_bytes) return RCB_ERR_OUT_CAPACITY;
+    if (f.n_syms > out_cap_bytes / f.sym_bytes) return RCB_ERR_OUT_CAPACITY;  // no product: cannot wrap
     if (f.n_syms == 0) return RCB_OK;
     rcb_model* m = nullptr;
     r = rcb_frame_model(c, h_frame, &f, &m);
@@ -1650,3 +1736,6 @@ extern "C" int rcb_frame_decode_host(rcb_ctx* c, const uint8_t* h_frame, uint64_
     rcb_model_destroy(m);
     return r;
 }
+
+// ------------------------------------------------------------------ multi-GPU
+#include "rcb_comm.cuh"

@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
     const uint64_t seg_begin = a.seg.state ? (a.seg.first < chunk_cnt ? a.seg.first : chunk_cnt) : 0;
     const uint64_t seg_end =
         seg_save ? (a.seg.first + a.seg.syms < chunk_cnt ? a.seg.first + a.seg.syms : chunk_cnt) : chunk_cnt;
-    const uint64_t cnt = seg_end - seg_begin;
+    uint64_t cnt = seg_end - seg_begin;
     SYM* dst = reinterpret_cast<SYM*>(a.out) + first + seg_begin;
 
     const uint2* tab = SHARED ? s_tab : a.tabs + chunk * a.K;
@@ -310,8 +310,14 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
     const float max_bucket = (float)(hdr.nb ? hdr.nb - 1 : 0);
     const uint32_t K = a.K;
 
-    const uint64_t off0 = a.offsets[chunk], off1 = a.offsets[chunk + 1];
     const uint64_t total_bytes = a.offsets[a.n_chunks];
+    uint64_t off0 = a.offsets[chunk], off1 = a.offsets[chunk + 1];
+    // Offsets come from the caller (a corrupt frame, a damaged index): a chunk is at least the 8 bytes
+    // Decoder::new pops (src/decoder.rs:14-23) and lies inside the stream.  A lane whose offsets break
+    // that decodes nothing and reports ST_TRUNCATED; it stays in the warp (the loops below vote), reads
+    // no global memory (no piece is requested, no symbol decoded) and writes nothing.
+    const bool offsets_ok = off0 <= off1 && off1 - off0 >= 8 && off1 <= total_bytes;
+    if (!offsets_ok) off0 = off1 = 0;
     const uint64_t pb = off0 & ~15ull;                               // piece base (byte offset)
     const uint64_t readable = ((total_bytes + 15) & ~15ull) - pb;    // rcb200.h: readable to the next 16
     const uint32_t skip = (uint32_t)(off0 & 3u);
@@ -320,12 +326,13 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
     RingFill fill;
     fill.pbase = a.stream + pb;
     fill.wr = 0;
-    fill.npieces = readable > (0xFFFFFFF0ull << 4) ? 0xFFFFFFF0u : (uint32_t)(readable >> 4);
+    fill.npieces = !offsets_ok ? 0u : readable > (0xFFFFFFF0ull << 4) ? 0xFFFFFFF0u : (uint32_t)(readable >> 4);
+    if (!offsets_ok) cnt = 0;
     RingFetch rf;
     rf.ring = (uint32_t)__cvta_generic_to_shared(s_ring + (size_t)threadIdx.x * RING_STRIDE);
     rf.rd = seg_load ? a.seg.state[chunk].rd : rd0;
     rf.cur = 0;
-    const uint32_t last_word = fill.npieces * 4 - 1;
+    const uint32_t last_word = fill.npieces ? fill.npieces * 4 - 1 : 0u;
 
     // L2 prefetch of the next 2 KiB of this lane's code bytes; afterwards every ring piece carries a
     // 256-byte L2 prefetch hint (no per-word prefetch branch in the loops)
@@ -334,7 +341,7 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
     auto prefetch_to = [&](uint32_t upto_words) {
         while (pf_next < upto_words) {
             const uint64_t o = (uint64_t)pf_next * 4;
-            if (o < readable) {
+            if (offsets_ok && o < readable) {
                 const uint64_t left = readable - o;
                 prefetch_l2_bulk_dec(fill.pbase + o, (uint32_t)(left < PF_WORDS * 4 ? left : PF_WORDS * 4));
             }
@@ -360,6 +367,7 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
     } else {
         sink.prime(skip);  // src/decoder.rs:14-23
     }
+    if (!offsets_ok) err = ST_TRUNCATED;  // src/decoder.rs:33: pop_front on an empty buffer
 
     constexpr uint32_t PER = 4 / sizeof(SYM);  // symbols per 32-bit store
     constexpr uint32_t SYM_BITS = 8 * sizeof(SYM);

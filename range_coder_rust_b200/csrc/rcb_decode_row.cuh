@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(512, 1) decode_row_kernel(DecodeRowArgs a) {
     const uint64_t seg_begin = a.seg.state ? (a.seg.first < chunk_cnt ? a.seg.first : chunk_cnt) : 0;
     const uint64_t seg_end =
         seg_save ? (a.seg.first + a.seg.syms < chunk_cnt ? a.seg.first + a.seg.syms : chunk_cnt) : chunk_cnt;
-    const uint64_t cnt = seg_end - seg_begin;
+    const uint64_t cnt_all = seg_end - seg_begin;
     SYM* dst = reinterpret_cast<SYM*>(a.out) + first + seg_begin;
 
     const uint32_t* row = s_rows + (TABLE == TAB_LANE ? (size_t)threadIdx.x * row_words : 0);
@@ -145,8 +145,11 @@ __global__ void __launch_bounds__(512, 1) decode_row_kernel(DecodeRowArgs a) {
     const DivParams div = hdr.div;
     const bool pow2 = (hdr.flags & MODEL_POW2) != 0;
 
-    const uint64_t off0 = a.offsets[chunk], off1 = a.offsets[chunk + 1];
     const uint64_t total_bytes = a.offsets[a.n_chunks];
+    uint64_t off0 = a.offsets[chunk], off1 = a.offsets[chunk + 1];
+    // caller-supplied offsets are validated per lane (see decode_kernel): a bad lane decodes nothing
+    const bool offsets_ok = off0 <= off1 && off1 - off0 >= 8 && off1 <= total_bytes;
+    if (!offsets_ok) off0 = off1 = 0;
     const uint64_t pb = off0 & ~15ull;
     const uint64_t readable = ((total_bytes + 15) & ~15ull) - pb;
     const uint32_t skip = (uint32_t)(off0 & 3u);
@@ -155,19 +158,20 @@ __global__ void __launch_bounds__(512, 1) decode_row_kernel(DecodeRowArgs a) {
     RingFill fill;
     fill.pbase = a.stream + pb;
     fill.wr = 0;
-    fill.npieces = readable > (0xFFFFFFF0ull << 4) ? 0xFFFFFFF0u : (uint32_t)(readable >> 4);
+    fill.npieces = !offsets_ok ? 0u : readable > (0xFFFFFFF0ull << 4) ? 0xFFFFFFF0u : (uint32_t)(readable >> 4);
+    const uint64_t cnt = offsets_ok ? cnt_all : 0;
     RingFetch rf;
     rf.ring = (uint32_t)__cvta_generic_to_shared(s_ring + (size_t)threadIdx.x * RING_STRIDE);
     rf.rd = seg_load ? a.seg.state[chunk].rd : rd0;
     rf.cur = 0;
-    const uint32_t last_word = fill.npieces * 4 - 1;
+    const uint32_t last_word = fill.npieces ? fill.npieces * 4 - 1 : 0u;
 
     constexpr uint32_t PF_WORDS = 256;
     uint32_t pf_next = rf.rd & ~3u;
     auto prefetch_to = [&](uint32_t upto_words) {
         while (pf_next < upto_words) {
             const uint64_t o = (uint64_t)pf_next * 4;
-            if (o < readable) {
+            if (offsets_ok && o < readable) {
                 const uint64_t left = readable - o;
                 prefetch_l2_bulk_dec(fill.pbase + o, (uint32_t)(left < PF_WORDS * 4 ? left : PF_WORDS * 4));
             }
@@ -193,6 +197,7 @@ __global__ void __launch_bounds__(512, 1) decode_row_kernel(DecodeRowArgs a) {
     } else {
         sink.prime(skip);  // src/decoder.rs:14-23
     }
+    if (!offsets_ok) err = ST_TRUNCATED;  // src/decoder.rs:33
     constexpr uint32_t PER = 4 / sizeof(SYM);
     constexpr uint32_t SYM_BITS = 8 * sizeof(SYM);
     const FusedParams fp = make_fused(div);

@@ -363,6 +363,10 @@ __global__ void __launch_bounds__(256) finalize_models_kernel(const uint2* __res
         if (e.x > total) bad |= 4u;
         if (i + 1 < K) {
             if ((unsigned long long)tab[i + 1].x != end) bad |= 2u;
+        } else if (end != total) {
+            // unused code space above the last symbol (legal for a PModel): the row kernels derive
+            // c[K-1] as total - cum[K-1], so such a table is not a prefix-sum table either
+            bad |= 2u;
         }
         if (e.y && e.y < minc) minc = e.y;
     }

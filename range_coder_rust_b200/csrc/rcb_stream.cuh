@@ -35,16 +35,17 @@ struct ByteSinkEnc {
 };
 
 struct ByteSinkDec {
-    const uint8_t* code;
+    const uint8_t* code;  // device copy of code[base .. len): only the unread tail travels per call
     uint64_t len, pos;
     uint64_t data;
     bool truncated;
+    uint64_t base;
     __device__ void put(uint32_t, uint32_t sh) {
         for (uint32_t b = 0; b < sh; b += 8) put_byte(0);
     }
     __device__ void put_byte(uint32_t) {  // src/decoder.rs:31-35
         uint32_t v = 0;
-        if (pos < len) v = code[pos]; else truncated = true;
+        if (pos < len) v = code[pos - base]; else truncated = true;
         pos++;
         data = (data << 8) | v;
     }
@@ -90,14 +91,14 @@ __global__ void encode_stream_kernel(StreamState* st, const uint8_t* syms, uint6
 }
 
 // Decoder::new (first call: consumed == 0) + Decoder::decode for n symbols.
-__global__ void decode_stream_kernel(StreamState* st, const uint8_t* code, uint64_t len, uint64_t n,
-                                     int sym_bytes, const uint2* tab, const ModelHdr* hdr, uint32_t K,
+__global__ void decode_stream_kernel(StreamState* st, const uint8_t* code, uint64_t code_base, uint64_t len,
+                                     uint64_t n, int sym_bytes, const uint2* tab, const ModelHdr* hdr, uint32_t K,
                                      uint8_t* out_syms) {
     if (threadIdx.x || blockIdx.x) return;
     uint64_t lo = st->lower_bound, rg = st->range;
     const ModelHdr h = *hdr;
     const bool pow2 = (h.flags & MODEL_POW2) != 0;
-    ByteSinkDec sink{code, len, st->consumed, st->data, false};
+    ByteSinkDec sink{code, len, st->consumed, st->data, false, code_base};
     uint32_t err = 0;
     if (sink.pos == 0)  // src/decoder.rs:14-23
         for (int i = 0; i < 8; i++) sink.put_byte(0);

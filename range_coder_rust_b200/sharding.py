@@ -21,11 +21,31 @@ def shard_symbols(n_syms, chunk_syms, rank, world):
     return lo * chunk_syms, min(hi * chunk_syms, n_syms)
 
 
-def allreduce_counts(counts):
+def init_comm(ctx):
+    """The library's own NCCL communicator for this process group (include/rcb200.h, rcb_comm_*):
+    torch.distributed only ships rank 0's 128-byte unique id to the other ranks; the all-reduce on
+    the path is then issued by librcb200.so itself (`Context.allreduce_counts`).  Returns None for a
+    single process."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return None
+    from .api import Comm
+
+    world, rank = dist.get_world_size(), dist.get_rank()
+    box = [Comm.unique_id(ctx.lib) if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    return ctx.comm_init_rank(box[0], world, rank)
+
+
+def allreduce_counts(counts, ctx=None, comm=None):
     """Sum the local u64 histograms (stored as int64 bit patterns) over all ranks, in place.
-    Counts never exceed 2^63 in practice (that would be 8 EiB of symbols), so the signed sum is exact."""
+    With a library communicator (`init_comm`) this is rcb_allreduce_counts -- NCCL driven through the
+    C ABI, on the context's stream; without one (the gloo tests of the host logic on CPU) it falls to
+    torch.distributed.  Counts never exceed 2^63 in practice (8 EiB of symbols), so gloo's signed sum
+    is exact too."""
     assert counts.dtype == torch.int64
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+    if comm is not None:
+        ctx.allreduce_counts(counts, comm)
+    elif dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
     return counts
 

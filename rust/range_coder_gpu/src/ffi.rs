@@ -9,6 +9,11 @@ pub struct RcbCtx {
 pub struct RcbModel {
     _p: [u8; 0],
 }
+#[repr(C)]
+pub struct RcbComm {
+    _p: [u8; 0],
+}
+pub const RCB_UNIQUE_ID_BYTES: usize = 128;
 
 /// `rcb_stream_state`: RangeCoder { lower_bound, range } (src/range_coder.rs:7-12 of the reference)
 /// + Decoder::data (src/decoder.rs:8-12) + bookkeeping.
@@ -31,6 +36,7 @@ pub const RCB_ERR_UPPER_OVERFLOW: c_int = -6;
 pub const RCB_ERR_SYMBOL_OUT_OF_RANGE: c_int = -7;
 pub const RCB_ERR_OUT_CAPACITY: c_int = -8;
 pub const RCB_ERR_TRUNCATED_STREAM: c_int = -9;
+pub const RCB_ERR_NCCL: c_int = -13;
 
 extern "C" {
     pub fn rcb_ctx_create(device: c_int, stream: *mut c_void, out: *mut *mut RcbCtx) -> c_int;
@@ -94,6 +100,51 @@ extern "C" {
         sym_bytes: c_int,
         m: *const RcbModel,
         h_syms_out: *mut c_void,
+    ) -> c_int;
+
+    // device memory + the device-pointer entry points (sharding over several GPUs)
+    pub fn rcb_device_count() -> c_int;
+    pub fn rcb_device_alloc(ctx: *mut RcbCtx, bytes: u64, d_out: *mut *mut c_void) -> c_int;
+    pub fn rcb_device_free(ctx: *mut RcbCtx, d_ptr: *mut c_void) -> c_int;
+    pub fn rcb_copy_to_device(ctx: *mut RcbCtx, d_dst: *mut c_void, h_src: *const c_void, bytes: u64) -> c_int;
+    pub fn rcb_copy_to_host(ctx: *mut RcbCtx, h_dst: *mut c_void, d_src: *const c_void, bytes: u64) -> c_int;
+    pub fn rcb_histogram(
+        ctx: *mut RcbCtx,
+        d_syms: *const c_void,
+        n_syms: u64,
+        sym_bytes: c_int,
+        k: u32,
+        chunk_syms: u64,
+        d_counts: *mut c_void,
+    ) -> c_int;
+    pub fn rcb_model_from_counts(ctx: *mut RcbCtx, m: *mut RcbModel, d_counts: *const c_void, count_bytes: c_int) -> c_int;
+    pub fn rcb_encode_chunks(
+        ctx: *mut RcbCtx,
+        d_syms: *const c_void,
+        n_syms: u64,
+        sym_bytes: c_int,
+        chunk_syms: u64,
+        m: *const RcbModel,
+        d_out: *mut u8,
+        out_cap: u64,
+        d_offsets: *mut u64,
+        d_status: *mut u32,
+        h_out_bytes: *mut u64,
+    ) -> c_int;
+
+    // the path's only exchange step: one NCCL all-reduce of the K u64 counts (include/rcb200.h)
+    pub fn rcb_comm_unique_id(id: *mut u8) -> c_int;
+    pub fn rcb_comm_init_rank(ctx: *mut RcbCtx, id: *const u8, n_ranks: c_int, rank: c_int, out: *mut *mut RcbComm) -> c_int;
+    pub fn rcb_comm_init_all(ctxs: *const *mut RcbCtx, n_ctx: c_int, out: *mut *mut RcbComm) -> c_int;
+    pub fn rcb_comm_destroy(comm: *mut RcbComm) -> c_int;
+    pub fn rcb_comm_last_error(comm: *const RcbComm) -> *const c_char;
+    pub fn rcb_allreduce_counts(ctx: *mut RcbCtx, comm: *mut RcbComm, d_counts: *mut c_void, k: u32) -> c_int;
+    pub fn rcb_allreduce_counts_multi(
+        ctxs: *const *mut RcbCtx,
+        comms: *const *mut RcbComm,
+        d_counts: *const *mut c_void,
+        k: u32,
+        n_ctx: c_int,
     ) -> c_int;
 
     pub fn rcb_frame_bound(k: u32, n_chunks: u64, per_chunk: c_int, payload: u64) -> u64;

@@ -322,3 +322,107 @@ impl<'g> Decoder<'g> {
         sym[0] as usize
     }
 }
+
+/// A static table shared by chunks that live on several GPUs, one host thread driving all of them
+/// (`rcb_comm_init_all`).  GPU `g` owns the chunks `[n_chunks*g/G, n_chunks*(g+1)/G)`; the table is
+/// what the reference's caller builds with `add_alphabet_freq` over ALL the data + `calc_cum`
+/// (examples/sample_impl.rs:77-81): per-GPU histograms, ONE all-reduce of the K counts over NVLink,
+/// the same deterministic table on every GPU.  No payload byte crosses GPUs.
+pub struct MultiGpu {
+    gpus: Vec<Gpu>,
+    comms: Vec<*mut ffi::RcbComm>,
+}
+
+impl MultiGpu {
+    pub fn new(n_gpus: usize) -> Result<Self, GpuError> {
+        let gpus = (0..n_gpus).map(|g| Gpu::try_new(g as i32)).collect::<Result<Vec<_>, _>>()?;
+        let ctxs: Vec<*mut ffi::RcbCtx> = gpus.iter().map(|g| g.ctx).collect();
+        let mut comms = vec![std::ptr::null_mut(); n_gpus];
+        to_result(unsafe { ffi::rcb_comm_init_all(ctxs.as_ptr(), n_gpus as c_int, comms.as_mut_ptr()) })?;
+        Ok(MultiGpu { gpus, comms })
+    }
+
+    /// histogram (sharded) -> all-reduce -> table -> encode; the per-GPU streams concatenate in chunk order.
+    pub fn encode_chunks(&self, symbols: &[u8], k: u32, chunk_syms: u64) -> Result<Encoded, GpuError> {
+        let g_n = self.gpus.len() as u64;
+        let n = symbols.len() as u64;
+        let n_chunks = (n + chunk_syms - 1) / chunk_syms;
+        let first: Vec<u64> = (0..=g_n).map(|g| n.min(n_chunks * g / g_n * chunk_syms)).collect();
+        let mut d_syms = vec![std::ptr::null_mut::<c_void>(); g_n as usize];
+        let mut d_counts = vec![std::ptr::null_mut::<c_void>(); g_n as usize];
+        unsafe {
+            for (g, gpu) in self.gpus.iter().enumerate() {
+                let cnt = first[g + 1] - first[g];
+                to_result(ffi::rcb_device_alloc(gpu.ctx, cnt, &mut d_syms[g]))?;
+                to_result(ffi::rcb_device_alloc(gpu.ctx, k as u64 * 8, &mut d_counts[g]))?;
+                let src = symbols[first[g] as usize..].as_ptr() as *const c_void;
+                to_result(ffi::rcb_copy_to_device(gpu.ctx, d_syms[g], src, cnt))?;
+                to_result(ffi::rcb_histogram(gpu.ctx, d_syms[g], cnt, 1, k, 0, d_counts[g]))?;
+            }
+            let ctxs: Vec<*mut ffi::RcbCtx> = self.gpus.iter().map(|g| g.ctx).collect();
+            to_result(ffi::rcb_allreduce_counts_multi(
+                ctxs.as_ptr(),
+                self.comms.as_ptr(),
+                d_counts.as_ptr(),
+                k,
+                g_n as c_int,
+            ))?;
+            let mut enc = Encoded { stream: Vec::new(), offsets: vec![0u64], chunk_syms };
+            for (g, gpu) in self.gpus.iter().enumerate() {
+                let cnt = first[g + 1] - first[g];
+                let chunks = (cnt + chunk_syms - 1) / chunk_syms;
+                let mut m = std::ptr::null_mut();
+                to_result(ffi::rcb_model_create(gpu.ctx, k, 1, &mut m))?;
+                to_result(ffi::rcb_model_from_counts(gpu.ctx, m, d_counts[g], 8))?;
+                let cap = ffi::rcb_encode_bound(gpu.ctx, m, cnt, 1, chunk_syms) + 16;
+                let (mut d_out, mut d_off) = (std::ptr::null_mut::<c_void>(), std::ptr::null_mut::<c_void>());
+                to_result(ffi::rcb_device_alloc(gpu.ctx, cap, &mut d_out))?;
+                to_result(ffi::rcb_device_alloc(gpu.ctx, (chunks + 1) * 8, &mut d_off))?;
+                let mut bytes = 0u64;
+                to_result(ffi::rcb_encode_chunks(
+                    gpu.ctx,
+                    d_syms[g],
+                    cnt,
+                    1,
+                    chunk_syms,
+                    m,
+                    d_out as *mut u8,
+                    cap,
+                    d_off as *mut u64,
+                    std::ptr::null_mut(),
+                    &mut bytes,
+                ))?;
+                let base = enc.stream.len();
+                let k0 = enc.offsets.len() - 1;
+                enc.stream.resize(base + bytes as usize, 0);
+                enc.offsets.resize(k0 + chunks as usize + 1, 0);
+                to_result(ffi::rcb_copy_to_host(gpu.ctx, enc.stream[base..].as_mut_ptr() as *mut c_void, d_out, bytes))?;
+                to_result(ffi::rcb_copy_to_host(
+                    gpu.ctx,
+                    enc.offsets[k0..].as_mut_ptr() as *mut c_void,
+                    d_off,
+                    (chunks + 1) * 8,
+                ))?;
+                for o in &mut enc.offsets[k0..] {
+                    *o += base as u64; // local -> global offsets
+                }
+                ffi::rcb_device_free(gpu.ctx, d_out);
+                ffi::rcb_device_free(gpu.ctx, d_off);
+                ffi::rcb_device_free(gpu.ctx, d_syms[g]);
+                ffi::rcb_device_free(gpu.ctx, d_counts[g]);
+                ffi::rcb_model_destroy(m);
+            }
+            Ok(enc)
+        }
+    }
+}
+
+impl Drop for MultiGpu {
+    fn drop(&mut self) {
+        for &k in &self.comms {
+            unsafe {
+                ffi::rcb_comm_destroy(k);
+            }
+        }
+    }
+}

@@ -69,7 +69,7 @@ void build_header(uint32_t K, const uint32_t* c, const uint32_t* cum, uint32_t t
     for (uint32_t i = 0; i < K; i++) {
         uint64_t end = (uint64_t)cum[i] + c[i];
         if (end > total) bad |= 1;
-        if (i + 1 < K && (uint64_t)cum[i + 1] != end) bad |= 2;
+        if (i + 1 < K ? (uint64_t)cum[i + 1] != end : end != total) bad |= 2;
     }
     h.flags = (pow2 ? MODEL_POW2 : 0) | ((bad & 1) ? 0 : MODEL_CONSISTENT) | ((bad & 3) ? 0 : MODEL_REGULAR);
     uint32_t bits = 0;

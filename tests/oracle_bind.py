@@ -172,6 +172,69 @@ def decode_chunks(stream, offsets, n_syms, chunk_syms, c, cum, total, sym_bytes=
     return out, used
 
 
+def histogram_mt(syms, K, threads=None):
+    """The same histogram with the symbols cut into one slice per host thread (ctypes releases the GIL
+    during the C call); the u64 partial tables are summed.  Used by the timed CPU baselines so that the
+    histogram does not run single-threaded next to multi-threaded coding."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    syms = np.ascontiguousarray(syms)
+    threads = max(1, min(threads or hardware_threads(), (syms.size + (1 << 16) - 1) >> 16))
+    if threads == 1:
+        return histogram(syms, K)
+    cuts = [syms.size * t // threads for t in range(threads + 1)]
+    with ThreadPoolExecutor(threads) as ex:
+        parts = list(ex.map(lambda t: histogram(syms[cuts[t]:cuts[t + 1]], K), range(threads)))
+    return np.sum(parts, axis=0, dtype=np.uint64)
+
+
+class RoundTripBuffers:
+    """Preallocated staging / output arrays for repeated timed passes over the same batch shape: the
+    timed window then holds only the reference algorithm (histogram, table, encode, decode), no numpy
+    allocation or stream concatenation."""
+
+    def __init__(self, n_syms, chunk_syms, sym_bytes=1):
+        self.n, self.chunk, self.sb = n_syms, chunk_syms, sym_bytes
+        self.n_chunks = (n_syms + chunk_syms - 1) // chunk_syms
+        self.pitch = 4 * chunk_syms * sym_bytes + 64
+        self.staging = np.zeros(self.n_chunks * self.pitch, dtype=np.uint8)
+        self.lens = np.zeros(self.n_chunks, dtype=np.int64)
+        self.offsets = (np.arange(self.n_chunks + 1, dtype=np.uint64) * np.uint64(self.pitch))
+        self.back = np.zeros(n_syms, dtype=np.uint8 if sym_bytes == 1 else np.uint16)
+        self.used = np.zeros(self.n_chunks, dtype=np.int64)
+
+    def encode(self, syms, c, cum, total, threads):
+        c = np.ascontiguousarray(c, dtype=np.uint32)
+        cum = np.ascontiguousarray(cum, dtype=np.uint32)
+        total = np.ascontiguousarray(np.atleast_1d(total), dtype=np.uint32)
+        bad = lib().rco_encode_chunks(_p(syms), self.n, self.sb, self.chunk, c.shape[-1], _p(c), _p(cum), _p(total),
+                                      1 if c.ndim == 2 else 0, _p(self.staging), self.pitch, _p(self.lens), threads)
+        if bad:
+            raise ValueError(f"{bad} chunks failed")
+
+    def decode(self, c, cum, total, threads):
+        """Decodes every chunk from its staging row (row i starts at i * pitch; a chunk reads no byte
+        past its own length, so the row pitch serves as the offset table)."""
+        c = np.ascontiguousarray(c, dtype=np.uint32)
+        cum = np.ascontiguousarray(cum, dtype=np.uint32)
+        total = np.ascontiguousarray(np.atleast_1d(total), dtype=np.uint32)
+        bad = lib().rco_decode_chunks(_p(self.staging), _p(self.offsets), self.n, self.sb, self.chunk, c.shape[-1],
+                                      _p(c), _p(cum), _p(total), 1 if c.ndim == 2 else 0, _p(self.back),
+                                      _p(self.used), threads)
+        if bad:
+            raise ValueError(f"{bad} chunks failed")
+        return self.back
+
+    def stream(self):
+        """(stream, offsets) in the dense layout of encode_chunks (not timed)."""
+        offsets = np.zeros(self.n_chunks + 1, dtype=np.uint64)
+        offsets[1:] = np.cumsum(self.lens)
+        stream = np.empty(int(offsets[-1]), dtype=np.uint8)
+        for i in range(self.n_chunks):
+            stream[int(offsets[i]):int(offsets[i + 1])] = self.staging[i * self.pitch:i * self.pitch + int(self.lens[i])]
+        return stream, offsets
+
+
 def generate(n, K, seed, thresholds, sym_bytes=1, chunk_syms=0, first=0, threads=None):
     thr = np.ascontiguousarray(thresholds, dtype=np.uint32)
     if thr.ndim == 1:

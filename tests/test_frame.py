@@ -57,6 +57,44 @@ def test_frame_parse_accepts_checker_frame(oracle):
     assert lib.rcb_frame_parse(broken.ctypes.data_as(ctypes.c_void_p), broken.size, ctypes.byref(info)) != 0
 
 
+def test_frame_parse_rejects_crafted_headers(oracle):
+    """Untrusted frames: sizes that wrap u64 arithmetic (n_syms * sym_bytes == 0 mod 2^64), a chunk size
+    above the coder's limit, and a chunk shorter than the 8 bytes of Encoder::finish must not parse."""
+    import struct
+
+    from range_coder_rust_b200 import _lib
+    from range_coder_rust_b200.api import FrameInfo
+
+    lib = _lib.load()
+    info = FrameInfo()
+
+    def parse(fr):
+        return lib.rcb_frame_parse(fr.ctypes.data_as(ctypes.c_void_p), fr.size, ctypes.byref(info))
+
+    syms = _data(oracle, 4000, 256)
+    frame = frame_ref.write_frame(syms, 1000, [oracle.model_from_symbols(syms, 256)], 256)
+    assert parse(frame) == 0
+    good = FrameInfo.from_buffer_copy(bytes(info))
+    # header fields: chunk_syms @24, n_syms @32, n_chunks @40 (include/rcb200.h)
+    crafted = frame.copy()
+    crafted[8:12] = np.frombuffer(struct.pack("<I", 2), dtype=np.uint8)            # sym_bytes = 2
+    crafted[24:48] = np.frombuffer(struct.pack("<QQQ", 1 << 63, 1 << 63, 1), dtype=np.uint8)
+    assert parse(crafted) != 0
+    crafted = frame.copy()
+    crafted[24:48] = np.frombuffer(struct.pack("<QQQ", (1 << 30) + 1, 4000, 1), dtype=np.uint8)
+    assert parse(crafted) != 0
+    # a zero-length chunk / a chunk of 7 bytes
+    for delta in (0, 7):
+        broken = frame.copy()
+        offs = broken[good.offsets_off:good.offsets_off + 8 * 5].view("<u8")
+        offs[2] = offs[1] + delta
+        assert parse(broken) != 0
+    # offsets not starting at zero
+    broken = frame.copy()
+    broken[good.offsets_off:good.offsets_off + 8].view("<u8")[0] = 1
+    assert parse(broken) != 0
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("K,chunk,n", [(256, 4096, 10 * 4096 + 77), (256, 65536, 3 * 65536), (4096, 2048, 50000),
                                        (2, 100, 1001)])

@@ -207,7 +207,7 @@ def test_k4096_u16(ctx, oracle):
 
 
 # ----------------------------------------------- reciprocal path / odd tables
-@pytest.mark.parametrize("kind", ["prime_total", "u32_max", "gaps", "single", "irregular"])
+@pytest.mark.parametrize("kind", ["prime_total", "u32_max", "gaps", "single", "irregular", "slack_total"])
 def test_tables_from_host(ctx, oracle, kind):
     rng = np.random.default_rng(11)
     if kind == "prime_total":
@@ -227,19 +227,168 @@ def test_tables_from_host(ctx, oracle, kind):
     if kind == "irregular":
         cum = (cum + np.arange(64, dtype=np.uint32) * 3).astype(np.uint32)
         total = int(cum[-1] + c[-1] + 10)
+    if kind == "slack_total":
+        # proper prefix sums but unused code space ABOVE the last symbol (legal for a PModel): the
+        # kernels that derive c[K-1] as total - cum[K-1] must not be chosen for it
+        total = int(total + 11)  # odd: misses the power-of-two paths as well
     used = np.flatnonzero(c)
     n, chunk = 200_000, 8192
     p = c[used].astype(np.float64)
     syms = rng.choice(used, size=n, p=p / p.sum()).astype(np.uint8)
     model = ctx.model_from_tables(c, cum, total)
     _, _, _, flags = model.tables()
-    assert bool(flags & 4) == (kind != "irregular")  # RCB_MODEL_REGULAR
+    assert bool(flags & 4) == (kind not in ("irregular", "slack_total"))  # RCB_MODEL_REGULAR
     d_syms = to_dev(ctx, syms)
     stream, offsets, nbytes = ctx.encode_chunks(d_syms, chunk, model)
     ref_stream, ref_offsets = oracle.encode_chunks(syms, chunk, c, cum, total)
     assert_streams_equal(stream, offsets, nbytes, ref_stream, ref_offsets)
     out = ctx.decode_chunks(stream, offsets, n, chunk, model)
     assert np.array_equal(dev_to_np(out), syms)
+
+
+def test_slack_total_per_chunk_models(ctx, oracle):
+    """Per-chunk tables whose last symbol does not end at total_freq (and the last symbol is coded a
+    lot): bytes must match the oracle and decode must return the symbols, through the chunk API."""
+    rng = np.random.default_rng(5)
+    n_chunks, K, chunk = 40, 32, 3000
+    c = rng.integers(1, 500, size=(n_chunks, K)).astype(np.uint32)
+    cum = np.zeros_like(c)
+    total = np.zeros(n_chunks, dtype=np.uint32)
+    for j in range(n_chunks):
+        cum[j], t = oracle.calc_cum(c[j])
+        total[j] = t + 7 + 2 * j  # slack above the last symbol
+    syms = rng.integers(0, K, size=n_chunks * chunk).astype(np.uint8)
+    syms[::3] = K - 1
+    model = ctx.model_from_tables(c, cum, total)
+    for j in (0, n_chunks - 1):
+        assert not (model.tables(j)[3] & 4)  # not RCB_MODEL_REGULAR
+    d = to_dev(ctx, syms)
+    stream, offsets, nbytes = ctx.encode_chunks(d, chunk, model)
+    ref_stream, ref_offsets = oracle.encode_chunks(syms, chunk, c, cum, total)
+    assert_streams_equal(stream, offsets, nbytes, ref_stream, ref_offsets)
+    out = ctx.decode_chunks(stream, offsets, syms.size, chunk, model)
+    assert np.array_equal(dev_to_np(out), syms)
+    # the container stores per-chunk c only (total = sum c): such a model cannot be framed
+    import range_coder_rust_b200 as rcb
+    with pytest.raises(rcb.RcbError):
+        ctx.frame_encode(syms, chunk, model)
+
+
+def test_kat2_empty_encoder_run(ctx, oracle):
+    """SURVEY KAT-2: an Encoder that saw no symbol finishes to eight zero bytes (src/encoder.rs:40-46),
+    and a Decoder built on them decodes zero symbols having consumed exactly those 8 bytes
+    (src/decoder.rs:14-23)."""
+    import ctypes
+
+    from test_gpu_stream_api import StreamState, _p
+
+    lib = ctx.lib
+    st = StreamState()
+    lib.rcb_stream_state_init(ctypes.byref(st))
+    out = np.full(16, 0xAA, dtype=np.uint8)
+    n_out = ctypes.c_uint64()
+    rc = lib.rcb_encode_stream(ctx.h, ctypes.byref(st), None, 0, 1, None, _p(out), out.size, ctypes.byref(n_out),
+                               None, 1)
+    assert rc == 0 and n_out.value == 8
+    assert out[:8].tobytes() == bytes(8) == oracle.encode(np.zeros(0, np.uint8), [1], [0], 1)
+    assert out[8] == 0xAA
+    model = ctx.model_from_tables(np.array([1, 5, 2], np.uint32), np.array([0, 1, 6], np.uint32), 8)
+    st = StreamState()
+    lib.rcb_stream_state_init(ctypes.byref(st))
+    code = out[:8].copy()
+    rc = lib.rcb_decode_stream(ctx.h, ctypes.byref(st), _p(code), 8, 0, 1, model.h, None)
+    assert rc == 0 and st.consumed == 8 and st.data == 0 and st.lower_bound == 0
+    # the same run through the chunk API: one chunk whose only content is the flush
+    one = np.zeros(1, dtype=np.uint8)
+    m1 = ctx.model_from_tables(np.array([7], np.uint32), np.array([0], np.uint32), 7)
+    stream, offsets, nbytes = ctx.encode_chunks(to_dev(ctx, one), 1, m1)
+    assert dev_to_np(stream, nbytes).tobytes() == oracle.encode(one, [7], [0], 7)
+
+
+def test_corrupt_offsets_are_contained(ctx, oracle):
+    """Offsets are caller data (a damaged index, a crafted frame): a chunk shorter than the 8 bytes
+    Decoder::new pops, offsets beyond the stream or running backwards must end in a status, never in
+    a fault, and the context must stay usable -- through every decode kernel family."""
+    import range_coder_rust_b200 as rcb
+    from range_coder_rust_b200 import _lib
+
+    chunk, n = 4096, 40 * 4096
+    for kind in ("static_pow2", "static_odd", "adaptive"):
+        syms = oracle.generate(n, 256, 0x5EED0001, oracle.zipf_thresholds(256, 1.1))
+        d = to_dev(ctx, syms)
+        if kind == "adaptive":
+            model = ctx.model_from_counts(ctx.histogram(d, 256, chunk_syms=chunk))
+        else:
+            counts = ctx.histogram(d, 256)
+            if kind == "static_odd":
+                counts[0] += 999
+            model = ctx.model_from_counts(counts)
+        stream, offsets, nbytes = ctx.encode_chunks(d, chunk, model)
+        good = dev_to_np(offsets).copy()
+        tight = stream[:(nbytes + 15) // 16 * 16].clone()  # nothing readable past the padded end
+        status = torch.zeros(40, dtype=torch.int32, device=ctx.device)
+        cases = []
+        o = good.copy(); o[7] = o[8]; cases.append((o, [7]))                      # empty chunk
+        o = good.copy(); o[7] = o[8] - 5; cases.append((o, [7]))                  # 5-byte chunk
+        o = good.copy(); o[20] = nbytes + (1 << 40); cases.append((o, [19, 20]))  # far beyond the stream
+        o = good.copy(); o[30] = 0; cases.append((o, [29]))                       # runs backwards
+        o = good.copy(); o[:] = nbytes; cases.append((o, list(range(40))))        # every chunk empty, at the end
+        for offs, bad in cases:
+            with pytest.raises(rcb.RcbError) as e:
+                ctx.decode_chunks(tight, to_dev(ctx, offs), n, chunk, model, status=status)
+            assert e.value.code == _lib.RCB_ERR_TRUNCATED_STREAM
+            st = status.cpu().numpy()
+            assert all(st[b] == 6 for b in bad), (kind, st)
+        back = ctx.decode_chunks(stream, offsets, n, chunk, model)
+        assert np.array_equal(dev_to_np(back), syms)
+    # the host entry point refuses non-monotone offsets before sizing any copy with them
+    h_stream = np.zeros((nbytes + 31) // 16 * 16, dtype=np.uint8)
+    h_stream[:nbytes] = dev_to_np(stream, nbytes)
+    o = good.astype(np.uint64).copy()
+    o[5] = o[6] + 1
+    with pytest.raises(rcb.RcbError) as e:
+        ctx.decode_host(h_stream, o, n, chunk, model)
+    assert e.value.code == _lib.RCB_ERR_INVALID_ARGUMENT
+
+
+def test_config5_shard_on_one_gpu(ctx, oracle):
+    """BASELINE.json configs[4] as one of its eight ranks sees it: an 8 GiB shard of the 64 GiB stream
+    generated at first = 3 * n (rank 3's symbols), the all-reduced count table (sum 2^36 > u32, so the
+    2^31 rescale of DESIGN.md fires) stood in for by 8 x the local counts, encode + decode of all
+    131072 chunks, and >= 1 % of the chunks (every 64th: 2048 chunks) byte-compared with the oracle."""
+    free, _ = torch.cuda.mem_get_info(ctx.device)
+    if free < 30 << 30:
+        pytest.skip("needs ~24 GiB of free device memory")
+    n, chunk, rank = 8 << 30, 65536, 3
+    thr = oracle.zipf_thresholds(256, 1.1)
+    d_syms = ctx.generate(n, 256, 0x5EED0001, thr, first=rank * n)
+    counts = ctx.histogram(d_syms, 256)
+    assert int(counts.sum().item()) == n
+    counts *= 8  # what the all-reduce over 8 statistically identical shards delivers: sum = 2^36
+    model = ctx.model_from_counts(counts)
+    c, cum, total, flags = model.tables()
+    rc, scaled = oracle.normalise(dev_to_np(counts).astype(np.uint64))
+    rcum, rtotal = oracle.calc_cum(rc)
+    assert scaled == 1 and total == rtotal == 1 << 31 and np.array_equal(c, rc) and np.array_equal(cum, rcum)
+    stream, offsets, nbytes = ctx.encode_chunks(d_syms, chunk, model)
+    assert 0.70 < nbytes / n < 0.74
+    out = ctx.decode_chunks(stream, offsets, n, chunk, model)
+    assert torch.equal(out, d_syms)
+    del out
+    offs = dev_to_np(offsets).astype(np.uint64)
+    n_chunks = n // chunk
+    picked = np.arange(5, n_chunks, 64)
+    assert picked.size >= n_chunks // 100
+    # the oracle generates the same symbols from the global index (no device->host copy of the input)
+    for i in picked[:: max(1, picked.size // 16)]:
+        ref_syms = oracle.generate(chunk, 256, 0x5EED0001, thr, first=rank * n + int(i) * chunk)
+        assert np.array_equal(dev_to_np(d_syms[int(i) * chunk:(int(i) + 1) * chunk]), ref_syms)
+    idx = torch.from_numpy(picked).to(ctx.device)
+    sample = d_syms.view(n_chunks, chunk)[idx].reshape(-1).cpu().numpy()
+    ref_stream, ref_offsets = oracle.encode_chunks(sample, chunk, rc, rcum, rtotal)
+    for k, i in enumerate(picked):
+        got = dev_to_np(stream[int(offs[i]):int(offs[i + 1])])
+        assert np.array_equal(got, ref_stream[int(ref_offsets[k]):int(ref_offsets[k + 1])]), f"chunk {i}"
 
 
 def test_count_normalisation_above_u32(ctx, oracle):
@@ -464,3 +613,62 @@ def test_full_size_round_trip_and_sampled_parity(ctx, oracle):
         ref = oracle.encode(s, c, cum, total)
         got = dev_to_np(stream[int(offs[i]):int(offs[i + 1])]).tobytes()
         assert got == ref, f"chunk {i} differs from the oracle"
+
+
+# ------------------------------------------------- multi-GPU exchange step (C ABI)
+def test_comm_single_rank_allreduce(ctx, oracle):
+    """rcb_comm_* / rcb_allreduce_counts with a one-rank communicator: NCCL is found at run time, the
+    call is issued on the context's stream, and a sum over one rank leaves the counts unchanged --
+    the model built after it is the single-GPU model."""
+    import range_coder_rust_b200 as rcb
+
+    syms = oracle.generate(1 << 20, 256, 0x5EED0001, oracle.zipf_thresholds(256, 1.1))
+    d = to_dev(ctx, syms)
+    counts = ctx.histogram(d, 256)
+    before = counts.clone()
+    comm = ctx.comm_init_rank(rcb.Comm.unique_id(), 1, 0)
+    assert comm.nccl_version >= 21800
+    n0 = ctx.launch_count
+    ctx.allreduce_counts(counts, comm)
+    model = ctx.model_from_counts(counts)  # same stream: ordered after the all-reduce
+    assert ctx.launch_count > n0
+    assert torch.equal(counts, before)
+    c, cum, total, _ = model.tables()
+    rc, rcum, rtotal = oracle.model_from_symbols(syms, 256)
+    assert total == rtotal and np.array_equal(c, rc) and np.array_equal(cum, rcum)
+    comm.close()
+
+
+def test_comm_two_gpus_share_one_table(oracle):
+    """Two GPUs driven by one thread (rcb_comm_init_all + rcb_allreduce_counts_multi): each codes its
+    own half of the chunks under the table built from the summed counts; both tables equal the
+    oracle's table of the whole stream and the concatenated streams equal the oracle's stream."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import range_coder_rust_b200 as rcb
+
+    n, chunk, K = 64 * 65536, 65536, 256
+    thr = oracle.zipf_thresholds(K, 1.1)
+    whole = oracle.generate(n, K, 0x5EED0001, thr)
+    ctxs = [rcb.Context(i) for i in range(2)]
+    comms = rcb.Context.comm_init_all(ctxs)
+    half = n // 2
+    shards = [ctxs[i].generate(half, K, 0x5EED0001, thr, first=i * half) for i in range(2)]
+    counts = [ctxs[i].histogram(shards[i], K) for i in range(2)]
+    rcb.Context.allreduce_counts_multi(ctxs, comms, counts)
+    rc, rcum, rtotal = oracle.model_from_symbols(whole, K)
+    ref_stream, ref_offsets = oracle.encode_chunks(whole, chunk, rc, rcum, rtotal)
+    parts = []
+    for i in range(2):
+        model = ctxs[i].model_from_counts(counts[i])
+        c, cum, total, _ = model.tables()
+        assert total == rtotal and np.array_equal(c, rc) and np.array_equal(cum, rcum)
+        stream, offsets, nbytes = ctxs[i].encode_chunks(shards[i], chunk, model)
+        parts.append(stream[:nbytes].cpu().numpy())
+        back = ctxs[i].decode_chunks(stream, offsets, half, chunk, model)
+        assert torch.equal(back, shards[i])
+    assert np.array_equal(np.concatenate(parts), ref_stream)
+    for k in comms:
+        k.close()
+    for c in ctxs:
+        c.close()

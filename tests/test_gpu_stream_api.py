@@ -38,6 +38,15 @@ def test_cpp_sample_impl_example():
     assert "test passed" in res.stdout
 
 
+def test_cpp_multi_gpu_example():
+    """examples/multi_gpu.cpp: gpu::MultiGpu (rcb_comm_init_all + rcb_allreduce_counts_multi behind the
+    C++ mirror) on every visible GPU -- one is enough to run the whole code path."""
+    subprocess.run(["make", "-C", os.path.join(ROOT, "examples")], check=True, capture_output=True)
+    res = subprocess.run([os.path.join(ROOT, "examples", "multi_gpu")], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "test passed" in res.stdout and "==" in res.stdout
+
+
 def test_encoder_decoder_symbol_by_symbol(ctx, oracle):
     """Encoder::encode returns the bytes each symbol produced; the concatenation + finish() equals
     the oracle's Encoder run; Decoder::decode returns the symbols one at a time."""
