@@ -49,7 +49,7 @@ def parse_args():
     p.add_argument("--mode", default="static", choices=["static", "adaptive"],
                    help="static: one global table (all-reduced counts); adaptive: one table per chunk, mixed entropy")
     p.add_argument("--seed", type=lambda s: int(s, 0), default=None)
-    p.add_argument("--e2e-steps", type=int, default=2)
+    p.add_argument("--e2e-steps", type=int, default=6)
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-parity", action="store_true")
@@ -507,20 +507,64 @@ def run_ours(a):
         if sym_bytes == 2:
             a_syms, a_back = a_syms.view(np.uint16), a_back.view(np.uint16)
 
-        def e2e_step():
-            _, offs, nb = ctx.encode_host(a_syms, chunk, model, out_np=a_stream)
-            ctx.decode_host(a_stream[:nb], offs, n_syms, chunk, model, sym_bytes=sym_bytes, out_np=a_back)
-            return nb, offs
+        # Two contexts on this GPU, one host thread each ("one ctx per GPU per thread", include/rcb200.h):
+        # the encode of batch i+1 runs while batch i is decoded, so both directions of the link carry
+        # data at the same time (one call alone is dominated by one direction).  Every step still copies
+        # its input host->device and its results device->host inside the timed region; a step's decode
+        # starts when its own encode has returned (it needs that call's offsets and byte count).
+        import queue
+        import threading as th_
 
-        e2e_step()  # warm-up: sizes the device scratch
+        ctx2 = rcb.Context(local_rank, stream=torch.cuda.Stream(dev))
+        c_, cum_, total_, _f = (counts, None, None, None) if adaptive else model.tables()
+        if adaptive:
+            model2 = ctx2.model_from_counts(counts)
+        else:
+            model2 = ctx2.model_from_tables(c_, cum_, total_)
+        # double-buffered code streams: batch i's stream is read by the decoder while batch i+1 is encoded
+        h_stream2 = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+        streams = (a_stream, h_stream2.numpy())
+        result = {}
+
+        def run_steps(k_steps):
+            q = queue.Queue()
+            free = th_.Semaphore(2)  # a code-stream buffer is free again when its batch has been decoded
+
+            def decoder():
+                with torch.cuda.device(dev):
+                    while True:
+                        item = q.get()
+                        if item is None:
+                            return
+                        buf, offs, nb = item
+                        ctx2.decode_host(buf[:nb], offs, n_syms, chunk, model2, sym_bytes=sym_bytes, out_np=a_back)
+                        result["nb"], result["offs"] = nb, offs
+                        free.release()
+
+            t = th_.Thread(target=decoder)
+            t.start()
+            for i in range(k_steps):
+                free.acquire()
+                buf, offs, nb = ctx.encode_host(a_syms, chunk, model, out_np=streams[i & 1])
+                q.put((buf, offs, nb))
+            q.put(None)
+            t.join()
+
+        run_steps(2)  # warm-up: sizes the device scratch of both contexts
         barrier()
         t0 = time.perf_counter()
-        for _ in range(a.e2e_steps):
-            nb, offs = e2e_step()
+        run_steps(a.e2e_steps)
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - t0)
         barrier()
+        nb, offs = result["nb"], result["offs"]
         assert np.array_equal(a_back, a_syms)
+        # the same two calls back to back on one context (no overlap between steps), for reference
+        t1 = time.perf_counter()
+        _, offs1, nb1 = ctx.encode_host(a_syms, chunk, model, out_np=a_stream)
+        ctx.decode_host(a_stream[:nb1], offs1, n_syms, chunk, model, sym_bytes=sym_bytes, out_np=a_back)
+        dt_serial = max_over_ranks(time.perf_counter() - t1)
+        barrier()
         off_bytes = (n_chunks + 1) * 8
         # the bus ceiling on this box, every rank copying at once (aggregate over ranks)
         h2d, d2h, duplex = measure_bus(torch, dev, barrier)
@@ -533,12 +577,17 @@ def run_ours(a):
                "d2h_bytes_per_step": int(world * (nb + off_bytes + n)),
                "bytes_are": "aggregate over all ranks, like `value`",
                "steps": a.e2e_steps, "ms_per_step": dt / a.e2e_steps * 1e3,
+               "serial_ms_per_step": dt_serial * 1e3, "serial_value": world * n / dt_serial / 1e9,
+               "pipelining": "encode of step i+1 overlaps decode of step i (two contexts, two host threads); "
+                             "serial_* = the two calls back to back on one context",
                "bus": bus, "bus_gbs": moved * a.e2e_steps / dt / 1e9,
                "bus_frac": moved * a.e2e_steps / dt / 1e9 / bus["duplex_gbs"],
                "api": "rcb_encode_host + rcb_decode_host (C ABI, pinned host buffers)"}
         if old_affinity:
             os.sched_setaffinity(0, old_affinity)
-        del h_syms, h_stream, h_back
+        model2.close()
+        ctx2.close()
+        del h_syms, h_stream, h_back, h_stream2
 
     # ---- parity on EVERY rank at every N: a deterministic >= 1 % subset of this rank's chunks (every 64th,
     # starting at 5) re-encoded by the oracle under this rank's table and compared byte for byte
