@@ -76,6 +76,8 @@ struct rcb_model {
     uint32_t* d_total = nullptr;
     ModelHdr* d_hdr = nullptr;
     LutEntry* d_lut = nullptr;
+    uint2* d_tab_cs = nullptr;  // shared model: floor(c * 2^64 / total) per symbol
+    uint4* d_lut_cs = nullptr;  // ... and per LUT entry (both candidates)
     ModelHdr h_hdr0;       // header of model 0 (the shared model)
     uint32_t min_c = 0;    // smallest non-zero c over all models
     uint32_t max_total = 0;
@@ -387,7 +389,10 @@ extern "C" int rcb_model_create(rcb_ctx* c, uint32_t K, uint64_t n_models, rcb_m
     bool ok = cudaMalloc(&m->d_tab, n_models * K * sizeof(uint2)) == cudaSuccess &&
               cudaMalloc(&m->d_total, n_models * sizeof(uint32_t)) == cudaSuccess &&
               cudaMalloc(&m->d_hdr, n_models * sizeof(ModelHdr)) == cudaSuccess;
-    if (ok && n_models == 1) ok = cudaMalloc(&m->d_lut, LUT_CAP * sizeof(LutEntry)) == cudaSuccess;
+    if (ok && n_models == 1)
+        ok = cudaMalloc(&m->d_lut, LUT_CAP * sizeof(LutEntry)) == cudaSuccess &&
+             cudaMalloc(&m->d_tab_cs, (size_t)K * sizeof(uint2)) == cudaSuccess &&
+             cudaMalloc(&m->d_lut_cs, LUT_CAP * sizeof(uint4)) == cudaSuccess;
     if (!ok) {
         c->last_err = cudaGetLastError();
         rcb_model_destroy(m);
@@ -405,6 +410,8 @@ extern "C" int rcb_model_destroy(rcb_model* m) {
     cudaFree(m->d_total);
     cudaFree(m->d_hdr);
     cudaFree(m->d_lut);
+    cudaFree(m->d_tab_cs);
+    cudaFree(m->d_lut_cs);
     delete m;
     return RCB_OK;
 }
@@ -484,7 +491,8 @@ static int finalize_model(rcb_ctx* c, rcb_model* m) {
     CK(c, cudaMemcpyAsync(c->d_words + 3, c->h_words + 7, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     if (m->n_models > 0x7FFFFFFFull) return RCB_ERR_UNSUPPORTED;
     finalize_models_kernel<<<(unsigned)m->n_models, 256, 0, c->stream>>>(
-        m->d_tab, m->d_total, m->K, m->d_hdr, m->n_models == 1 ? m->d_lut : nullptr, LUT_CAP, c->d_words);
+        m->d_tab, m->d_total, m->K, m->d_hdr, m->n_models == 1 ? m->d_lut : nullptr, LUT_CAP,
+        m->n_models == 1 ? m->d_tab_cs : nullptr, m->n_models == 1 ? m->d_lut_cs : nullptr, c->d_words);
     CK_LAUNCH(c);
     CK(c, cudaMemcpyAsync(c->h_words, c->d_words, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaMemcpyAsync(&m->h_hdr0, m->d_hdr, sizeof(ModelHdr), cudaMemcpyDeviceToHost, c->stream));
@@ -604,9 +612,12 @@ static EncPlan plan_encode(const rcb_ctx* c, const rcb_model* m, uint64_t n_chun
     if (shared) {
         p.table = TAB_SHARED;
         const bool pow2 = (m->h_hdr0.flags & MODEL_POW2) != 0;
-        p.fmode = p.checked ? FM_GENERIC : (pow2 ? (m->h_hdr0.div.shift >= 24 ? FM_BIG : FM_POW2) : FM_GEN);
+        // general totals: the divide-free step needs cs = floor(c * 2^64 / total) < 2^64, i.e. no c == total
+        const bool gencs = !pow2 && !(m->h_hdr0.flags & MODEL_FULLC) && !getenv("RCB_NO_GENCS");
+        p.fmode = p.checked ? FM_GENERIC
+                            : (pow2 ? (m->h_hdr0.div.shift >= 24 ? FM_BIG : FM_POW2) : (gencs ? FM_GENCS : FM_GEN));
         p.lanes = (uint32_t)p.threads;
-        p.smem = (((size_t)m->K * sizeof(uint2) + 15) & ~(size_t)15);
+        p.smem = (((size_t)m->K * (p.fmode == FM_GENCS ? sizeof(uint4) : sizeof(uint2)) + 15) & ~(size_t)15);
         if (p.fmode != FM_GENERIC) p.smem += (size_t)p.threads * ENC_RING_STRIDE;  // per-lane input rings
         return p;
     }
@@ -654,6 +665,7 @@ static void launch_encode_variant(rcb_ctx* c, const rcb_model* m, const EncodeAr
             case FM_BIG: launch_encode_rc<SYM, TAB_SHARED, FM_BIG, false>(c, a, p, blocks, rangechk); break;
             case FM_POW2: launch_encode_rc<SYM, TAB_SHARED, FM_POW2, false>(c, a, p, blocks, rangechk); break;
             case FM_GEN: launch_encode_rc<SYM, TAB_SHARED, FM_GEN, false>(c, a, p, blocks, rangechk); break;
+            case FM_GENCS: launch_encode_rc<SYM, TAB_SHARED, FM_GENCS, false>(c, a, p, blocks, rangechk); break;
             default: launch_encode_rc<SYM, TAB_SHARED, FM_GENERIC, true>(c, a, p, blocks, rangechk); break;
         }
     } else if (p.table == TAB_LANE) {
@@ -680,6 +692,7 @@ static int encode_issue(rcb_ctx* c, const void* d_syms, uint64_t n_syms, int sym
     a.n_chunks = n_chunks;
     a.tabs = shared ? m->d_tab : m->d_tab + model_first * m->K;
     a.hdrs = shared ? m->d_hdr : m->d_hdr + model_first;
+    a.tab_cs = m->d_tab_cs;
     a.K = m->K;
     a.staging = staging;
     a.pitch = pitch;
@@ -824,13 +837,20 @@ static DecPlan plan_decode(const rcb_ctx* c, const rcb_model* m, uint64_t n_chun
         const uint32_t shift = m->h_hdr0.div.shift;
         const uint64_t total = m->h_hdr0.div.total;
         if (!p.checked && regular) {
-            // fat LUT (two candidates per 1/4096 of the range): only when no bucket can hold two boundaries
-            const bool fat_ok = p.pow2 && shift >= 24 && (uint64_t)m->min_c >= (total >> 12) + (total >> 15) + 1;
+            // fat LUT (two candidates per bucket of 2^wshift, <= 4096 buckets): only when no bucket can hold
+            // two boundaries, i.e. every frequency >= one bucket + the 1/8 estimate margin.  Any total: a power
+            // of two >= 2^24 folds the division into the renormalisation shift (FM_BIG), smaller powers of two
+            // take two shifts (FM_POW2), everything else the divide-free step (FM_GEN here = FUSE_GEN with cs).
+            const uint64_t bucket = 1ull << m->h_hdr0.wshift;
+            bool fat_ok = total >= 2 && (uint64_t)m->min_c >= bucket + (bucket >> 3) + 1 && !getenv("RCB_NO_FAT");
+            if (!p.pow2 && ((m->h_hdr0.flags & MODEL_FULLC) || getenv("RCB_NO_GENCS"))) fat_ok = false;
             if (fat_ok) {
                 p.kind = 0;
-                p.fmode = FM_BIG;
+                p.fmode = p.pow2 ? (shift >= 24 ? FM_BIG : FM_POW2) : FM_GEN;
                 // FUSED kernel: candidates (16 bytes) + reciprocals of their frequencies (8 bytes) per bucket
-                const size_t fixed = (size_t)LUT_CAP * (sizeof(LutEntry) + 8) + (size_t)m->K * sizeof(uint2);
+                // (+ their 64-bit reciprocal constants, 16 bytes, for general totals)
+                const size_t fixed = (size_t)LUT_CAP * (sizeof(LutEntry) + 8 + (p.fmode == FM_GEN ? 16 : 0)) +
+                                     (size_t)m->K * sizeof(uint2);
                 while (p.threads > 32 && (size_t)p.threads * RING_STRIDE + fixed > budget) p.threads >>= 1;
                 p.lanes = (uint32_t)p.threads;
                 p.smem = (size_t)p.threads * RING_STRIDE + fixed;
@@ -894,17 +914,19 @@ static void launch_decode_variant(rcb_ctx* c, const rcb_model* m, const DecodeAr
     };
     (void)m;
     if (p.table == TAB_SHARED) {
-        if (p.fmode == FM_BIG) go(decode_kernel<SYM, true, true, false, true>);
+        if (p.fmode == FM_BIG) go(decode_kernel<SYM, true, true, false, FUSE_BIG>);
+        else if (p.fmode == FM_POW2) go(decode_kernel<SYM, true, true, false, FUSE_POW2>);
+        else if (p.fmode == FM_GEN) go(decode_kernel<SYM, true, false, false, FUSE_GEN>);
         else if (p.pow2) {
-            if (p.checked) go(decode_kernel<SYM, true, true, true, false>);
-            else go(decode_kernel<SYM, true, true, false, false>);
+            if (p.checked) go(decode_kernel<SYM, true, true, true, -1>);
+            else go(decode_kernel<SYM, true, true, false, -1>);
         } else {
-            if (p.checked) go(decode_kernel<SYM, true, false, true, false>);
-            else go(decode_kernel<SYM, true, false, false, false>);
+            if (p.checked) go(decode_kernel<SYM, true, false, true, -1>);
+            else go(decode_kernel<SYM, true, false, false, -1>);
         }
     } else {
-        if (p.checked) go(decode_kernel<SYM, false, false, true, false>);
-        else go(decode_kernel<SYM, false, false, false, false>);
+        if (p.checked) go(decode_kernel<SYM, false, false, true, -1>);
+        else go(decode_kernel<SYM, false, false, false, -1>);
     }
 }
 
@@ -945,6 +967,7 @@ static int decode_issue(rcb_ctx* c, const uint8_t* d_stream, const uint64_t* d_o
     a.tabs = shared ? m->d_tab : m->d_tab + model_first * m->K;
     a.hdrs = shared ? m->d_hdr : m->d_hdr + model_first;
     a.lut = m->d_lut;
+    a.lut_cs = m->d_lut_cs;
     a.K = m->K;
     a.per_chunk = !shared;
     a.out = d_syms_out;

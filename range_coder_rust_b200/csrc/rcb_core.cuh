@@ -360,6 +360,53 @@ RCB_HD bool fused_step(uint64_t lo, uint64_t rpt, uint32_t cum, uint32_t c, cons
 }
 
 // ---------------------------------------------------------------------------
+// FUSE_GEN without a divide on the dependency chain.  The fused general-total step needs
+//   rpt_next = floor((range' << sh) / total),   range' = rpt * c      (src/range_coder.rs:62,65)
+// and a 64-bit divide by a run-time constant costs ~60 cycles of latency after range' and sh are known
+// (shift, multiply-high by the reciprocal, remainder fix-up) -- 2/3 of the whole fused step.  Instead each
+// symbol carries cs = floor(c * 2^64 / total) (c < total), so that with Y = rpt << sh (< 2^64 because
+// Y * c = range' << sh):
+//   Y * c / total = Y * cs / 2^64 + Y * delta / 2^64,   0 <= delta < 1
+//   q' = floor(Y * cs / 2^64) = bits [64-sh, 128-sh) of the 128-bit product rpt * cs
+// The product starts from rpt alone (it runs beside the lower/upper multiply-adds) and sh only enters
+// in a final funnel shift.  q' is the exact quotient unless frac(Y * cs / 2^64) + Y / 2^64 reaches 1:
+// with G the top 32 bits of that fraction and hy = hi32(Y) a sufficient test is G + hy + 2 <= 2^32 --
+// it fails for ~2^-30 of the symbols of a real table; those take the exact path (word re-code), so the
+// result never depends on the approximation.
+// ---------------------------------------------------------------------------
+RCB_HD uint64_t recip_of_freq(uint32_t c, uint32_t total) {  // floor(c * 2^64 / total), c < total
+    return (uint64_t)((((unsigned __int128)c) << 64) / total);
+}
+
+RCB_HD bool fused_rpt_cs(uint64_t rpt, uint64_t cs, uint32_t sh, uint64_t& nrpt) {
+    const uint32_t rl = lo32(rpt), rh = hi32(rpt), cl = lo32(cs), ch = hi32(cs);
+    const uint64_t p0 = (uint64_t)rl * cl;
+    const uint64_t t1 = (uint64_t)rl * ch + hi32(p0);
+    const uint64_t t2 = (uint64_t)rh * cl + lo32(t1);
+    const uint64_t ph = (uint64_t)rh * ch + hi32(t1) + hi32(t2);  // bits 64..127 of rpt * cs
+    const uint32_t pm = lo32(t2), pl = lo32(p0);                   // bits 32..63, 0..31
+    const uint32_t q_lo = funnel_l(pm, lo32(ph), sh), q_hi = funnel_l(lo32(ph), hi32(ph), sh);
+    nrpt = ((uint64_t)q_hi << 32) | q_lo;
+    const uint32_t G = funnel_l(pl, pm, sh);   // top 32 bits of frac((rpt << sh) * cs / 2^64)
+    const uint32_t hy = funnel_l(rl, rh, sh);  // hi32(rpt << sh)
+    return (uint64_t)G + hy <= 0xFFFFFFFEull;
+}
+
+// fused_step with the divide-free rpt_next (encoder, FUSE_GEN tables that carry cs)
+RCB_HD bool fused_step_cs(uint64_t lo, uint64_t rpt, uint32_t cum, uint32_t c, uint64_t cs,
+                          uint64_t& nlo, uint64_t& rgp, uint64_t& nrpt, uint32_t& sh) {
+    nlo = mad64x32(rpt, cum, lo);
+    const uint64_t up = mad64x32(rpt, cum + c, lo);
+    rgp = mad64x32(rpt, c, 0ull);
+    const uint32_t xh = hi32(nlo) ^ hi32(up);
+    const bool p1 = xh < (1u << 24), p2 = xh < (1u << 16), p3 = xh < (1u << 8);
+    sh = p2 ? (p3 ? 24u : 16u) : (p1 ? 8u : 0u);
+    const bool exact = fused_rpt_cs(rpt, cs, sh, nrpt);
+    const uint32_t need = p2 ? 1u : (p1 ? (1u << 8) : (1u << 16));  // see fused_step
+    return exact & (hi32(rgp) >= need);
+}
+
+// ---------------------------------------------------------------------------
 // Decoder input window (src/decoder.rs:9,31-35).  (dh:dl) is `data`, aligned
 // with lower_bound; (wh:wl) holds the following bytes left-aligned with `cnt`
 // valid bits, refilled 32 bits at a time from Fetch (peek_be32(): the next
@@ -463,7 +510,8 @@ struct ModelHdr {
     uint32_t pad0, pad1;
 };
 
-enum : uint32_t { MODEL_POW2 = 1, MODEL_CONSISTENT = 2, MODEL_REGULAR = 4 };
+// MODEL_FULLC (internal): some symbol has c == total, for which floor(c * 2^64 / total) does not fit 64 bits
+enum : uint32_t { MODEL_POW2 = 1, MODEL_CONSISTENT = 2, MODEL_REGULAR = 4, MODEL_FULLC = 8 };
 
 RCB_HD float fast_rcp(float x) {
 #if defined(__CUDA_ARCH__)
@@ -526,6 +574,8 @@ RCB_HD float u64_to_float(uint64_t x) {
 #endif
 }
 RCB_HD uint32_t fused_sr(const FusedParams& fp) { return fp.s < 32u ? 32u - fp.s : 0u; }
+// general totals: the estimate uses the whole rpt (no pre-shift), so rc carries no 2^-sr
+RCB_HD float lut_q_gen(uint64_t rpt) { return fast_rcp(u64_to_float(rpt)); }
 RCB_HD float lut_rc16(uint32_t c, float lut_scale, uint32_t sr) {
     return c ? (16.0f * lut_scale / (float)(1u << sr)) / (float)c : 0.0f;
 }
@@ -581,6 +631,32 @@ RCB_HD FusedDec fused_decode_step(uint64_t lo, uint64_t rpt, uint64_t data, cons
     r.takeB = takeB;
     r.inside = inside;
     r.ok = inside & (hi32(r.rgp) >= need);
+    return r;
+}
+
+
+// The same step for a general total with divide-free rpt_next: (csA, csB) are recip_of_freq of the
+// entry's two candidates.
+RCB_HD FusedDec fused_decode_step_cs(uint64_t lo, uint64_t rpt, uint64_t data, const LutEntry& e, uint64_t csA,
+                                     uint64_t csB) {
+    FusedDec r;
+    const uint64_t loA = mad64x32(rpt, e.cumA, lo);
+    const uint64_t loB = mad64x32(rpt, e.cumB, lo);
+    const uint64_t loC = mad64x32(rpt, e.cumC, lo);
+    const bool takeB = data >= loB;
+    r.nlo = takeB ? loB : loA;
+    const uint64_t up = takeB ? loC : loB;
+    r.sym = takeB ? (e.syms >> 16) : (e.syms & 0xFFFFu);
+    const bool inside = (data - r.nlo) < (up - r.nlo);
+    r.rgp = up - r.nlo;
+    const uint32_t xh = hi32(r.nlo) ^ hi32(up);
+    const bool p1 = xh < (1u << 24), p2 = xh < (1u << 16), p3 = xh < (1u << 8);
+    r.sh = p2 ? (p3 ? 24u : 16u) : (p1 ? 8u : 0u);
+    const bool exact = fused_rpt_cs(rpt, takeB ? csB : csA, r.sh, r.nrpt);
+    const uint32_t need = p2 ? 1u : (p1 ? (1u << 8) : (1u << 16));
+    r.takeB = takeB;
+    r.inside = inside;
+    r.ok = inside & exact & (hi32(r.rgp) >= need);
     return r;
 }
 

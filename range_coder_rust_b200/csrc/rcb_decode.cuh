@@ -50,6 +50,7 @@ struct DecodeArgs {
     const uint2* tabs;
     const ModelHdr* hdrs;
     const LutEntry* lut;      // shared model only
+    const uint4* lut_cs;      // shared model: {csA lo, csA hi, csB lo, csB hi} per LUT entry (FUSE_GEN)
     uint32_t K;
     uint32_t per_chunk;
     void* out;
@@ -258,11 +259,18 @@ __device__ __noinline__ DecLaneState dec_exact(DecLaneState s, const uint2* tab,
     return s;
 }
 
-template <typename SYM, bool SHARED, bool POW2, bool CHECKED, bool FUSED>
+// FMODE: -1 = generic per-symbol loop (bucket LUT + exact search); FUSE_BIG / FUSE_POW2 / FUSE_GEN = the fused
+// word-speculative loop over the fat LUT for a power-of-two total >= 2^24 / any power of two / any total
+// (FUSE_GEN: divide-free rpt_next from the candidates' reciprocal constants, rcb_core.cuh).
+template <typename SYM, bool SHARED, bool POW2, bool CHECKED, int FMODE>
 __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
+    constexpr bool FUSED = FMODE >= 0;
+    constexpr bool CSM = FMODE == FUSE_GEN;
+    constexpr int MODE = FUSED ? FMODE : FUSE_BIG;
     extern __shared__ __align__(16) uint8_t s_raw[];
     __shared__ ModelHdr s_hdr;
-    // shared layout: rings[blockDim.x][RING_STRIDE] | LutEntry[nb or 4096] | (FUSED) float2 rc[4096] | uint2[K]
+    // shared layout: rings[blockDim.x][RING_STRIDE] | LutEntry[nb or 4096] | (FUSED) float2 rc[4096]
+    //                | (FUSE_GEN) uint4 cs[4096] | uint2[K]
     // (entries and reciprocals in separate arrays: 16- and 8-byte strides spread random lookups over all
     // banks; one 32-byte record per bucket doubled the bank conflicts once several warps share an SM)
     uint8_t* s_ring = s_raw;
@@ -274,16 +282,18 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
         const uint32_t nb = (s_hdr.flags & MODEL_REGULAR) ? s_hdr.nb : 0u;
         const uint32_t nb_pad = FUSED ? 4096u : nb;  // FUSED indexes any of 4096 entries
         float2* s_rc = reinterpret_cast<float2*>(s_lut + nb_pad);
-        s_tab = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(s_rc) + (FUSED ? 4096u * sizeof(float2) : 0u));
+        uint4* s_cs = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(s_rc) + (FUSED ? 4096u * sizeof(float2) : 0u));
+        s_tab = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(s_cs) + (CSM ? 4096u * sizeof(uint4) : 0u));
         const uint4* gl = reinterpret_cast<const uint4*>(a.lut);
         uint4* sl = reinterpret_cast<uint4*>(s_lut);
         const uint32_t total = s_hdr.div.total;
-        const uint32_t sr = fused_sr(make_fused(s_hdr.div));
+        const uint32_t sr = CSM ? 0u : fused_sr(make_fused(s_hdr.div));
         for (uint32_t i = threadIdx.x; i < nb_pad; i += blockDim.x) {
             const uint4 e = i < nb ? gl[i] : make_uint4(total, total, total, 0u);  // empty interval: never verifies
             sl[i] = e;
             if (FUSED)  // reciprocals of the candidates' frequencies for the shift-free estimate (rcb_core.cuh)
                 s_rc[i] = make_float2(lut_rc16(e.y - e.x, s_hdr.lut_scale, sr), lut_rc16(e.z - e.y, s_hdr.lut_scale, sr));
+            if (CSM) s_cs[i] = i < nb ? a.lut_cs[i] : make_uint4(0u, 0u, 0u, 0u);
         }
         for (uint32_t i = threadIdx.x; i < a.K; i += blockDim.x) s_tab[i] = a.tabs[i];
         __syncthreads();
@@ -396,12 +406,15 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
 
     if constexpr (FUSED) {
         const FusedParams fp = make_fused(div);
-        uint64_t rpt = rg >> fp.s;
-        const uint32_t sr = fused_sr(fp);
-        float q = lut_q(rpt, sr);                                      // 1 / float(rpt >> sr)
+        uint64_t rpt = fused_rpt<MODE>(rg, fp);
+        const uint32_t sr = CSM ? 0u : fused_sr(fp);
+        auto q_of = [&](uint64_t r) -> float { return CSM ? lut_q_gen(r) : lut_q(r, sr); };  // 1 / float(rpt >> sr)
+        auto range_of = [&](uint64_t r) -> uint64_t { return CSM ? r * (uint64_t)div.total : r << fp.s; };
+        float q = q_of(rpt);
         float bf = lut_bf16_init(sink.data() - lo, rg, lut_scale);     // byte offset of the next entry
         const uint32_t lut_saddr = (uint32_t)__cvta_generic_to_shared(s_lut);
         const uint32_t rc_saddr = lut_saddr + 4096u * (uint32_t)sizeof(LutEntry);
+        const uint32_t cs_saddr = rc_saddr + 4096u * (uint32_t)sizeof(float2);
         // Four symbols, straight-line and speculative; `bad` = some symbol needs the exact path.
         auto decode_word = [&](uint32_t& acc, bool& bad) {
             acc = 0;
@@ -412,13 +425,20 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
                 const uint32_t off = lut_offset16(bf);
                 const LutEntry e = lds_lut(lut_saddr + off);
                 const float2 rc = lds_f2(rc_saddr + (off >> 1));
-                const FusedDec r = fused_decode_step(lo, rpt, data, e, fp);
+                FusedDec r;
+                if constexpr (CSM) {
+                    const LutEntry k = lds_lut(cs_saddr + off);  // {csA lo, csA hi, csB lo, csB hi}
+                    r = fused_decode_step_cs(lo, rpt, data, e, ((uint64_t)k.cumB << 32) | k.cumA,
+                                             ((uint64_t)k.syms << 32) | k.cumC);
+                } else {
+                    r = fused_decode_step<MODE>(lo, rpt, data, e, fp);
+                }
                 // next symbol's entry from the unshifted residue: no dependence on the shift (rcb_core.cuh)
                 bf = u64_to_float(data - r.nlo) * (q * (r.takeB ? rc.y : rc.x));
                 sink.put(0u, r.sh);
                 lo = r.nlo << r.sh;
                 rpt = r.nrpt;
-                q = lut_q(rpt, sr);
+                q = q_of(rpt);
                 acc |= r.sym << (SYM_BITS * b);
                 bad |= !r.ok;
             }
@@ -450,8 +470,8 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
 #pragma unroll 1
             for (uint32_t b = 0; b < PER; b++) {
                 const uint64_t data = sink.data();
-                const uint32_t off = lut_offset16(lut_bf16_init(data - lo, rpt << fp.s, lut_scale));
-                const FusedDec r = fused_decode_step(lo, rpt, data, lds_lut(lut_saddr + off), fp);
+                const uint32_t off = lut_offset16(lut_bf16_init(data - lo, range_of(rpt), lut_scale));
+                const FusedDec r = fused_decode_step<MODE>(lo, rpt, data, lds_lut(lut_saddr + off), fp);
                 uint32_t sym = r.sym;
                 if (RCB_LIKELY(r.ok)) {
                     sink.put(0u, r.sh);
@@ -467,12 +487,12 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
                     }
                     renorm_slow<CHECKED>(l2, g2, sink, err);  // src/range_coder.rs:83-89, bytes from the ring
                     lo = l2;
-                    rpt = g2 >> fp.s;
+                    rpt = fused_rpt<MODE>(g2, fp);
                 }
                 acc |= sym << (SYM_BITS * b);
             }
-            rg = rpt << fp.s;
-            q = lut_q(rpt, sr);
+            rg = range_of(rpt);
+            q = q_of(rpt);
             bf = lut_bf16_init(sink.data() - lo, rg, lut_scale);
             return acc;
         };
@@ -508,7 +528,7 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
             dw[i] = acc;
         }
         done = nw * PER;
-        rg = rpt << fp.s;
+        rg = range_of(rpt);
     }
 
     auto step = [&]() -> uint32_t {

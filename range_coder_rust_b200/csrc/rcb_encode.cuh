@@ -36,7 +36,9 @@
 namespace rcb {
 
 enum : int { TAB_SHARED = 0, TAB_LANE = 1, TAB_GLOBAL = 2 };
-enum : int { FM_GENERIC = -1, FM_BIG = FUSE_BIG, FM_POW2 = FUSE_POW2, FM_GEN = FUSE_GEN, FM_LANE = 3 };
+// FM_GENCS: general total with the divide-free step (each table entry carries cs = floor(c * 2^64 / total),
+// rcb_core.cuh: fused_step_cs); TAB_SHARED only.  FM_GEN keeps the multiply-high reciprocal.
+enum : int { FM_GENERIC = -1, FM_BIG = FUSE_BIG, FM_POW2 = FUSE_POW2, FM_GEN = FUSE_GEN, FM_LANE = 3, FM_GENCS = 4 };
 
 struct EncodeArgs {
     const void* syms;
@@ -45,6 +47,7 @@ struct EncodeArgs {
     uint64_t n_chunks;
     const uint2* tabs;      // [n_models][K]
     const ModelHdr* hdrs;   // [n_models]
+    const uint2* tab_cs;    // [K] floor(c * 2^64 / total) as {lo, hi} (shared model, FM_GENCS)
     uint32_t K;
     uint32_t lanes_per_block;  // chunks per block (<= blockDim.x)
     uint8_t* staging;       // [n_chunks][pitch]
@@ -104,6 +107,17 @@ template <int SPW>
 struct EncEntries {
     uint2 e[SPW];  // {cum, c}
 };
+template <int SPW>
+struct EncEntries4 {
+    uint4 e[SPW];  // {cum, c, cs lo, cs hi}
+};
+__device__ __forceinline__ uint4 lds_u4(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return r;
+}
 
 // Lane state of the fused loop; travels by value through the exact re-code path.
 struct EncWordState {
@@ -157,12 +171,22 @@ __global__ void __launch_bounds__(512, 1) encode_kernel(EncodeArgs a) {
     const uint32_t L = a.lanes_per_block;
     const uint64_t block_first = (uint64_t)blockIdx.x * L;
     // shared layout: table (TAB_SHARED: uint2[K]; TAB_LANE: u32[L][K+1]) | input rings[blockDim.x] (fused loops)
-    const uint32_t ring_off = TABLE == TAB_SHARED ? ((K * 8u + 15u) & ~15u)
+    constexpr bool CS = FMODE == FM_GENCS;
+    static_assert(!CS || TABLE == TAB_SHARED, "FM_GENCS needs the shared table");
+    const uint32_t ring_off = TABLE == TAB_SHARED ? ((K * (CS ? 16u : 8u) + 15u) & ~15u)
                               : TABLE == TAB_LANE ? ((L * (K + 1u) * 4u + 15u) & ~15u)
                                                   : 0u;
     if (TABLE == TAB_SHARED) {
-        uint2* s_tab = reinterpret_cast<uint2*>(s_raw);
-        for (uint32_t i = threadIdx.x; i < K; i += blockDim.x) s_tab[i] = a.tabs[i];
+        if (CS) {
+            uint4* s_tab4 = reinterpret_cast<uint4*>(s_raw);
+            for (uint32_t i = threadIdx.x; i < K; i += blockDim.x) {
+                const uint2 t = a.tabs[i], r = a.tab_cs[i];
+                s_tab4[i] = make_uint4(t.x, t.y, r.x, r.y);
+            }
+        } else {
+            uint2* s_tab = reinterpret_cast<uint2*>(s_raw);
+            for (uint32_t i = threadIdx.x; i < K; i += blockDim.x) s_tab[i] = a.tabs[i];
+        }
         if (threadIdx.x == 0) s_hdr = a.hdrs[0];
         __syncthreads();
     }
@@ -188,6 +212,7 @@ __global__ void __launch_bounds__(512, 1) encode_kernel(EncodeArgs a) {
     const SYM* src = reinterpret_cast<const SYM*>(a.syms) + first;
 
     const uint2* tab = TABLE == TAB_SHARED ? reinterpret_cast<const uint2*>(s_raw) : a.tabs + chunk * K;
+    const uint4* tab4 = reinterpret_cast<const uint4*>(s_raw);  // FM_GENCS
     const uint32_t* row = reinterpret_cast<const uint32_t*>(s_raw) + (size_t)threadIdx.x * (K + 1);
     DivParams div;
     bool pow2;
@@ -207,7 +232,7 @@ __global__ void __launch_bounds__(512, 1) encode_kernel(EncodeArgs a) {
     EncSink<RowStore, true> sink(rs, cap);
 
     constexpr int SPW = 4 / sizeof(SYM);  // symbols per 32-bit word
-    using Entries = EncEntries<SPW>;
+    using Entries = typename std::conditional<CS, EncEntries4<SPW>, EncEntries<SPW>>::type;
     auto entry = [&](uint32_t s) -> uint2 {
         if (RANGECHK && s >= K) {
             if (!err) err = ST_SYMBOL_RANGE;
@@ -217,13 +242,27 @@ __global__ void __launch_bounds__(512, 1) encode_kernel(EncodeArgs a) {
             const uint32_t cum = row[s];
             return make_uint2(cum, row[s + 1] - cum);  // regular table: c = cum[s+1] - cum[s]
         }
+        if (CS) {
+            const uint4 t = lds_u4(tab4 + s);
+            return make_uint2(t.x, t.y);
+        }
         return tab[s];
     };
     auto lookup = [&](uint32_t w) -> Entries {
         Entries r;
 #pragma unroll
-        for (int b = 0; b < SPW; b++)
-            r.e[b] = entry(sizeof(SYM) == 1 ? ((w >> (8 * b)) & 0xFFu) : ((w >> (16 * b)) & 0xFFFFu));
+        for (int b = 0; b < SPW; b++) {
+            uint32_t sy = sizeof(SYM) == 1 ? ((w >> (8 * b)) & 0xFFu) : ((w >> (16 * b)) & 0xFFFFu);
+            if constexpr (CS) {
+                if (RANGECHK && sy >= K) {
+                    if (!err) err = ST_SYMBOL_RANGE;
+                    sy = 0;
+                }
+                r.e[b] = lds_u4(tab4 + sy);
+            } else {
+                r.e[b] = entry(sy);
+            }
+        }
         return r;
     };
     auto generic_symbol = [&](uint2 e) {
@@ -279,7 +318,12 @@ __global__ void __launch_bounds__(512, 1) encode_kernel(EncodeArgs a) {
                         for (int b = 0; b < SPW; b++) {  // speculative: straight-line, no branch
                             uint64_t nlo, rgp, nrpt;
                             uint32_t sh;
-                            const bool ok = fused_step<MODE>(lo, rpt, en.e[b].x, en.e[b].y, fp, nlo, rgp, nrpt, sh);
+                            bool ok;
+                            if constexpr (CS)
+                                ok = fused_step_cs(lo, rpt, en.e[b].x, en.e[b].y,
+                                                   ((uint64_t)en.e[b].w << 32) | en.e[b].z, nlo, rgp, nrpt, sh);
+                            else
+                                ok = fused_step<MODE>(lo, rpt, en.e[b].x, en.e[b].y, fp, nlo, rgp, nrpt, sh);
                             fs.put(em_hi, em_sh);
                             em_hi = hi32(nlo);
                             em_sh = sh;
@@ -288,7 +332,10 @@ __global__ void __launch_bounds__(512, 1) encode_kernel(EncodeArgs a) {
                             bad |= !ok;
                         }
                         if (RCB_UNLIKELY(bad)) {  // restore the checkpoint and re-code the word exactly
-                            const EncWordState r = enc_word_exact<SPW, MODE>(chk, en, fp, rs.row, cap);
+                            EncEntries<SPW> en2;
+#pragma unroll
+                            for (int b = 0; b < SPW; b++) en2.e[b] = make_uint2(en.e[b].x, en.e[b].y);
+                            const EncWordState r = enc_word_exact<SPW, MODE>(chk, en2, fp, rs.row, cap);
                             lo = r.lo;
                             rpt = r.rpt;
                             fs.pend = r.pend;
@@ -326,6 +373,8 @@ __global__ void __launch_bounds__(512, 1) encode_kernel(EncodeArgs a) {
                 if constexpr (FMODE == FM_LANE) {
                     if (pow2) run(std::integral_constant<int, FUSE_POW2>{});
                     else run(std::integral_constant<int, FUSE_GEN>{});
+                } else if constexpr (CS) {
+                    run(std::integral_constant<int, FUSE_GEN>{});
                 } else {
                     run(std::integral_constant<int, FMODE>{});
                 }

@@ -344,8 +344,9 @@ __global__ void __launch_bounds__(256) finalize_models_kernel(const uint2* __res
                                                               const uint32_t* __restrict__ totals,
                                                               uint32_t K, ModelHdr* hdrs,
                                                               LutEntry* lut, uint32_t lut_cap,
+                                                              uint2* tab_cs, uint4* lut_cs,
                                                               uint32_t* summary /*[0]=min c, [1]=bad bits, [3]=max total*/) {
-    __shared__ uint32_t s_flags_bad;  // bit0 inconsistent, bit1 irregular, bit2 cum>total
+    __shared__ uint32_t s_flags_bad;  // bit0 inconsistent, bit1 irregular, bit2 cum>total, bit3 c==total
     __shared__ uint32_t s_minc;
     const uint64_t model = blockIdx.x;
     const uint2* tab = tabs + model * K;
@@ -369,6 +370,12 @@ __global__ void __launch_bounds__(256) finalize_models_kernel(const uint2* __res
             bad |= 2u;
         }
         if (e.y && e.y < minc) minc = e.y;
+        if (e.y == total) bad |= 8u;
+        // shared model: reciprocal constants of the divide-free general-total step (rcb_core.cuh)
+        if (tab_cs && total) {
+            const uint64_t r = e.y < total ? recip_of_freq(e.y, total) : ~0ull;
+            tab_cs[i] = make_uint2(lo32(r), hi32(r));
+        }
     }
     if (bad) atomicOr(&s_flags_bad, bad);
     atomicMin(&s_minc, minc);
@@ -387,6 +394,7 @@ __global__ void __launch_bounds__(256) finalize_models_kernel(const uint2* __res
         }
         if (!(s_flags_bad & 1u)) flags |= MODEL_CONSISTENT;
         if (!(s_flags_bad & 3u)) flags |= MODEL_REGULAR;
+        if (s_flags_bad & 8u) flags |= MODEL_FULLC;
         h.flags = flags;
         h.min_c = s_minc;
         h.K = K;
@@ -434,6 +442,12 @@ __global__ void __launch_bounds__(256) finalize_models_kernel(const uint2* __res
         e.cumC = cumC;
         e.syms = A | ((B & 0xFFFFu) << 16);
         lut[b] = e;
+        if (lut_cs) {  // cs of the entry's two candidates
+            const uint32_t cA = cumB - cumA, cB = cumC - cumB;
+            const uint64_t ra = cA < total ? recip_of_freq(cA, total) : ~0ull;
+            const uint64_t rb = cB < total ? recip_of_freq(cB, total) : ~0ull;
+            lut_cs[b] = make_uint4(lo32(ra), hi32(ra), lo32(rb), hi32(rb));
+        }
     }
 }
 

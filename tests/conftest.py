@@ -62,6 +62,8 @@ def hostcore():
     L.hc_decode.argtypes = [vp, u64, u64, u64, u64, ci, u32, vp, vp, u32, vp, ci, ci, u32, vp, vp]
     L.hc_check_division.restype = u64
     L.hc_check_division.argtypes = [vp, u64, u32]
+    L.hc_check_cs.restype = u64
+    L.hc_check_cs.argtypes = [vp, vp, vp, u64, u32, vp]
     return L
 
 

@@ -151,7 +151,37 @@ extern "C" int64_t hc_encode(const uint8_t* syms, uint64_t n, int sym_bytes, uin
         };
         if (pow2 && div.shift >= 24) return run(std::integral_constant<int, FUSE_BIG>{});
         if (pow2) return run(std::integral_constant<int, FUSE_POW2>{});
-        return run(std::integral_constant<int, FUSE_GEN>{});
+        bool full = false;  // a symbol with c == total has no reciprocal constant (plan_encode: FM_GEN)
+        for (uint32_t i = 0; i < K; i++) full |= c[i] == total;
+        if (full) return run(std::integral_constant<int, FUSE_GEN>{});
+        // divide-free general total (mirrors encode_kernel's FM_GENCS instantiation)
+        std::vector<uint64_t> cs(K);
+        for (uint32_t i = 0; i < K; i++) cs[i] = recip_of_freq(c[i], total);
+        uint64_t rpt = fused_rpt<FUSE_GEN>(rg, fp);
+        for (uint64_t i = 0; i < n; i++) {
+            uint32_t s = load_sym(syms, i, sym_bytes);
+            if (s >= K) {
+                if (!err) err = ST_SYMBOL_RANGE;
+                s = 0;
+            }
+            uint64_t nlo, rgp, nrpt;
+            uint32_t sh;
+            if (fused_step_cs(lo, rpt, cum[s], c[s], cs[s], nlo, rgp, nrpt, sh)) {
+                if (nrpt != (rgp << sh) / total) return -2;  // the exactness test must never pass a wrong quotient
+                sink.put((uint32_t)(nlo >> 32), sh);
+                lo = nlo << sh;
+                rpt = nrpt;
+            } else {
+                lo = nlo;
+                rg = rgp;
+                renorm_slow<false>(lo, rg, sink, err);
+                rpt = fused_rpt<FUSE_GEN>(rg, fp);
+            }
+        }
+        uint32_t len = sink.finish(lo);
+        if (!err && sink.overflowed()) err = ST_OUT_CAPACITY;
+        *status = err;
+        return (int64_t)len;
     }
     for (uint64_t i = 0; i < n; i++) {
         uint32_t s = load_sym(syms, i, sym_bytes);
@@ -194,18 +224,26 @@ extern "C" int64_t hc_decode(const uint8_t* stream, uint64_t off0, uint64_t off1
     sink.prime(skip);
     uint64_t lo = 0, rg = ~0ull, fallbacks = 0;
     uint32_t err = 0;
-    // fused pow2 path (mirrors decode_kernel's FUSED instantiation)
-    if (lut_ok && pow2 && h.div.shift >= 24 && (h.flags & MODEL_CONSISTENT) && !checked && lut_cap == 4096) {
+    // fused fat-LUT path (mirrors decode_kernel's FUSE_BIG / FUSE_POW2 / FUSE_GEN instantiations)
+    bool full = false;
+    for (uint32_t i = 0; i < K; i++) full |= c[i] == total;
+    if (lut_ok && total >= 2 && !(!pow2 && full) && (h.flags & MODEL_CONSISTENT) && !checked && lut_cap == 4096) {
+        const int mode = pow2 ? (h.div.shift >= 24 ? FUSE_BIG : FUSE_POW2) : FUSE_GEN;
         FusedParams fp = make_fused(h.div);
         std::vector<LutEntry> pad(4096);
         for (uint32_t b = 0; b < 4096; b++) {
             if (b < h.nb) pad[b] = lut[b];
             else pad[b] = LutEntry{total, total, total, 0};
         }
-        uint64_t rpt = rg >> fp.s;
+        auto rpt_of = [&](uint64_t range) {
+            return mode == FUSE_GEN ? fused_rpt<FUSE_GEN>(range, fp) : (range >> fp.s);
+        };
+        auto range_of = [&](uint64_t r) { return mode == FUSE_GEN ? r * (uint64_t)total : r << fp.s; };
+        uint64_t rpt = rpt_of(rg);
         // shift-free estimate, as in decode_kernel: q = 1/float(rpt >> sr), rc = const / c of the candidate
-        const uint32_t sr = fused_sr(fp);
-        float q = lut_q(rpt, sr);
+        const uint32_t sr = mode == FUSE_GEN ? 0u : fused_sr(fp);
+        auto q_of = [&](uint64_t r) { return mode == FUSE_GEN ? lut_q_gen(r) : lut_q(r, sr); };
+        float q = q_of(rpt);
         float bf = lut_bf16_init(sink.data() - lo, rg, h.lut_scale);
         for (uint64_t i = 0; i < n_syms; i++) {
             const uint64_t data = sink.data();
@@ -213,7 +251,14 @@ extern "C" int64_t hc_decode(const uint8_t* stream, uint64_t off0, uint64_t off1
             const LutEntry e = pad[off >> 4];
             const float rcA = lut_rc16(e.cumB - e.cumA, h.lut_scale, sr);
             const float rcB = lut_rc16(e.cumC - e.cumB, h.lut_scale, sr);
-            FusedDec r = fused_decode_step(lo, rpt, data, e, fp);
+            FusedDec r;
+            if (mode == FUSE_BIG) r = fused_decode_step<FUSE_BIG>(lo, rpt, data, e, fp);
+            else if (mode == FUSE_POW2) r = fused_decode_step<FUSE_POW2>(lo, rpt, data, e, fp);
+            else {
+                r = fused_decode_step_cs(lo, rpt, data, e, recip_of_freq(e.cumB - e.cumA, total),
+                                         recip_of_freq(e.cumC - e.cumB, total));
+                if (r.ok && r.nrpt != (r.rgp << r.sh) / total) return -2;  // exactness test passed a wrong quotient
+            }
             uint32_t sym;
             if (r.ok) {
                 sym = r.sym;
@@ -221,16 +266,16 @@ extern "C" int64_t hc_decode(const uint8_t* stream, uint64_t off0, uint64_t off1
                 sink.put(0, r.sh);
                 lo = r.nlo << r.sh;
                 rpt = r.nrpt;
-                q = lut_q(rpt, sr);
+                q = q_of(rpt);
             } else {
                 fallbacks++;
                 sym = find_index_exact(data - lo, rpt, K, [&](uint32_t j) { return cum[j]; });
                 lo = lo + rpt * (uint64_t)cum[sym];
                 rg = rpt * (uint64_t)c[sym];
                 renorm<false>(lo, rg, sink, err);
-                rpt = rg >> fp.s;
-                q = lut_q(rpt, sr);
-                bf = lut_bf16_init(sink.data() - lo, rg, h.lut_scale);
+                rpt = rpt_of(rg);
+                q = q_of(rpt);
+                bf = lut_bf16_init(sink.data() - lo, range_of(rpt), h.lut_scale);
             }
             store_sym(out, i, sym_bytes, sym);
         }
@@ -286,4 +331,26 @@ extern "C" uint64_t hc_check_division(const uint64_t* ranges, uint64_t n, uint32
         if (q != ranges[i] / total) bad++;
     }
     return bad;
+}
+
+// Divide-free rpt_next (fused_rpt_cs): for every (rpt, c, sh) with (rpt * c) << sh < 2^64, a passing
+// exactness test must come with the exact quotient.  Returns the number of wrong quotients that passed
+// (must be 0) and, in *n_inexact, how many cases the test sent to the exact path.
+extern "C" uint64_t hc_check_cs(const uint64_t* rpts, const uint32_t* cs_c, const uint32_t* shs, uint64_t n,
+                                uint32_t total, uint64_t* n_inexact) {
+    uint64_t wrong = 0, inexact = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint64_t rpt = rpts[i];
+        const uint32_t c = cs_c[i], sh = shs[i];
+        const unsigned __int128 x = ((unsigned __int128)rpt * c) << sh;
+        if (c == 0 || c >= total || (x >> 64) != 0) continue;  // outside the step's preconditions
+        uint64_t nrpt;
+        if (fused_rpt_cs(rpt, recip_of_freq(c, total), sh, nrpt)) {
+            if (nrpt != (uint64_t)x / total) wrong++;
+        } else {
+            inexact++;
+        }
+    }
+    if (n_inexact) *n_inexact = inexact;
+    return wrong;
 }

@@ -246,6 +246,57 @@ def test_tables_from_host(ctx, oracle, kind):
     assert np.array_equal(dev_to_np(out), syms)
 
 
+@pytest.mark.parametrize("kind", ["gen_2e30", "gen_prime", "pow2_2e20", "pow2_4096", "gen_small", "gen_u16",
+                                  "gen_full_c"])
+def test_fused_paths_for_general_totals(ctx, oracle, kind):
+    """The word-speculative encoder and the fat-LUT decoder for totals that are not a power of two >= 2^24:
+    the divide-free general-total step (reciprocal constant per symbol, exactness test, exact re-code on a
+    flagged word), small powers of two (two shifts), and the table the divide-free step must refuse
+    (a symbol with c == total).  Bytes against the oracle, symbols back, cross-decode of the oracle's stream."""
+    rng = np.random.default_rng(17)
+    K, sb = 256, 1
+    if kind == "gen_2e30":
+        total = (1 << 30) + 12345
+    elif kind == "gen_prime":
+        total = 1_000_003
+    elif kind == "pow2_2e20":
+        total = 1 << 20
+    elif kind == "pow2_4096":
+        K, total = 64, 4096
+    elif kind == "gen_small":
+        K, total = 50, 3001
+    elif kind == "gen_u16":
+        K, total, sb = 1000, (1 << 28) + 7, 2
+    else:
+        K, total = 3, 1_000_003
+    if kind == "gen_full_c":
+        c = np.array([0, total, 0], dtype=np.uint32)
+    else:
+        w = np.arange(1, K + 1, dtype=np.float64) ** -0.9
+        floor_c = max(2, int(total / 4096 * 1.2) + 2)  # every symbol resolvable by the 4096-bucket table
+        c = np.maximum(floor_c, (w / w.sum() * (total - K * floor_c)).astype(np.int64))
+        c[0] += total - int(c.sum())
+        assert c[0] > 0
+        c = c.astype(np.uint32)
+    cum, t = oracle.calc_cum(c)
+    assert t == total
+    n, chunk = 1_500_000 + 777, 65536
+    used = np.flatnonzero(c)
+    p = c[used].astype(np.float64)
+    syms = rng.choice(used, size=n, p=p / p.sum()).astype(np.uint16 if sb == 2 else np.uint8)
+    model = ctx.model_from_tables(c, cum, total)
+    d_syms = to_dev(ctx, syms)
+    stream, offsets, nbytes = ctx.encode_chunks(d_syms, chunk, model)
+    ref_stream, ref_offsets = oracle.encode_chunks(syms, chunk, c, cum, total)
+    assert_streams_equal(stream, offsets, nbytes, ref_stream, ref_offsets)
+    out = ctx.decode_chunks(stream, offsets, n, chunk, model, sym_bytes=sb)
+    assert np.array_equal(dev_to_np(out, dtype=syms.dtype), syms)
+    pad = np.zeros(((ref_stream.size + 31) // 16) * 16, dtype=np.uint8)
+    pad[:ref_stream.size] = ref_stream
+    out2 = ctx.decode_chunks(to_dev(ctx, pad), to_dev(ctx, ref_offsets.view(np.int64)), n, chunk, model, sym_bytes=sb)
+    assert np.array_equal(dev_to_np(out2, dtype=syms.dtype), syms)
+
+
 def test_slack_total_per_chunk_models(ctx, oracle):
     """Per-chunk tables whose last symbol does not end at total_freq (and the last symbol is coded a
     lot): bytes must match the oracle and decode must return the symbols, through the chunk API."""
@@ -470,7 +521,7 @@ def test_error_statuses(ctx, oracle):
 
 
 @pytest.mark.timeout(120)
-@pytest.mark.parametrize("kind", ["static_pow2", "static_odd", "adaptive", "k4096"])
+@pytest.mark.parametrize("kind", ["static_pow2", "static_odd", "static_odd_fat", "adaptive", "k4096"])
 def test_garbage_streams_terminate(ctx, oracle, kind):
     """Corrupt input must never hang or fault the decoder (the reference would panic or spin): random
     bytes in place of the code stream, through every kernel family.  Any status is acceptable; the call
@@ -487,6 +538,9 @@ def test_garbage_streams_terminate(ctx, oracle, kind):
     else:
         counts = ctx.histogram(d, K)
         if kind == "static_odd":
+            counts[0] += 999
+        if kind == "static_odd_fat":  # every count above one LUT bucket: the fat-LUT kernel, general total
+            counts += 200
             counts[0] += 999
         model = ctx.model_from_counts(counts)
     stream, offsets, nbytes = ctx.encode_chunks(d, chunk, model)

@@ -186,3 +186,44 @@ def test_reciprocal_division_is_exact(hostcore, total):
     mult = k * np.uint64(total)
     allr = np.concatenate([r, edge, mult, mult - np.uint64(1), mult + np.uint64(1)])
     assert hostcore.hc_check_division(_p(allr), allr.size, total) == 0
+
+
+@pytest.mark.parametrize("total", [3, 17, 255, 65537, 1000003, (1 << 30) - 125, (1 << 30) + 12345, (1 << 31) + 1,
+                                   0xFFFFFFFF, 0xFFFFFFFE, 6, 1 << 20])
+def test_divide_free_rpt_is_exact_or_flagged(hostcore, total):
+    """fused_rpt_cs (general totals without a divide on the chain): whenever its exactness test passes the
+    quotient equals floor((rpt * c << sh) / total); the cases it flags are rare for real tables.  Inputs:
+    states as the coder produces them (range in [2^48, 2^64) before the symbol), plus quotients that sit
+    exactly on a multiple of total (remainder 0 and total-1: where an off-by-one would show)."""
+    rng = np.random.default_rng(total % 7919)
+    n = 400_000
+    rng_range = rng.integers(1 << 48, (1 << 64) - 1, size=n, dtype=np.uint64, endpoint=True)
+    rpt = rng_range // np.uint64(total)
+    c = rng.integers(1, max(2, total), size=n, dtype=np.uint64).astype(np.uint32)
+    c[: n // 4] = rng.integers(1, min(total, 64), size=n // 4)          # rare symbols: the weakest margin
+    c[n // 4: n // 2] = total - rng.integers(1, min(total, 64), size=n // 4)  # dominant symbols
+    sh = (rng.integers(0, 4, size=n) * 8).astype(np.uint32)
+    # keep only shifts the coder could take: (rpt * c) << sh < 2^64
+    prod = rpt.astype(object) * c.astype(object)
+    ok = np.array([(int(p) << int(s)) < (1 << 64) for p, s in zip(prod[:20000], sh[:20000])])
+    sh[:20000][~ok] = 0
+    sh[20000:] = 0
+    # quotients on a multiple of total: rpt * c == k * total (+ 0 / - 1) needs rpt a multiple of total/gcd
+    k = rng.integers(1, 1 << 20, size=1000, dtype=np.uint64)
+    rpt_edge = k * np.uint64(total)
+    rpts = np.concatenate([rpt, rpt_edge, rpt_edge + np.uint64(1), rpt_edge - np.uint64(1)])
+    cs = np.concatenate([c, c[:1000], c[:1000], c[:1000]])
+    shs = np.concatenate([sh, np.zeros(3000, np.uint32)])
+    inexact = ctypes.c_uint64()
+    wrong = hostcore.hc_check_cs(_p(rpts), _p(cs), _p(shs), rpts.size, total, ctypes.byref(inexact))
+    assert wrong == 0
+    if total & (total - 1):  # quotients on an exact multiple of total are (rightly) sent to the exact path
+        assert inexact.value > 0
+    # coder-like states and symbols a 4096-bucket table resolves (c >= total / 4096; a symbol's share of
+    # flagged steps is ~ 2^-8 / c): far below the loop-2 rate (7e-4)
+    keep = c >= max(1, total >> 12)
+    r2, c2, s2 = (np.ascontiguousarray(a[keep]) for a in (rpt, c, sh))
+    wrong = hostcore.hc_check_cs(_p(r2), _p(c2), _p(s2), r2.size, total, ctypes.byref(inexact))
+    assert wrong == 0
+    if total >= 1 << 20:
+        assert inexact.value < max(3, r2.size * 2e-5)
