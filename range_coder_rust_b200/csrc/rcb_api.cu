@@ -837,11 +837,12 @@ static DecPlan plan_decode(const rcb_ctx* c, const rcb_model* m, uint64_t n_chun
         const uint32_t shift = m->h_hdr0.div.shift;
         const uint64_t total = m->h_hdr0.div.total;
         if (!p.checked && regular) {
-            // fat LUT (two candidates per bucket of 2^wshift, <= 4096 buckets): only when no bucket can hold
+            // fat LUT (two candidates per bucket of total / nb, nb <= 4096 buckets): only when no bucket can hold
             // two boundaries, i.e. every frequency >= one bucket + the 1/8 estimate margin.  Any total: a power
             // of two >= 2^24 folds the division into the renormalisation shift (FM_BIG), smaller powers of two
             // take two shifts (FM_POW2), everything else the divide-free step (FM_GEN here = FUSE_GEN with cs).
-            const uint64_t bucket = 1ull << m->h_hdr0.wshift;
+            const uint64_t nbk = m->h_hdr0.nb ? m->h_hdr0.nb : 1;
+            const uint64_t bucket = (total + nbk - 1) / nbk;  // bucket width, rounded up
             bool fat_ok = total >= 2 && (uint64_t)m->min_c >= bucket + (bucket >> 3) + 1 && !getenv("RCB_NO_FAT");
             if (!p.pow2 && ((m->h_hdr0.flags & MODEL_FULLC) || getenv("RCB_NO_GENCS"))) fat_ok = false;
             if (fat_ok) {

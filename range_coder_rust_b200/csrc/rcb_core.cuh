@@ -380,11 +380,19 @@ RCB_HD uint64_t recip_of_freq(uint32_t c, uint32_t total) {  // floor(c * 2^64 /
 
 RCB_HD bool fused_rpt_cs(uint64_t rpt, uint64_t cs, uint32_t sh, uint64_t& nrpt) {
     const uint32_t rl = lo32(rpt), rh = hi32(rpt), cl = lo32(cs), ch = hi32(cs);
+#if defined(__CUDA_ARCH__)
+    // hi64 through the compiler's multiply-high (wide multiply-adds chained by carry predicates, 7
+    // instructions); the middle limb is recomputed in wrapping 32-bit arithmetic (2 multiply-adds + 1 add)
+    const uint64_t ph = __umul64hi(rpt, cs);  // bits 64..127 of rpt * cs
+    const uint64_t p0 = (uint64_t)rl * cl;
+    const uint32_t pm = hi32(p0) + rl * ch + rh * cl, pl = lo32(p0);  // bits 32..63, 0..31
+#else
     const uint64_t p0 = (uint64_t)rl * cl;
     const uint64_t t1 = (uint64_t)rl * ch + hi32(p0);
     const uint64_t t2 = (uint64_t)rh * cl + lo32(t1);
     const uint64_t ph = (uint64_t)rh * ch + hi32(t1) + hi32(t2);  // bits 64..127 of rpt * cs
     const uint32_t pm = lo32(t2), pl = lo32(p0);                   // bits 32..63, 0..31
+#endif
     const uint32_t q_lo = funnel_l(pm, lo32(ph), sh), q_hi = funnel_l(lo32(ph), hi32(ph), sh);
     nrpt = ((uint64_t)q_hi << 32) | q_lo;
     const uint32_t G = funnel_l(pl, pm, sh);   // top 32 bits of frac((rpt << sh) * cs / 2^64)
@@ -482,10 +490,10 @@ RCB_HD uint32_t find_index_exact(uint64_t d, uint64_t rpt, uint32_t K, CumAt cum
 
 // ---------------------------------------------------------------------------
 // Table-driven lookup for a REGULAR table (cum[i+1] == cum[i] + c[i]).
-// The rfreq axis [0,total) is cut into nb buckets of width 2^wshift.  Entry b
-// describes the symbol A whose interval contains b<<wshift and the next
+// The rfreq axis [0,total) is cut into nb = min(total, 4096) buckets of equal (fractional) width
+// total / nb.  Entry b describes the symbol A whose interval contains floor(b * total / nb) and the next
 // non-zero symbol B:  [cumA,cumB) -> A, [cumB,cumC) -> B.
-// (Entry b is built for the point 1/8 bucket below b<<wshift, which absorbs the
+// (Entry b is built for the point 1/8 bucket below that start, which absorbs the
 // error of the estimate.)  The bucket comes from a float estimate of
 // d/rpt ~= d*total/range taken from the high words only (range >= 2^48, so each
 // high word carries >= 16 significant bits: the estimate is within 1/16 bucket
@@ -504,8 +512,8 @@ struct ModelHdr {
     uint32_t flags;      // RCB_MODEL_* (include/rcb200.h)
     uint32_t min_c;      // smallest non-zero c_freq (staging bound)
     uint32_t nb;         // LUT buckets (shared model only, else 0)
-    uint32_t wshift;     // log2(bucket width)
-    float lut_scale;     // total / 2^wshift
+    uint32_t wshift;     // unused (0); kept for the 48-byte layout
+    float lut_scale;     // number of buckets as a float: bucket = rfreq * lut_scale / total
     uint32_t K;
     uint32_t pad0, pad1;
 };

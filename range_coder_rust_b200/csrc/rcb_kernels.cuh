@@ -398,12 +398,12 @@ __global__ void __launch_bounds__(256) finalize_models_kernel(const uint2* __res
         h.flags = flags;
         h.min_c = s_minc;
         h.K = K;
-        // LUT geometry (used only when lut != nullptr)
-        uint32_t bits = total > 1 ? 32u - (uint32_t)__clz((int)(total - 1)) : 0u;  // ceil(log2 total)
-        uint32_t lg_cap = 31u - (uint32_t)__clz((int)lut_cap);
-        h.wshift = bits > lg_cap ? bits - lg_cap : 0u;
-        h.nb = total ? (uint32_t)((((unsigned long long)total - 1) >> h.wshift) + 1) : 0u;
-        h.lut_scale = (float)total / (float)(1ull << h.wshift);
+        // LUT geometry (used only when lut != nullptr): nb = min(total, cap) buckets of equal, in general
+        // fractional, width total / nb; bucket b starts at floor(b * total / nb).  (For a power-of-two total
+        // >= cap this is the shift geometry b << log2(total / cap).)
+        h.nb = total < lut_cap ? total : lut_cap;
+        h.wshift = 0u;
+        h.lut_scale = (float)h.nb;
         h.pad0 = h.pad1 = 0;
         hdrs[model] = h;
         if (s_flags_bad & 4u) atomicOr(&summary[1], 1u);
@@ -420,8 +420,8 @@ __global__ void __launch_bounds__(256) finalize_models_kernel(const uint2* __res
     if (!(H.flags & MODEL_REGULAR)) return;
     for (uint32_t b = threadIdx.x; b < H.nb; b += blockDim.x) {
         // the point this entry is built for: 1/8 bucket below the bucket start (estimate margin)
-        unsigned long long v0 = (unsigned long long)b << H.wshift;  // < total
-        const unsigned long long margin = (1ull << H.wshift) >> 3;
+        unsigned long long v0 = (unsigned long long)b * total / H.nb;  // < total
+        const unsigned long long margin = (total / H.nb) >> 3;
         v0 = v0 > margin ? v0 - margin : 0ull;
         // A = number of i in [1,K-1] with cum[i] <= v0  (the reference's search result)
         uint32_t left = 0, right = K - 1;

@@ -72,20 +72,16 @@ void build_header(uint32_t K, const uint32_t* c, const uint32_t* cum, uint32_t t
         if (i + 1 < K ? (uint64_t)cum[i + 1] != end : end != total) bad |= 2;
     }
     h.flags = (pow2 ? MODEL_POW2 : 0) | ((bad & 1) ? 0 : MODEL_CONSISTENT) | ((bad & 3) ? 0 : MODEL_REGULAR);
-    uint32_t bits = 0;
-    while (bits < 32 && (1ull << bits) < total) bits++;
-    uint32_t lg_cap = 0;
-    while ((1u << (lg_cap + 1)) <= lut_cap) lg_cap++;
-    h.wshift = bits > lg_cap ? bits - lg_cap : 0;
-    h.nb = (uint32_t)((((uint64_t)total - 1) >> h.wshift) + 1);
-    h.lut_scale = (float)total / (float)(1ull << h.wshift);
+    h.nb = total < lut_cap ? total : lut_cap;
+    h.wshift = 0;
+    h.lut_scale = (float)h.nb;
     h.K = K;
     lut.clear();
     if (!(h.flags & MODEL_REGULAR)) return;
     lut.resize(h.nb);
     for (uint32_t b = 0; b < h.nb; b++) {
-        uint64_t v0 = (uint64_t)b << h.wshift;
-        const uint64_t margin = (1ull << h.wshift) >> 3;
+        uint64_t v0 = (uint64_t)b * total / h.nb;
+        const uint64_t margin = (total / h.nb) >> 3;
         v0 = v0 > margin ? v0 - margin : 0;
         uint32_t left = 0, right = K - 1;
         while (left < right) {
