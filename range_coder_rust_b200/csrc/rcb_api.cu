@@ -813,7 +813,7 @@ struct DecPlan {
     int kind;       // 0: fat-LUT fused kernel / generic (rcb_decode.cuh), 1: row kernel (rcb_decode_row.cuh)
     int table;      // TAB_*
     int fmode;      // FM_* (row kernel), FM_BIG / FM_GENERIC (kind 0)
-    bool checked, pow2, lut16;
+    bool checked, pow2, lut16, m2;
     int threads;
     uint32_t lanes, nb;
     size_t smem;
@@ -848,9 +848,11 @@ static DecPlan plan_decode(const rcb_ctx* c, const rcb_model* m, uint64_t n_chun
             if (fat_ok) {
                 p.kind = 0;
                 p.fmode = p.pow2 ? (shift >= 24 ? FM_BIG : FM_POW2) : FM_GEN;
+                // general totals >= 2^25: one table-wide reciprocal; smaller ones: per-candidate constants
+                p.m2 = p.fmode == FM_GEN && recip2_ok((uint32_t)total) && !getenv("RCB_NO_M2");
                 // FUSED kernel: candidates (16 bytes) + reciprocals of their frequencies (8 bytes) per bucket
-                // (+ their 64-bit reciprocal constants, 16 bytes, for general totals)
-                const size_t fixed = (size_t)LUT_CAP * (sizeof(LutEntry) + 8 + (p.fmode == FM_GEN ? 16 : 0)) +
+                // (+ their 64-bit reciprocal constants, 16 bytes, for general totals < 2^25)
+                const size_t fixed = (size_t)LUT_CAP * (sizeof(LutEntry) + 8 + (p.fmode == FM_GEN && !p.m2 ? 16 : 0)) +
                                      (size_t)m->K * sizeof(uint2);
                 while (p.threads > 32 && (size_t)p.threads * RING_STRIDE + fixed > budget) p.threads >>= 1;
                 p.lanes = (uint32_t)p.threads;
@@ -917,6 +919,7 @@ static void launch_decode_variant(rcb_ctx* c, const rcb_model* m, const DecodeAr
     if (p.table == TAB_SHARED) {
         if (p.fmode == FM_BIG) go(decode_kernel<SYM, true, true, false, FUSE_BIG>);
         else if (p.fmode == FM_POW2) go(decode_kernel<SYM, true, true, false, FUSE_POW2>);
+        else if (p.fmode == FM_GEN && p.m2) go(decode_kernel<SYM, true, false, false, FUSE_GEN_M2>);
         else if (p.fmode == FM_GEN) go(decode_kernel<SYM, true, false, false, FUSE_GEN>);
         else if (p.pow2) {
             if (p.checked) go(decode_kernel<SYM, true, true, true, -1>);

@@ -315,6 +315,8 @@ struct EncSink {
 //   FUSE_POW2  total = 2^s, any s        : rpt_next = (range' << sh) >> s     (two shifts)
 //   FUSE_GEN   any total                 : rpt_next = (range' << sh) / total  (multiply-high reciprocal)
 enum : int { FUSE_BIG = 0, FUSE_POW2 = 1, FUSE_GEN = 2 };
+// decode_kernel's fused flavours additionally tell the two divide-free forms of FUSE_GEN apart
+enum : int { FUSE_GEN_M2 = 3 };
 
 struct FusedParams {
     uint32_t s;      // log2(total) (power-of-two totals)
@@ -398,6 +400,32 @@ RCB_HD bool fused_rpt_cs(uint64_t rpt, uint64_t cs, uint32_t sh, uint64_t& nrpt)
     const uint32_t G = funnel_l(pl, pm, sh);   // top 32 bits of frac((rpt << sh) * cs / 2^64)
     const uint32_t hy = funnel_l(rl, rh, sh);  // hi32(rpt << sh)
     return (uint64_t)G + hy <= 0xFFFFFFFEull;
+}
+
+// The same idea with ONE table-wide constant, for totals >= 2^25: with l = floor(log2 total) and
+// m2 = floor(2^(64+l) / total) (63 < log2 m2 < 64 for a total that is not a power of two)
+//   (range' << sh) / total = (range' * m2 / 2^64) / 2^(l-sh) + e,   0 <= e < 2^-l
+// so q' = hi64(range' * m2) >> (l - sh) is the exact quotient unless the l-sh bits shifted out are all
+// ones (then the exact path decides).  No per-symbol constant and no extra table lookup -- the decoder's
+// candidates would need a third shared-memory array for theirs -- at the price of starting from range'
+// instead of rpt (a longer chain: the encoder keeps the cs form).  Flagged share ~ 2^-(l-sh): 1e-5 of the
+// symbols for l = 30, 3e-4 for l = 25.
+struct Recip2 {
+    uint64_t m2;  // floor(2^(64+l) / total)
+    uint32_t l;   // floor(log2 total), >= 25
+};
+RCB_HD bool recip2_ok(uint32_t total) { return total >= (1u << 25) && (total & (total - 1u)) != 0u; }
+RCB_HD Recip2 make_recip2(uint32_t total) {
+    Recip2 r;
+    r.l = 31u - clz32(total);
+    r.m2 = (uint64_t)((((unsigned __int128)1) << (64u + r.l)) / total);
+    return r;
+}
+RCB_HD bool fused_rpt_m2(uint64_t rgp, uint32_t sh, const Recip2& k, uint64_t& nrpt) {
+    const uint64_t ph = umul64hi(rgp, k.m2);
+    const uint32_t D = k.l - sh;  // 1 .. 31
+    nrpt = ph >> D;
+    return ((~lo32(ph)) << (32u - D)) != 0u;  // the D bits shifted out are not all ones
 }
 
 // fused_step with the divide-free rpt_next (encoder, FUSE_GEN tables that carry cs)
@@ -668,6 +696,29 @@ RCB_HD FusedDec fused_decode_step_cs(uint64_t lo, uint64_t rpt, uint64_t data, c
     return r;
 }
 
+
+// ... and with the table-wide constant (totals >= 2^25): no per-candidate constants to look up
+RCB_HD FusedDec fused_decode_step_m2(uint64_t lo, uint64_t rpt, uint64_t data, const LutEntry& e, const Recip2& k) {
+    FusedDec r;
+    const uint64_t loA = mad64x32(rpt, e.cumA, lo);
+    const uint64_t loB = mad64x32(rpt, e.cumB, lo);
+    const uint64_t loC = mad64x32(rpt, e.cumC, lo);
+    const bool takeB = data >= loB;
+    r.nlo = takeB ? loB : loA;
+    const uint64_t up = takeB ? loC : loB;
+    r.sym = takeB ? (e.syms >> 16) : (e.syms & 0xFFFFu);
+    const bool inside = (data - r.nlo) < (up - r.nlo);
+    r.rgp = up - r.nlo;
+    const uint32_t xh = hi32(r.nlo) ^ hi32(up);
+    const bool p1 = xh < (1u << 24), p2 = xh < (1u << 16), p3 = xh < (1u << 8);
+    r.sh = p2 ? (p3 ? 24u : 16u) : (p1 ? 8u : 0u);
+    const bool exact = fused_rpt_m2(r.rgp, r.sh, k, r.nrpt);
+    const uint32_t need = p2 ? 1u : (p1 ? (1u << 8) : (1u << 16));
+    r.takeB = takeB;
+    r.inside = inside;
+    r.ok = inside & exact & (hi32(r.rgp) >= need);
+    return r;
+}
 
 // Renormalisation half of the fused decode step, for callers that pick the symbol themselves
 // (row kernel: candidates from a thin LUT, then a short scan): from lower' and upper' of the

@@ -265,8 +265,10 @@ __device__ __noinline__ DecLaneState dec_exact(DecLaneState s, const uint2* tab,
 template <typename SYM, bool SHARED, bool POW2, bool CHECKED, int FMODE>
 __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
     constexpr bool FUSED = FMODE >= 0;
-    constexpr bool CSM = FMODE == FUSE_GEN;
-    constexpr int MODE = FUSED ? FMODE : FUSE_BIG;
+    constexpr bool CSM = FMODE == FUSE_GEN;     // general total, per-candidate reciprocal constants (third array)
+    constexpr bool M2M = FMODE == FUSE_GEN_M2;  // general total >= 2^25, one table-wide constant
+    constexpr bool GENM = CSM || M2M;
+    constexpr int MODE = !FUSED ? FUSE_BIG : (GENM ? FUSE_GEN : FMODE);
     extern __shared__ __align__(16) uint8_t s_raw[];
     __shared__ ModelHdr s_hdr;
     // shared layout: rings[blockDim.x][RING_STRIDE] | LutEntry[nb or 4096] | (FUSED) float2 rc[4096]
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
         const uint4* gl = reinterpret_cast<const uint4*>(a.lut);
         uint4* sl = reinterpret_cast<uint4*>(s_lut);
         const uint32_t total = s_hdr.div.total;
-        const uint32_t sr = CSM ? 0u : fused_sr(make_fused(s_hdr.div));
+        const uint32_t sr = GENM ? 0u : fused_sr(make_fused(s_hdr.div));
         for (uint32_t i = threadIdx.x; i < nb_pad; i += blockDim.x) {
             const uint4 e = i < nb ? gl[i] : make_uint4(total, total, total, 0u);  // empty interval: never verifies
             sl[i] = e;
@@ -407,9 +409,10 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
     if constexpr (FUSED) {
         const FusedParams fp = make_fused(div);
         uint64_t rpt = fused_rpt<MODE>(rg, fp);
-        const uint32_t sr = CSM ? 0u : fused_sr(fp);
-        auto q_of = [&](uint64_t r) -> float { return CSM ? lut_q_gen(r) : lut_q(r, sr); };  // 1 / float(rpt >> sr)
-        auto range_of = [&](uint64_t r) -> uint64_t { return CSM ? r * (uint64_t)div.total : r << fp.s; };
+        const uint32_t sr = GENM ? 0u : fused_sr(fp);
+        auto q_of = [&](uint64_t r) -> float { return GENM ? lut_q_gen(r) : lut_q(r, sr); };  // 1 / float(rpt >> sr)
+        auto range_of = [&](uint64_t r) -> uint64_t { return GENM ? r * (uint64_t)div.total : r << fp.s; };
+        const Recip2 k2 = M2M ? make_recip2(div.total) : Recip2{0ull, 0u};
         float q = q_of(rpt);
         float bf = lut_bf16_init(sink.data() - lo, rg, lut_scale);     // byte offset of the next entry
         const uint32_t lut_saddr = (uint32_t)__cvta_generic_to_shared(s_lut);
@@ -430,6 +433,8 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
                     const LutEntry k = lds_lut(cs_saddr + off);  // {csA lo, csA hi, csB lo, csB hi}
                     r = fused_decode_step_cs(lo, rpt, data, e, ((uint64_t)k.cumB << 32) | k.cumA,
                                              ((uint64_t)k.syms << 32) | k.cumC);
+                } else if constexpr (M2M) {
+                    r = fused_decode_step_m2(lo, rpt, data, e, k2);
                 } else {
                     r = fused_decode_step<MODE>(lo, rpt, data, e, fp);
                 }

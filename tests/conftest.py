@@ -64,6 +64,8 @@ def hostcore():
     L.hc_check_division.argtypes = [vp, u64, u32]
     L.hc_check_cs.restype = u64
     L.hc_check_cs.argtypes = [vp, vp, vp, u64, u32, vp]
+    L.hc_check_m2.restype = u64
+    L.hc_check_m2.argtypes = [vp, vp, u64, u32, vp]
     return L
 
 

@@ -251,8 +251,10 @@ extern "C" int64_t hc_decode(const uint8_t* stream, uint64_t off0, uint64_t off1
             if (mode == FUSE_BIG) r = fused_decode_step<FUSE_BIG>(lo, rpt, data, e, fp);
             else if (mode == FUSE_POW2) r = fused_decode_step<FUSE_POW2>(lo, rpt, data, e, fp);
             else {
-                r = fused_decode_step_cs(lo, rpt, data, e, recip_of_freq(e.cumB - e.cumA, total),
-                                         recip_of_freq(e.cumC - e.cumB, total));
+                // decode_kernel: table-wide constant for totals >= 2^25, per-candidate constants below
+                if (recip2_ok(total)) r = fused_decode_step_m2(lo, rpt, data, e, make_recip2(total));
+                else r = fused_decode_step_cs(lo, rpt, data, e, recip_of_freq(e.cumB - e.cumA, total),
+                                              recip_of_freq(e.cumC - e.cumB, total));
                 if (r.ok && r.nrpt != (r.rgp << r.sh) / total) return -2;  // exactness test passed a wrong quotient
             }
             uint32_t sym;
@@ -343,6 +345,27 @@ extern "C" uint64_t hc_check_cs(const uint64_t* rpts, const uint32_t* cs_c, cons
         uint64_t nrpt;
         if (fused_rpt_cs(rpt, recip_of_freq(c, total), sh, nrpt)) {
             if (nrpt != (uint64_t)x / total) wrong++;
+        } else {
+            inexact++;
+        }
+    }
+    if (n_inexact) *n_inexact = inexact;
+    return wrong;
+}
+
+// fused_rpt_m2 (table-wide constant, totals >= 2^25): same contract as hc_check_cs, on range' directly.
+extern "C" uint64_t hc_check_m2(const uint64_t* rgps, const uint32_t* shs, uint64_t n, uint32_t total,
+                                uint64_t* n_inexact) {
+    if (!recip2_ok(total)) return ~0ull;
+    const Recip2 k = make_recip2(total);
+    uint64_t wrong = 0, inexact = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint64_t rgp = rgps[i];
+        const uint32_t sh = shs[i];
+        if ((((unsigned __int128)rgp) << sh) >> 64) continue;  // outside the step's preconditions
+        uint64_t nrpt;
+        if (fused_rpt_m2(rgp, sh, k, nrpt)) {
+            if (nrpt != (rgp << sh) / total) wrong++;
         } else {
             inexact++;
         }

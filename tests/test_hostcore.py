@@ -227,3 +227,26 @@ def test_divide_free_rpt_is_exact_or_flagged(hostcore, total):
     assert wrong == 0
     if total >= 1 << 20:
         assert inexact.value < max(3, r2.size * 2e-5)
+
+
+@pytest.mark.parametrize("total", [(1 << 25) + 1, (1 << 26) - 1, (1 << 30) - 125, (1 << 30) + 12345, (1 << 31) + 1,
+                                   0xFFFFFFFF, 0xFFFFFFFE, 3 << 29, 1_000_000_007])
+def test_table_wide_reciprocal_is_exact_or_flagged(hostcore, total):
+    """fused_rpt_m2 (decoder, totals >= 2^25): a passing test comes with floor((range' << sh) / total);
+    inputs are post-symbol ranges at every legal shift plus ranges on exact multiples of total."""
+    rng = np.random.default_rng(total % 7919)
+    n = 400_000
+    sh = (rng.integers(0, 4, size=n) * 8).astype(np.uint32)
+    x = rng.integers(1 << 48, (1 << 64) - 1, size=n, dtype=np.uint64, endpoint=True)  # range' << sh
+    rgp = x >> sh.astype(np.uint64)
+    k = rng.integers(1 << 17, ((1 << 64) - 1) // total, size=3000, dtype=np.uint64)
+    mult = k * np.uint64(total)
+    rgps = np.concatenate([rgp, mult, mult - np.uint64(1), mult + np.uint64(1)])
+    shs = np.concatenate([sh, np.zeros(9000, np.uint32)])
+    inexact = ctypes.c_uint64()
+    assert hostcore.hc_check_m2(_p(rgps), _p(shs), rgps.size, total, ctypes.byref(inexact)) == 0
+    w = hostcore.hc_check_m2(_p(rgp), _p(sh), n, total, ctypes.byref(inexact))
+    assert w == 0
+    l = total.bit_length() - 1
+    # flagged share: 2^-(l - sh) per symbol, uniform sh here -> dominated by sh = 24
+    assert inexact.value < n * (2.0 ** -(l - 24)) * 0.5 + 50

@@ -6,9 +6,16 @@ import sys
 import collections
 
 rows = list(csv.reader(open(sys.argv[1])))
-hdr = rows[1]
+# the export holds one section per kernel: a "Kernel Name" line, a header line, then the instructions;
+# argv[3] (default 0) picks the section
+starts = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name']
+which = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+lo = starts[which]
+hi = starts[which + 1] if which + 1 < len(starts) else len(rows)
+print(rows[lo][1][:100])
+hdr = rows[lo + 1]
 ix = {h: i for i, h in enumerate(hdr)}
-data = rows[2:]
+data = [r for r in rows[lo + 2:hi] if len(r) >= len(hdr) - 1]
 ie = [int(r[ix['Instructions Executed']] or 0) for r in data]
 mx = max(ie)
 tot = sum(int(r[ix['# Samples']] or 0) for r in data)
