@@ -614,8 +614,10 @@ static EncPlan plan_encode(const rcb_ctx* c, const rcb_model* m, uint64_t n_chun
         const bool pow2 = (m->h_hdr0.flags & MODEL_POW2) != 0;
         // general totals: the divide-free step needs cs = floor(c * 2^64 / total) < 2^64, i.e. no c == total
         const bool gencs = !pow2 && !(m->h_hdr0.flags & MODEL_FULLC) && !getenv("RCB_NO_GENCS");
+        const bool genm2 = !pow2 && recip2_ok(m->h_hdr0.div.total) && !getenv("RCB_NO_M2");  // table-wide reciprocal
         p.fmode = p.checked ? FM_GENERIC
-                            : (pow2 ? (m->h_hdr0.div.shift >= 24 ? FM_BIG : FM_POW2) : (gencs ? FM_GENCS : FM_GEN));
+                            : (pow2 ? (m->h_hdr0.div.shift >= 24 ? FM_BIG : FM_POW2)
+                                    : (genm2 ? FM_GENM2 : (gencs ? FM_GENCS : FM_GEN)));
         p.lanes = (uint32_t)p.threads;
         p.smem = (((size_t)m->K * (p.fmode == FM_GENCS ? sizeof(uint4) : sizeof(uint2)) + 15) & ~(size_t)15);
         if (p.fmode != FM_GENERIC) p.smem += (size_t)p.threads * ENC_RING_STRIDE;  // per-lane input rings
@@ -666,6 +668,7 @@ static void launch_encode_variant(rcb_ctx* c, const rcb_model* m, const EncodeAr
             case FM_POW2: launch_encode_rc<SYM, TAB_SHARED, FM_POW2, false>(c, a, p, blocks, rangechk); break;
             case FM_GEN: launch_encode_rc<SYM, TAB_SHARED, FM_GEN, false>(c, a, p, blocks, rangechk); break;
             case FM_GENCS: launch_encode_rc<SYM, TAB_SHARED, FM_GENCS, false>(c, a, p, blocks, rangechk); break;
+            case FM_GENM2: launch_encode_rc<SYM, TAB_SHARED, FM_GENM2, false>(c, a, p, blocks, rangechk); break;
             default: launch_encode_rc<SYM, TAB_SHARED, FM_GENERIC, true>(c, a, p, blocks, rangechk); break;
         }
     } else if (p.table == TAB_LANE) {

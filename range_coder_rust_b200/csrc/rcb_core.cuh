@@ -442,6 +442,20 @@ RCB_HD bool fused_step_cs(uint64_t lo, uint64_t rpt, uint32_t cum, uint32_t c, u
     return exact & (hi32(rgp) >= need);
 }
 
+// ... and with the table-wide constant (totals >= 2^25)
+RCB_HD bool fused_step_m2(uint64_t lo, uint64_t rpt, uint32_t cum, uint32_t c, const Recip2& k,
+                          uint64_t& nlo, uint64_t& rgp, uint64_t& nrpt, uint32_t& sh) {
+    nlo = mad64x32(rpt, cum, lo);
+    const uint64_t up = mad64x32(rpt, cum + c, lo);
+    rgp = mad64x32(rpt, c, 0ull);
+    const uint32_t xh = hi32(nlo) ^ hi32(up);
+    const bool p1 = xh < (1u << 24), p2 = xh < (1u << 16), p3 = xh < (1u << 8);
+    sh = p2 ? (p3 ? 24u : 16u) : (p1 ? 8u : 0u);
+    const bool exact = fused_rpt_m2(rgp, sh, k, nrpt);
+    const uint32_t need = p2 ? 1u : (p1 ? (1u << 8) : (1u << 16));  // see fused_step
+    return exact & (hi32(rgp) >= need);
+}
+
 // ---------------------------------------------------------------------------
 // Decoder input window (src/decoder.rs:9,31-35).  (dh:dl) is `data`, aligned
 // with lower_bound; (wh:wl) holds the following bytes left-aligned with `cnt`

@@ -38,7 +38,9 @@ namespace rcb {
 enum : int { TAB_SHARED = 0, TAB_LANE = 1, TAB_GLOBAL = 2 };
 // FM_GENCS: general total with the divide-free step (each table entry carries cs = floor(c * 2^64 / total),
 // rcb_core.cuh: fused_step_cs); TAB_SHARED only.  FM_GEN keeps the multiply-high reciprocal.
-enum : int { FM_GENERIC = -1, FM_BIG = FUSE_BIG, FM_POW2 = FUSE_POW2, FM_GEN = FUSE_GEN, FM_LANE = 3, FM_GENCS = 4 };
+// FM_GENM2: general total >= 2^25 with the table-wide reciprocal (fused_step_m2); plain {cum, c} table.
+enum : int { FM_GENERIC = -1, FM_BIG = FUSE_BIG, FM_POW2 = FUSE_POW2, FM_GEN = FUSE_GEN, FM_LANE = 3, FM_GENCS = 4,
+             FM_GENM2 = 5 };
 
 struct EncodeArgs {
     const void* syms;
@@ -172,6 +174,7 @@ __global__ void __launch_bounds__(512, 1) encode_kernel(EncodeArgs a) {
     const uint64_t block_first = (uint64_t)blockIdx.x * L;
     // shared layout: table (TAB_SHARED: uint2[K]; TAB_LANE: u32[L][K+1]) | input rings[blockDim.x] (fused loops)
     constexpr bool CS = FMODE == FM_GENCS;
+    constexpr bool M2 = FMODE == FM_GENM2;
     static_assert(!CS || TABLE == TAB_SHARED, "FM_GENCS needs the shared table");
     const uint32_t ring_off = TABLE == TAB_SHARED ? ((K * (CS ? 16u : 8u) + 15u) & ~15u)
                               : TABLE == TAB_LANE ? ((L * (K + 1u) * 4u + 15u) & ~15u)
@@ -305,6 +308,7 @@ __global__ void __launch_bounds__(512, 1) encode_kernel(EncodeArgs a) {
                 // per vector (16 symbols x at most 15 bytes + the deferred emission < 320 bytes)
                 EncSink<RowStore, false> fs(rs, cap);
                 const FusedParams fp = make_fused(div);
+                const Recip2 k2 = M2 ? make_recip2(div.total) : Recip2{0ull, 0u};
                 uint32_t em_hi = 0, em_sh = 0;  // previous symbol's bytes, emitted one symbol late
                 uint64_t rpt;
                 // one flavour of the word coder per division mode (FM_LANE picks per lane at run time)
@@ -322,6 +326,8 @@ __global__ void __launch_bounds__(512, 1) encode_kernel(EncodeArgs a) {
                             if constexpr (CS)
                                 ok = fused_step_cs(lo, rpt, en.e[b].x, en.e[b].y,
                                                    ((uint64_t)en.e[b].w << 32) | en.e[b].z, nlo, rgp, nrpt, sh);
+                            else if constexpr (M2)
+                                ok = fused_step_m2(lo, rpt, en.e[b].x, en.e[b].y, k2, nlo, rgp, nrpt, sh);
                             else
                                 ok = fused_step<MODE>(lo, rpt, en.e[b].x, en.e[b].y, fp, nlo, rgp, nrpt, sh);
                             fs.put(em_hi, em_sh);
@@ -373,7 +379,7 @@ __global__ void __launch_bounds__(512, 1) encode_kernel(EncodeArgs a) {
                 if constexpr (FMODE == FM_LANE) {
                     if (pow2) run(std::integral_constant<int, FUSE_POW2>{});
                     else run(std::integral_constant<int, FUSE_GEN>{});
-                } else if constexpr (CS) {
+                } else if constexpr (CS || M2) {
                     run(std::integral_constant<int, FUSE_GEN>{});
                 } else {
                     run(std::integral_constant<int, FMODE>{});

@@ -149,6 +149,34 @@ extern "C" int64_t hc_encode(const uint8_t* syms, uint64_t n, int sym_bytes, uin
         if (pow2) return run(std::integral_constant<int, FUSE_POW2>{});
         bool full = false;  // a symbol with c == total has no reciprocal constant (plan_encode: FM_GEN)
         for (uint32_t i = 0; i < K; i++) full |= c[i] == total;
+        if (recip2_ok(total)) {  // table-wide reciprocal (mirrors encode_kernel's FM_GENM2 instantiation)
+            const Recip2 k2 = make_recip2(total);
+            uint64_t rpt = fused_rpt<FUSE_GEN>(rg, fp);
+            for (uint64_t i = 0; i < n; i++) {
+                uint32_t s = load_sym(syms, i, sym_bytes);
+                if (s >= K) {
+                    if (!err) err = ST_SYMBOL_RANGE;
+                    s = 0;
+                }
+                uint64_t nlo, rgp, nrpt;
+                uint32_t sh;
+                if (fused_step_m2(lo, rpt, cum[s], c[s], k2, nlo, rgp, nrpt, sh)) {
+                    if (nrpt != (rgp << sh) / total) return -2;
+                    sink.put((uint32_t)(nlo >> 32), sh);
+                    lo = nlo << sh;
+                    rpt = nrpt;
+                } else {
+                    lo = nlo;
+                    rg = rgp;
+                    renorm_slow<false>(lo, rg, sink, err);
+                    rpt = fused_rpt<FUSE_GEN>(rg, fp);
+                }
+            }
+            uint32_t len = sink.finish(lo);
+            if (!err && sink.overflowed()) err = ST_OUT_CAPACITY;
+            *status = err;
+            return (int64_t)len;
+        }
         if (full) return run(std::integral_constant<int, FUSE_GEN>{});
         // divide-free general total (mirrors encode_kernel's FM_GENCS instantiation)
         std::vector<uint64_t> cs(K);
