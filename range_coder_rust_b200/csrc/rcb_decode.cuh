@@ -133,6 +133,14 @@ struct RingFill {
         else
             resync(f);
     }
+    // Before an unclean word is re-decoded from its checkpoint (f.rd restored by the caller).
+    __device__ __forceinline__ void redo_ready(RingFetch& f) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (RCB_LIKELY((int32_t)(wr * 16 - f.rd * 4) >= 64 || wr >= npieces))
+            f.reload();
+        else
+            resync(f);
+    }
     // (Re)start after the read position moved arbitrarily (initial fill, exact path past the ring).
     __device__ __forceinline__ void resync(RingFetch& f) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -467,10 +475,12 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
             sink.wl = chk.wl;
             sink.cnt = chk.cnt;
             sink.f.rd = chk.rd;
-            // ring filled to the brim and landed (>= 112 bytes from the checkpoint; this word consumes at
-            // most ~52), current word reloaded: the invariant of round() holds again however many unclean
-            // words follow each other
-            fill.resync(sink.f);
+            // Everything requested has landed (the newest piece was issued a whole word ago: no wait in
+            // practice).  The re-decode reads at most 4 x 14 bytes beyond the checkpoint, so with >= 64 bytes
+            // in the ring it needs no new piece -- and no round trip to memory; otherwise (a run of unclean
+            // words, the start of a chunk) fill the ring to the brim first.  Either way the invariant of
+            // round1() (enough landed bytes for a clean word) holds again afterwards.
+            fill.redo_ready(sink.f);
             uint32_t acc = 0;
 #pragma unroll 1
             for (uint32_t b = 0; b < PER; b++) {
