@@ -594,10 +594,42 @@ extern "C" uint64_t rcb_encode_bound(rcb_ctx* c, const rcb_model* m, uint64_t n_
 }
 
 // Launch geometry and kernel flavour of one encode call.
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// [n_rows][row_bytes] bytes, box {64 bytes, 32 rows}, 64-byte swizzle, 256-byte L2 promotion
+static bool make_symbol_tensor_map(CUtensorMap* tm, const void* base, uint64_t row_bytes, uint64_t n_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || row_bytes % 16 || row_bytes >= (1ull << 32) || n_rows == 0 || n_rows >= (1ull << 32)) return false;
+    const cuuint64_t dims[2] = {row_bytes, n_rows};
+    const cuuint64_t strides[1] = {row_bytes};
+    const cuuint32_t box[2] = {TMA_BOX_BYTES, 32};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 struct EncPlan {
     int table;      // TAB_*
     int fmode;      // FM_*
     bool checked;
+    bool tma;       // symbols staged by TMA (encode_tma_kernel)
     int threads;
     uint32_t lanes; // chunks per block
     size_t smem;
@@ -605,6 +637,7 @@ struct EncPlan {
 
 static EncPlan plan_encode(const rcb_ctx* c, const rcb_model* m, uint64_t n_chunks) {
     EncPlan p;
+    p.tma = false;
     const bool shared = m->n_models == 1;
     p.checked = (m->bad_bits & 4u) != 0;
     const bool regular = (m->bad_bits & 8u) == 0;
@@ -658,10 +691,29 @@ static void launch_encode_rc(rcb_ctx* c, const EncodeArgs& a, const EncPlan& p, 
     else go(encode_kernel<SYM, TABLE, FMODE, CHECKED, false>);
 }
 
+template <typename SYM, int FMODE>
+static void launch_encode_tma(rcb_ctx* c, const EncodeArgs& a, const EncPlan& p, unsigned blocks, bool rangechk,
+                              const CUtensorMap& tm) {
+    auto go = [&](auto kern) {
+        if (p.smem > 48 * 1024)
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+        kern<<<blocks, p.threads, p.smem, c->stream>>>(a, tm);
+    };
+    if (rangechk) go(encode_tma_kernel<SYM, FMODE, true>);
+    else go(encode_tma_kernel<SYM, FMODE, false>);
+}
+
 template <typename SYM>
 static void launch_encode_variant(rcb_ctx* c, const rcb_model* m, const EncodeArgs& a, const EncPlan& p,
                                   unsigned blocks) {
     const bool rangechk = (uint64_t)m->K < (1ull << (8 * sizeof(SYM)));
+    if (p.tma) {
+        CUtensorMap tm;
+        if (make_symbol_tensor_map(&tm, a.syms, a.chunk_syms * sizeof(SYM), a.n_chunks)) {
+            if (p.fmode == FM_BIG) return launch_encode_tma<SYM, FM_BIG>(c, a, p, blocks, rangechk, tm);
+            if (p.fmode == FM_GENM2) return launch_encode_tma<SYM, FM_GENM2>(c, a, p, blocks, rangechk, tm);
+        }
+    }
     if (p.table == TAB_SHARED) {
         switch (p.fmode) {
             case FM_BIG: launch_encode_rc<SYM, TAB_SHARED, FM_BIG, false>(c, a, p, blocks, rangechk); break;
@@ -701,7 +753,15 @@ static int encode_issue(rcb_ctx* c, const void* d_syms, uint64_t n_syms, int sym
     a.pitch = pitch;
     a.lens = lens;
     a.status = status;
-    const EncPlan plan = plan_encode(c, m, n_chunks);
+    EncPlan plan = plan_encode(c, m, n_chunks);
+    // TMA staging of the symbols (RCB_ENC_TMA=1): shared table, every chunk whole, rows a multiple of 16 bytes
+    if (getenv("RCB_ENC_TMA") && plan.table == TAB_SHARED && (plan.fmode == FM_BIG || plan.fmode == FM_GENM2) &&
+        n_syms % chunk_syms == 0 && (chunk_syms * sym_bytes) % 16 == 0 && chunk_syms * sym_bytes >= 64) {
+        plan.tma = true;
+        const size_t tab = (((size_t)m->K * sizeof(uint2) + 15) & ~(size_t)15);
+        const size_t warps = (size_t)plan.threads / 32;
+        plan.smem = tab + 1024 + warps * TMA_STAGES * TMA_STAGE_BYTES + warps * TMA_STAGES * 8;
+    }
     a.lanes_per_block = plan.lanes;
     const unsigned blocks = (unsigned)((n_chunks + plan.lanes - 1) / plan.lanes);
     if (sym_bytes == 1)

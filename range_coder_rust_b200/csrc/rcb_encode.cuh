@@ -29,11 +29,48 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cuda.h>  // CUtensorMap (type only; the driver entry point is resolved at run time)
+
 #include <type_traits>
 
 #include "rcb_core.cuh"
 
 namespace rcb {
+
+// ---------------------------------------------------------------------------
+// TMA input (encode_tma_kernel): the symbols are a 2-D tensor [n_chunks][chunk_bytes] of bytes and a
+// warp's 32 lanes consume vector i of their 32 consecutive rows at the same time, so ONE
+// cp.async.bulk.tensor.2d per warp fetches a {64 bytes x 32 rows} box -- four vectors for every lane -- into
+// a 2 KiB stage, completion on an mbarrier; TMA_STAGES stages per warp.  The box lands with the 64-byte
+// swizzle (16-byte chunk index ^= row/2 mod 4), which makes the lanes' 16-byte reads conflict-free.
+// ---------------------------------------------------------------------------
+constexpr uint32_t TMA_STAGES = 4;
+constexpr uint32_t TMA_BOX_BYTES = 64;
+constexpr uint32_t TMA_STAGE_BYTES = TMA_BOX_BYTES * 32;
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra W_%=;\n\t}"
+        :
+        : "r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, uint32_t x, uint32_t y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :
+        : "r"(dst), "l"(tmap), "r"(bar), "r"(x), "r"(y)
+        : "memory");
+}
 
 enum : int { TAB_SHARED = 0, TAB_LANE = 1, TAB_GLOBAL = 2 };
 // FM_GENCS: general total with the divide-free step (each table entry carries cs = floor(c * 2^64 / total),
@@ -165,10 +202,11 @@ __device__ __noinline__ EncWordState enc_word_exact(EncWordState s, EncEntries<S
     return s;
 }
 
-template <typename SYM, int TABLE, int FMODE, bool CHECKED, bool RANGECHK>
-__global__ void __launch_bounds__(512, 1) encode_kernel(EncodeArgs a) {
+template <typename SYM, int TABLE, int FMODE, bool CHECKED, bool RANGECHK, bool TMA_IN>
+__device__ __forceinline__ void encode_body(const EncodeArgs& a, const CUtensorMap* tmap) {
     extern __shared__ __align__(16) uint8_t s_raw[];
     __shared__ ModelHdr s_hdr;
+    static_assert(!TMA_IN || (TABLE == TAB_SHARED && FMODE != FM_GENERIC), "TMA input: shared table, fused loop");
     const uint32_t K = a.K;
     const uint32_t L = a.lanes_per_block;
     const uint64_t block_first = (uint64_t)blockIdx.x * L;
@@ -191,6 +229,13 @@ __global__ void __launch_bounds__(512, 1) encode_kernel(EncodeArgs a) {
             for (uint32_t i = threadIdx.x; i < K; i += blockDim.x) s_tab[i] = a.tabs[i];
         }
         if (threadIdx.x == 0) s_hdr = a.hdrs[0];
+        if (TMA_IN) {  // one "full" barrier per stage per warp
+            const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_raw);
+            const uint32_t stages = (sbase + ring_off + 1023u) & ~1023u;
+            const uint32_t bars = stages + (blockDim.x >> 5) * TMA_STAGES * TMA_STAGE_BYTES;
+            if (threadIdx.x < (blockDim.x >> 5) * TMA_STAGES) mbar_init(bars + threadIdx.x * 8u, 1u);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // inits visible to the async proxy
+        }
         __syncthreads();
     }
     if (TABLE == TAB_LANE) {
@@ -296,13 +341,45 @@ __global__ void __launch_bounds__(512, 1) encode_kernel(EncodeArgs a) {
                 // ring prologue: pieces 0 .. AHEAD-1, one commit group each
                 const uint32_t ring =
                     (uint32_t)__cvta_generic_to_shared(s_raw + ring_off + (size_t)threadIdx.x * ENC_RING_STRIDE);
+                // TMA input: this warp's stages and barriers, the lane's swizzled slot inside a stage
+                const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+                const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_raw);
+                const uint32_t stages0 = (sbase + ring_off + 1023u) & ~1023u;
+                const uint32_t my_stages = stages0 + warp * TMA_STAGES * TMA_STAGE_BYTES;
+                const uint32_t my_bars = stages0 + (blockDim.x >> 5) * TMA_STAGES * TMA_STAGE_BYTES + warp * TMA_STAGES * 8u;
+                const uint32_t row0 = (uint32_t)(chunk - lane);              // first chunk (tensor row) of this warp
+                const uint32_t ncol = (uint32_t)((nvec + 3) >> 2);           // 64-byte columns of the row
+                const uint32_t lane_off = lane * TMA_BOX_BYTES, lane_swz = (lane >> 1) & 3u;
+                const unsigned wmask = TMA_IN ? __activemask() : 0u;
+                uint32_t issued = 0;  // columns requested so far (lane 0 issues; every lane counts)
+                auto tma_issue = [&](uint32_t col) {
+                    const uint32_t st = col & (TMA_STAGES - 1);
+                    if (lane == 0) {
+                        mbar_expect_tx(my_bars + st * 8u, TMA_STAGE_BYTES);
+                        tma_load_2d(my_stages + st * TMA_STAGE_BYTES, tmap, my_bars + st * 8u, col * TMA_BOX_BYTES, row0);
+                    }
+                };
+                auto tma_wait = [&](uint32_t col) {
+                    mbar_wait(my_bars + (col & (TMA_STAGES - 1)) * 8u, (col / TMA_STAGES) & 1u);
+                };
+                auto tma_vec = [&](uint64_t vi) -> uint4 {  // vector vi of this lane's row
+                    const uint32_t col = (uint32_t)(vi >> 2), k = (uint32_t)vi & 3u;
+                    return lds_v4(my_stages + (col & (TMA_STAGES - 1)) * TMA_STAGE_BYTES + lane_off + ((k ^ lane_swz) << 4));
+                };
+                uint4 cur;
+                if constexpr (TMA_IN) {
+                    for (; issued < TMA_STAGES && issued < ncol; issued++) tma_issue(issued);
+                    tma_wait(0);
+                    cur = tma_vec(0);
+                } else {
 #pragma unroll
-                for (uint32_t q = 0; q < ENC_RING_AHEAD; q++) {
-                    enc_ring_issue(q < nvec, ring + q * 16, v + q);
-                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    for (uint32_t q = 0; q < ENC_RING_AHEAD; q++) {
+                        enc_ring_issue(q < nvec, ring + q * 16, v + q);
+                        asm volatile("cp.async.commit_group;" ::: "memory");
+                    }
+                    asm volatile("cp.async.wait_group %0;" ::"n"(ENC_RING_AHEAD - 1) : "memory");
+                    cur = lds_v4(ring);
                 }
-                asm volatile("cp.async.wait_group %0;" ::"n"(ENC_RING_AHEAD - 1) : "memory");
-                uint4 cur = lds_v4(ring);
                 Entries eA = lookup(cur.x);
                 // fast sink: no capacity test per store; room for a whole vector is checked once
                 // per vector (16 symbols x at most 15 bytes + the deferred emission < 320 bytes)
@@ -354,6 +431,21 @@ __global__ void __launch_bounds__(512, 1) encode_kernel(EncodeArgs a) {
                     };
 #pragma unroll 1
                     for (; i < nvec; i++) {
+                        uint4 nxt;
+                        if constexpr (TMA_IN) {
+                            // the warp leaves together (lane 0 issues the loads the others wait for)
+                            if (__any_sync(wmask, fs.pos + 320u > cap)) break;
+                            const uint32_t k = (uint32_t)i & 3u, col = (uint32_t)(i >> 2);
+                            if (k == 0 && col >= 1) {
+                                // every vector of column col-1 has been consumed (the last one was `cur` of the
+                                // previous trip): its stage takes column col-1+STAGES
+                                __syncwarp(wmask);
+                                if (issued < ncol) tma_issue(issued);
+                                issued += issued < ncol ? 1u : 0u;
+                            }
+                            if (k == 3 && i + 1 < nvec) tma_wait(col + 1);  // vector i+1 opens the next column
+                            nxt = i + 1 < nvec ? tma_vec(i + 1) : make_uint4(0u, 0u, 0u, 0u);
+                        } else {
                         if (fs.pos + 320u > cap) break;  // finish this chunk on the capacity-checked path
                         // request piece i+AHEAD (its slot held piece i-2), retire all but the newest AHEAD-1
                         // groups: pieces <= i+1 have landed
@@ -361,7 +453,8 @@ __global__ void __launch_bounds__(512, 1) encode_kernel(EncodeArgs a) {
                         enc_ring_issue(q < nvec, ring + ((uint32_t)q & (ENC_RING_PIECES - 1)) * 16, v + q);
                         asm volatile("cp.async.commit_group;" ::: "memory");
                         asm volatile("cp.async.wait_group %0;" ::"n"(ENC_RING_AHEAD - 1) : "memory");
-                        const uint4 nxt = lds_v4(ring + (((uint32_t)i + 1u) & (ENC_RING_PIECES - 1)) * 16);
+                        nxt = lds_v4(ring + (((uint32_t)i + 1u) & (ENC_RING_PIECES - 1)) * 16);
+                        }
                         Entries eB = lookup(cur.y);
                         code(eA);
                         eA = lookup(cur.z);
@@ -385,6 +478,13 @@ __global__ void __launch_bounds__(512, 1) encode_kernel(EncodeArgs a) {
                     run(std::integral_constant<int, FMODE>{});
                 }
                 asm volatile("cp.async.wait_all;" ::: "memory");
+                if constexpr (TMA_IN) {
+                    // loads still in flight (an early exit): they must land before the block's shared memory
+                    // can go to another block.
+                    uint32_t seen = (uint32_t)(i >> 2) + 1u;  // columns 0 .. i/4 were waited for
+                    seen = seen < ncol ? seen : ncol;
+                    for (uint32_t cidx = seen; cidx < issued; cidx++) tma_wait(cidx);
+                }
                 sink.pend = fs.pend;
                 sink.nb = fs.nb;
                 sink.pos = fs.pos;
@@ -423,6 +523,17 @@ __global__ void __launch_bounds__(512, 1) encode_kernel(EncodeArgs a) {
     if (!err && sink.overflowed()) err = ST_OUT_CAPACITY;
     a.lens[chunk] = len;
     a.status[chunk] = err;
+}
+
+template <typename SYM, int TABLE, int FMODE, bool CHECKED, bool RANGECHK>
+__global__ void __launch_bounds__(512, 1) encode_kernel(EncodeArgs a) {
+    encode_body<SYM, TABLE, FMODE, CHECKED, RANGECHK, false>(a, nullptr);
+}
+
+// Same coder, symbols staged by TMA (shared table, whole chunks only: the tensor has n_chunks full rows).
+template <typename SYM, int FMODE, bool RANGECHK>
+__global__ void __launch_bounds__(512, 1) encode_tma_kernel(EncodeArgs a, const __grid_constant__ CUtensorMap tmap) {
+    encode_body<SYM, TAB_SHARED, FMODE, false, RANGECHK, true>(a, &tmap);
 }
 
 }  // namespace rcb

@@ -297,6 +297,42 @@ def test_fused_paths_for_general_totals(ctx, oracle, kind):
     assert np.array_equal(dev_to_np(out2, dtype=syms.dtype), syms)
 
 
+@pytest.mark.parametrize("shape", ["u8_64k", "u8_odd_total", "u16_k4096", "tiny_rows", "five_vectors", "many_warps"])
+def test_tma_symbol_staging_matches_oracle(ctx, oracle, shape, monkeypatch):
+    """encode_tma_kernel (RCB_ENC_TMA=1): the symbols reach the lanes through cp.async.bulk.tensor.2d boxes
+    of {64 bytes x 32 rows} instead of per-lane cp.async pieces; same bytes as the oracle.  Shapes cover a
+    partly filled last warp (zero-filled rows), rows of one box column, a row length that is not a multiple
+    of the box, u16 symbols and the general-total flavour."""
+    monkeypatch.setenv("RCB_ENC_TMA", "1")
+    K, sb, chunk, n_chunks, odd = 256, 1, 65536, 70, False
+    if shape == "u8_odd_total":
+        odd = True
+    elif shape == "u16_k4096":
+        K, sb, chunk, n_chunks = 4096, 2, 32768, 45
+    elif shape == "tiny_rows":
+        chunk, n_chunks = 64, 1000
+    elif shape == "five_vectors":
+        chunk, n_chunks = 80, 333
+    elif shape == "many_warps":
+        chunk, n_chunks = 4096, 5000
+    n = chunk * n_chunks
+    syms = oracle.generate(n, K, 0x5EED0001, oracle.zipf_thresholds(K, 1.1), sym_bytes=sb)
+    d_syms = to_dev(ctx, syms)
+    counts = ctx.histogram(d_syms, K)
+    counts += 1  # every symbol codable whatever the sample missed
+    if shape in ("tiny_rows", "five_vectors", "many_warps") or odd:
+        counts[0] += (1 << 26) + 12345  # a general total >= 2^25: the table-wide reciprocal flavour
+    else:
+        counts[0] += (1 << 28) - int(counts.sum().item())  # a power-of-two total >= 2^24
+    model = ctx.model_from_counts(counts)
+    c, cum, total, _ = model.tables()
+    stream, offsets, nbytes = ctx.encode_chunks(d_syms, chunk, model)
+    ref_stream, ref_offsets = oracle.encode_chunks(syms, chunk, c, cum, total)
+    assert_streams_equal(stream, offsets, nbytes, ref_stream, ref_offsets)
+    out = ctx.decode_chunks(stream, offsets, n, chunk, model, sym_bytes=sb)
+    assert np.array_equal(dev_to_np(out, dtype=syms.dtype), syms)
+
+
 def test_slack_total_per_chunk_models(ctx, oracle):
     """Per-chunk tables whose last symbol does not end at total_freq (and the last symbol is coded a
     lot): bytes must match the oracle and decode must return the symbols, through the chunk API."""
