@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(256) finalize_models_kernel(const uint2* __res
         if (e.y && e.y < minc) minc = e.y;
         if (e.y == total) bad |= 8u;
         // shared model: reciprocal constants of the divide-free general-total step (rcb_core.cuh)
-        if (tab_cs && total) {
+        if (tab_cs && total && (total & (total - 1u))) {  // only general totals use them
             const uint64_t r = e.y < total ? recip_of_freq(e.y, total) : ~0ull;
             tab_cs[i] = make_uint2(lo32(r), hi32(r));
         }
@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(256) finalize_models_kernel(const uint2* __res
         e.cumC = cumC;
         e.syms = A | ((B & 0xFFFFu) << 16);
         lut[b] = e;
-        if (lut_cs) {  // cs of the entry's two candidates
+        if (lut_cs && (total & (total - 1u))) {  // cs of the entry's two candidates (general totals)
             const uint32_t cA = cumB - cumA, cB = cumC - cumB;
             const uint64_t ra = cA < total ? recip_of_freq(cA, total) : ~0ull;
             const uint64_t rb = cB < total ? recip_of_freq(cB, total) : ~0ull;
