@@ -251,6 +251,31 @@ int rcb_frame_encode_host(rcb_ctx *ctx, const void *h_syms, uint64_t n_syms, int
 int rcb_frame_decode_host(rcb_ctx *ctx, const uint8_t *h_frame, uint64_t len, void *h_syms_out,
                           uint64_t out_cap_bytes, uint64_t *h_n_syms);
 
+/* ---- adaptive-per-symbol model --------------------------------
+ * The reference takes `&T: PModel` on every call (src/encoder.rs:24,
+ * src/decoder.rs:38): its caller may change the table between symbols.  The
+ * build defines one such model (DESIGN.md section 5 spells out the caller-side
+ * loop it stands for): counts start at 1, the coded symbol
+ * gains `inc` AFTER it was coded, all counts are halved (rounding up) when the
+ * total would pass `limit`; cum_freq = exclusive prefix sum, total_freq = sum.
+ * Every chunk restarts the coder and the table, so chunk i's bytes are what
+ * the reference's Encoder emits for that call sequence on chunk i's symbols.
+ * Device pointers, same conventions as rcb_encode_chunks / rcb_decode_chunks.
+ * Limits of this first path: K <= 4096, K <= limit, limit + inc <= 65535. */
+typedef struct rcb_adaptive_params {
+    uint32_t K;     /* alphabet size */
+    uint32_t inc;   /* added to the coded symbol's count (>= 1) */
+    uint32_t limit; /* halve all counts when total + inc would exceed this */
+} rcb_adaptive_params;
+uint64_t rcb_adaptive_encode_bound(const rcb_adaptive_params *p, uint64_t n_syms, uint64_t chunk_syms);
+int rcb_adaptive_encode_chunks(rcb_ctx *ctx, const void *d_syms, uint64_t n_syms, int sym_bytes,
+                               uint64_t chunk_syms, const rcb_adaptive_params *p, uint8_t *d_out,
+                               uint64_t out_cap, uint64_t *d_offsets, uint32_t *d_status,
+                               uint64_t *h_out_bytes);
+int rcb_adaptive_decode_chunks(rcb_ctx *ctx, const uint8_t *d_stream, const uint64_t *d_offsets,
+                               uint64_t n_syms, int sym_bytes, uint64_t chunk_syms,
+                               const rcb_adaptive_params *p, void *d_syms_out, uint32_t *d_status);
+
 /* ---- multi-GPU: the path's only exchange step -----------------
  * Chunks shard over GPUs with no data-path collective.  A static model shared by
  * chunks on several GPUs needs the sum of the per-GPU count tables -- in the

@@ -262,6 +262,93 @@ int rco_normalise(const uint64_t *counts, uint32_t K, uint32_t *c) {
 }
 
 /* ------------------------------------------------------------------------- */
+/* f4: adaptive-per-symbol table (build-defined; see rc_oracle.h).  Written as the caller-side loop  */
+/* of the reference API: the table is a FreqTable (examples/sample_impl.rs:10-70) whose counts the     */
+/* caller bumps between Encoder::encode / Decoder::decode calls, calc_cum() after every change.        */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+    uint32_t K, inc, limit, total;
+    uint32_t *c, *cum;
+} adaptive_table;
+
+static int adaptive_init(adaptive_table *t, uint32_t K, uint32_t inc, uint32_t limit) {
+    if (K == 0 || inc == 0 || limit < K || (uint64_t)limit + inc > 0xFFFFFFFFull) return -1;
+    t->K = K;
+    t->inc = inc;
+    t->limit = limit;
+    t->c = (uint32_t *)malloc(sizeof(uint32_t) * K);
+    t->cum = (uint32_t *)malloc(sizeof(uint32_t) * K);
+    if (!t->c || !t->cum) return -1;
+    for (uint32_t i = 0; i < K; i++) t->c[i] = 1; /* every symbol codable from the start */
+    t->total = rco_calc_cum(t->c, K, t->cum);
+    return 0;
+}
+static void adaptive_free(adaptive_table *t) {
+    free(t->c);
+    free(t->cum);
+}
+/* after symbol s was coded with the old table */
+static void adaptive_update(adaptive_table *t, uint32_t s) {
+    t->c[s] += t->inc;
+    if ((uint64_t)t->total + t->inc > t->limit)
+        for (uint32_t i = 0; i < t->K; i++) t->c[i] = (t->c[i] + 1) >> 1; /* stays >= 1 */
+    t->total = rco_calc_cum(t->c, t->K, t->cum); /* examples/sample_impl.rs:61-69 */
+}
+
+int64_t rco_adaptive_encode(const void *syms, uint64_t n, int sym_bytes, uint32_t K, uint32_t inc,
+                            uint32_t limit, uint8_t *out, uint64_t cap) {
+    adaptive_table t;
+    if (adaptive_init(&t, K, inc, limit)) return RCO_ERR_ZERO_TOTAL;
+    rco_range_coder rc;
+    rco_rc_new(&rc);
+    uint64_t len = 0;
+    uint8_t tmp[16];
+    int64_t ret = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        uint32_t index = load_sym(syms, i, sym_bytes);
+        if (index >= K) { ret = RCO_ERR_SYMBOL_RANGE; break; }
+        int k;
+        int e = rco_param_update(&rc, t.c[index], t.cum[index], t.total, tmp, &k); /* src/encoder.rs:27-33 */
+        if (e) { ret = e; break; }
+        if (len + (uint64_t)k > cap) { ret = RCO_ERR_CAPACITY; break; }
+        memcpy(out + len, tmp, (size_t)k);
+        len += (uint64_t)k;
+        adaptive_update(&t, index);
+    }
+    adaptive_free(&t);
+    if (ret) return ret;
+    if (len + 8 > cap) return RCO_ERR_CAPACITY;
+    for (int i = 0; i < 8; i++) out[len++] = left_shift(&rc); /* src/encoder.rs:42-44 */
+    return (int64_t)len;
+}
+
+int64_t rco_adaptive_decode(const uint8_t *code, uint64_t len, uint64_t n_syms, int sym_bytes,
+                            uint32_t K, uint32_t inc, uint32_t limit, void *out_syms) {
+    adaptive_table t;
+    if (adaptive_init(&t, K, inc, limit)) return RCO_ERR_ZERO_TOTAL;
+    rco_decoder d;
+    rco_rc_new(&d.range_coder);
+    d.data = 0;
+    d.buffer = code;
+    d.pos = 0;
+    d.len = len;
+    int e = shift_left_buffer(&d, 8); /* src/decoder.rs:21 */
+    uint8_t tmp[16];
+    for (uint64_t i = 0; i < n_syms && !e; i++) {
+        uint32_t idx = find_index(&d, K, t.cum, t.total); /* examples/sample_impl.rs:27-45 on the live table */
+        int n;
+        e = rco_param_update(&d.range_coder, t.c[idx], t.cum[idx], t.total, tmp, &n);
+        if (e) break;
+        e = shift_left_buffer(&d, n);
+        if (e) break;
+        store_sym(out_syms, i, sym_bytes, idx);
+        adaptive_update(&t, idx);
+    }
+    adaptive_free(&t);
+    return e ? e : (int64_t)d.pos;
+}
+
+/* ------------------------------------------------------------------------- */
 /* chunked multi-thread drivers: "one chunk per thread at a time"            */
 /* ------------------------------------------------------------------------- */
 
@@ -281,6 +368,8 @@ typedef struct {
     const uint64_t *offsets;
     int64_t *res;
     atomic_ullong next;
+    int adaptive; /* f4: table restarts with the chunk and follows the symbols */
+    uint32_t inc, limit;
 } chunk_job;
 
 static void *chunk_worker(void *arg) {
@@ -290,6 +379,16 @@ static void *chunk_worker(void *arg) {
         if (i >= j->n_chunks) break;
         uint64_t first = i * j->chunk_syms;
         uint64_t cnt = j->n - first < j->chunk_syms ? j->n - first : j->chunk_syms;
+        if (j->adaptive) {
+            if (!j->decode)
+                j->res[i] = rco_adaptive_encode(j->syms_in + first * j->sym_bytes, cnt, j->sym_bytes, j->K,
+                                                j->inc, j->limit, j->out + i * j->out_pitch, j->out_pitch);
+            else
+                j->res[i] = rco_adaptive_decode(j->stream + j->offsets[i], j->offsets[i + 1] - j->offsets[i],
+                                                cnt, j->sym_bytes, j->K, j->inc, j->limit,
+                                                j->syms_out + first * j->sym_bytes);
+            continue;
+        }
         const uint32_t *c = j->per_chunk_model ? j->c + i * j->K : j->c;
         const uint32_t *cum = j->per_chunk_model ? j->cum + i * j->K : j->cum;
         uint32_t total = j->per_chunk_model ? j->total[i] : j->total[0];
@@ -455,4 +554,45 @@ void rco_generate(void *out, uint64_t first, uint64_t n, int sym_bytes,
 int rco_hardware_threads(void) {
     long n = sysconf(_SC_NPROCESSORS_ONLN);
     return n > 0 ? (int)n : 1;
+}
+
+int rco_adaptive_encode_chunks(const void *syms, uint64_t n, int sym_bytes, uint64_t chunk_syms,
+                               uint32_t K, uint32_t inc, uint32_t limit, uint8_t *out,
+                               uint64_t out_pitch, int64_t *lens, int n_threads) {
+    chunk_job j;
+    memset(&j, 0, sizeof j);
+    j.adaptive = 1;
+    j.inc = inc;
+    j.limit = limit;
+    j.syms_in = (const uint8_t *)syms;
+    j.n = n;
+    j.sym_bytes = sym_bytes;
+    j.chunk_syms = chunk_syms;
+    j.n_chunks = chunk_syms ? (n + chunk_syms - 1) / chunk_syms : 0;
+    j.K = K;
+    j.out = out;
+    j.out_pitch = out_pitch;
+    j.res = lens;
+    return run_job(&j, n_threads);
+}
+
+int rco_adaptive_decode_chunks(const uint8_t *stream, const uint64_t *offsets, uint64_t n,
+                               int sym_bytes, uint64_t chunk_syms, uint32_t K, uint32_t inc,
+                               uint32_t limit, void *out_syms, int64_t *consumed, int n_threads) {
+    chunk_job j;
+    memset(&j, 0, sizeof j);
+    j.adaptive = 1;
+    j.decode = 1;
+    j.inc = inc;
+    j.limit = limit;
+    j.syms_out = (uint8_t *)out_syms;
+    j.n = n;
+    j.sym_bytes = sym_bytes;
+    j.chunk_syms = chunk_syms;
+    j.n_chunks = chunk_syms ? (n + chunk_syms - 1) / chunk_syms : 0;
+    j.K = K;
+    j.stream = stream;
+    j.offsets = offsets;
+    j.res = consumed;
+    return run_job(&j, n_threads);
 }

@@ -95,6 +95,27 @@ int rco_decode_chunks(const uint8_t *stream, const uint64_t *offsets,
                       const uint32_t *total, int per_chunk_model,
                       void *out_syms, int64_t *consumed, int n_threads);
 
+/* ---- adaptive-per-symbol model (build-defined) -------------------
+ * The reference takes `&T: PModel` on EVERY call (src/encoder.rs:24, src/decoder.rs:38), so a caller may
+ * change the table between symbols; it ships no such model.  The build defines one -- the textbook
+ * adaptive frequency count with periodic halving -- as the caller-side loop it would be in Rust:
+ *     table: c[i] = 1 for i < K; cum = exclusive prefix sum; total = K            (FreqTable + calc_cum)
+ *     for each symbol s:  encoder.encode(&table, s)        with the table as it is BEFORE the update
+ *                         c[s] += inc; if sum(c) > limit { c[i] = (c[i] + 1) >> 1 for all i }; calc_cum()
+ * and the mirror image in the decoder (decode, then the same update).  Requires 1 <= inc, K <= limit,
+ * limit + inc <= 2^32 - 1.  Bytes = exactly what the reference's Encoder emits for that call sequence. */
+int64_t rco_adaptive_encode(const void *syms, uint64_t n, int sym_bytes, uint32_t K, uint32_t inc,
+                            uint32_t limit, uint8_t *out, uint64_t cap);
+int64_t rco_adaptive_decode(const uint8_t *code, uint64_t len, uint64_t n_syms, int sym_bytes,
+                            uint32_t K, uint32_t inc, uint32_t limit, void *out_syms);
+/* chunked drivers (every chunk restarts coder AND table), same conventions as rco_encode_chunks */
+int rco_adaptive_encode_chunks(const void *syms, uint64_t n, int sym_bytes, uint64_t chunk_syms,
+                               uint32_t K, uint32_t inc, uint32_t limit, uint8_t *out,
+                               uint64_t out_pitch, int64_t *lens, int n_threads);
+int rco_adaptive_decode_chunks(const uint8_t *stream, const uint64_t *offsets, uint64_t n,
+                               int sym_bytes, uint64_t chunk_syms, uint32_t K, uint32_t inc,
+                               uint32_t limit, void *out_syms, int64_t *consumed, int n_threads);
+
 /* Synthetic data (not part of the reference).
  * u_j = mix64(seed + j*GOLDEN); r = u_j>>32; table t = (j/chunk_syms) % n_tables;
  * symbol = #{ i in [0,K-1) : thr[t][i] <= r }.  thr rows hold K-1 u32 thresholds

@@ -208,6 +208,45 @@ def decode(code, n, c, cum, total):
     return [d.decode(t) for _ in range(n)]
 
 
+class AdaptiveFreqTable(FreqTable):
+    """f4 (build-defined, see oracle/rc_oracle.h): a FreqTable the caller updates between calls --
+    counts start at 1, the coded symbol gains `inc`, all counts are halved (rounding up) when the total
+    would pass `limit`; calc_cum() after every change (examples/sample_impl.rs:61-69)."""
+
+    def __init__(self, alphabet_count, inc, limit):
+        super().__init__(alphabet_count)
+        assert inc >= 1 and alphabet_count <= limit and limit + inc <= M32
+        self.inc, self.limit = inc, limit
+        self.c = [1] * alphabet_count
+        self.calc_cum()
+
+    def update(self, s):
+        self.c[s] += self.inc
+        if self._total + self.inc > self.limit:
+            self.c = [(x + 1) >> 1 for x in self.c]
+        self.calc_cum()
+
+
+def adaptive_encode(symbols, K, inc, limit):
+    t = AdaptiveFreqTable(K, inc, limit)
+    e = Encoder()
+    for s in symbols:
+        e.encode(t, s)  # the table as it is before the update
+        t.update(s)
+    return bytes(e.finish())
+
+
+def adaptive_decode(code, n, K, inc, limit):
+    t = AdaptiveFreqTable(K, inc, limit)
+    d = Decoder(code)
+    out = []
+    for _ in range(n):
+        s = d.decode(t)
+        t.update(s)
+        out.append(s)
+    return out
+
+
 def sample_impl():
     """examples/sample_impl.rs:72-128 -- returns (table, code, decoded)."""
     test_data = [2, 1, 1, 4, 1, 4, 2, 1, 0, 1, 5, 9, 8, 7, 6, 5]

@@ -62,6 +62,9 @@ SIGNATURES = {
     "rcb_frame_encode_host": (ci, [vp, vp, u64, ci, u64, vp, vp, u64, u64p]),
     "rcb_frame_decode_host": (ci, [vp, vp, u64, vp, u64, u64p]),
     "rcb_generate": (ci, [vp, vp, u64, u64, ci, u32, u64, vp, u32, u64]),
+    "rcb_adaptive_encode_bound": (u64, [vp, u64, u64]),
+    "rcb_adaptive_encode_chunks": (ci, [vp, vp, u64, ci, u64, vp, vp, u64, vp, vp, u64p]),
+    "rcb_adaptive_decode_chunks": (ci, [vp, vp, vp, u64, ci, u64, vp, vp, vp]),
     "rcb_comm_unique_id": (ci, [vp]),
     "rcb_comm_init_rank": (ci, [vp, vp, ci, ci, ctypes.POINTER(vp)]),
     "rcb_comm_init_all": (ci, [ctypes.POINTER(vp), ci, ctypes.POINTER(vp)]),

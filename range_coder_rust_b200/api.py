@@ -67,6 +67,11 @@ class Model:
         return c, cum, total.value, flags.value
 
 
+class AdaptiveParams(ctypes.Structure):
+    """struct rcb_adaptive_params (include/rcb200.h): the adaptive-per-symbol table of SURVEY 8 f4."""
+    _fields_ = [("K", ctypes.c_uint32), ("inc", ctypes.c_uint32), ("limit", ctypes.c_uint32)]
+
+
 class Comm:
     """An NCCL communicator owned by the library (include/rcb200.h, multi-GPU section): the path's only
     exchange step is `Context.allreduce_counts` over it."""
@@ -311,6 +316,37 @@ class Context:
 
     def decode_result(self):
         self._check(self.lib.rcb_decode_result(self.h), "rcb_decode_result")
+
+    # ------------------------------------------- adaptive-per-symbol model (f4)
+    def adaptive_encode_chunks(self, syms, chunk_syms, K, inc=24, limit=60000, out=None, offsets=None, status=None):
+        """Every chunk through Encoder::encode under a table the caller updates after each symbol
+        (counts from 1, +inc for the coded symbol, halving at `limit`; rcb200.h)."""
+        n = syms.numel()
+        sb = self._sym_bytes(syms)
+        p = AdaptiveParams(K, inc, limit)
+        n_chunks = (n + chunk_syms - 1) // chunk_syms
+        if out is None:
+            cap = int(self.lib.rcb_adaptive_encode_bound(ctypes.byref(p), n, chunk_syms))
+            if cap == 0:
+                raise RcbError(_lib.RCB_ERR_UNSUPPORTED, "rcb_adaptive_encode_bound")
+            out = torch.empty(cap + 16, dtype=torch.uint8, device=self.device)
+        if offsets is None:
+            offsets = torch.empty(n_chunks + 1, dtype=torch.int64, device=self.device)
+        nbytes = ctypes.c_uint64()
+        rc = self.lib.rcb_adaptive_encode_chunks(self.h, _ptr(syms), n, sb, chunk_syms, ctypes.byref(p), _ptr(out),
+                                                 out.numel(), _ptr(offsets), _ptr(status), ctypes.byref(nbytes))
+        self._check(rc, "rcb_adaptive_encode_chunks")
+        return out, offsets, int(nbytes.value)
+
+    def adaptive_decode_chunks(self, stream, offsets, n_syms, chunk_syms, K, inc=24, limit=60000, sym_bytes=1, out=None,
+                               status=None):
+        p = AdaptiveParams(K, inc, limit)
+        if out is None:
+            out = torch.empty(n_syms, dtype=torch.uint8 if sym_bytes == 1 else torch.int16, device=self.device)
+        rc = self.lib.rcb_adaptive_decode_chunks(self.h, _ptr(stream), _ptr(offsets), n_syms, sym_bytes, chunk_syms,
+                                                 ctypes.byref(p), _ptr(out), _ptr(status))
+        self._check(rc, "rcb_adaptive_decode_chunks")
+        return out
 
     # ------------------------------------------------- host-buffer entry points
     def encode_host(self, syms_np, chunk_syms, model, out_np=None):

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librcb200.so")
 SOURCES = ["rcb_api.cu"]
-HEADERS = ["rcb_core.cuh", "rcb_kernels.cuh", "rcb_encode.cuh", "rcb_decode.cuh", "rcb_decode_row.cuh", "rcb_stream.cuh", "rcb_comm.cuh", os.path.join("..", "..", "include", "rcb200.h")]
+HEADERS = ["rcb_core.cuh", "rcb_kernels.cuh", "rcb_encode.cuh", "rcb_decode.cuh", "rcb_decode_row.cuh", "rcb_stream.cuh", "rcb_comm.cuh", "rcb_adaptive.cuh", os.path.join("..", "..", "include", "rcb200.h")]
 
 NVCC_FLAGS = [
     "-std=c++17",

@@ -14,6 +14,7 @@
 #include "rcb_kernels.cuh"
 #include "rcb_decode_row.cuh"
 #include "rcb_stream.cuh"
+#include "rcb_adaptive.cuh"
 
 using namespace rcb;
 
@@ -1825,6 +1826,154 @@ extern "C" int rcb_frame_decode_host(rcb_ctx* c, const uint8_t* h_frame, uint64_
     free(offs);
     rcb_model_destroy(m);
     return r;
+}
+
+// ------------------------------------------- adaptive-per-symbol model (f4)
+static bool adaptive_params_ok(const rcb_adaptive_params* p) {
+    return p && p->K >= 1 && p->K <= 4096 && p->inc >= 1 && p->limit >= p->K &&
+           (uint64_t)p->limit + p->inc <= 65535ull;
+}
+
+static uint64_t adaptive_pitch(uint64_t chunk_syms) {
+    // a symbol costs at most log2(total / 1) <= 16 bits, plus the loop-2 truncation (< 1 %) and the flush
+    const uint64_t p = chunk_syms * 2 + chunk_syms / 32 + 96;
+    return (p + 15) & ~15ull;
+}
+
+extern "C" uint64_t rcb_adaptive_encode_bound(const rcb_adaptive_params* p, uint64_t n_syms, uint64_t chunk_syms) {
+    if (!adaptive_params_ok(p) || chunk_syms == 0) return 0;
+    return (n_syms + chunk_syms - 1) / chunk_syms * adaptive_pitch(chunk_syms) + 16;
+}
+
+// lanes per block and the per-lane table pitch (u16 counts[K] + u16 tree[K+1], odd number of words)
+static void adaptive_geometry(const rcb_ctx* c, const rcb_adaptive_params* p, uint64_t n_chunks, size_t ring_bytes,
+                              AdaptiveArgs& a, int& threads, size_t& smem) {
+    uint32_t words = (2 * p->K + 1 + 1) / 2;
+    if ((words & 1u) == 0) words++;
+    const size_t per_lane = (size_t)words * 4 + ring_bytes;
+    uint32_t L = (uint32_t)((200 * 1024) / per_lane);
+    if (L > 512) L = 512;
+    const uint64_t sms = (uint64_t)(c->sm_count > 0 ? c->sm_count : 148);
+    const uint64_t even = (n_chunks + sms - 1) / sms;  // one wave over all SMs when it fits
+    if (even <= L) L = (uint32_t)(even ? even : 1);
+    a.lanes_per_block = L;
+    a.pitch_words = words;
+    threads = (int)((L + 31) / 32 * 32);
+    smem = (size_t)L * words * 4 + (size_t)threads * ring_bytes;
+}
+
+extern "C" int rcb_adaptive_encode_chunks(rcb_ctx* c, const void* d_syms, uint64_t n_syms, int sym_bytes,
+                                          uint64_t chunk_syms, const rcb_adaptive_params* p, uint8_t* d_out,
+                                          uint64_t out_cap, uint64_t* d_offsets, uint32_t* d_status,
+                                          uint64_t* h_out_bytes) {
+    if (!c || !d_offsets || chunk_syms == 0 || (n_syms && !d_syms)) return RCB_ERR_INVALID_ARGUMENT;
+    if (sym_bytes != 1 && sym_bytes != 2) return RCB_ERR_UNSUPPORTED;
+    if (!adaptive_params_ok(p) || (sym_bytes == 1 && p->K > 256)) return RCB_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(d_syms) & 15u) || (reinterpret_cast<uintptr_t>(d_out) & 15u) ||
+        (reinterpret_cast<uintptr_t>(d_offsets) & 7u))
+        return RCB_ERR_INVALID_ARGUMENT;
+    if (chunk_syms > 0x40000000ull) return RCB_ERR_UNSUPPORTED;
+    const uint64_t n_chunks = (n_syms + chunk_syms - 1) / chunk_syms;
+    if (n_chunks > 0x7FFFFFFFull) return RCB_ERR_UNSUPPORTED;
+    ON_DEVICE(c);
+    if (n_chunks == 0) {
+        CK(c, cudaMemsetAsync(d_offsets, 0, sizeof(uint64_t), c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        if (h_out_bytes) *h_out_bytes = 0;
+        return RCB_OK;
+    }
+    int r = ensure_chunks(c, n_chunks);
+    if (r) return r;
+    uint64_t pitch = adaptive_pitch(chunk_syms);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if (pitch > 0xFFFFFFF0ull) return RCB_ERR_UNSUPPORTED;
+        r = ensure_staging(c, (size_t)(n_chunks * pitch + 64));
+        if (r) return r;
+        AdaptiveArgs a;
+        memset(&a, 0, sizeof a);
+        a.K = p->K;
+        a.inc = p->inc;
+        a.limit = p->limit;
+        a.n_syms = n_syms;
+        a.chunk_syms = chunk_syms;
+        a.n_chunks = n_chunks;
+        a.syms = d_syms;
+        a.staging = c->staging;
+        a.pitch = pitch;
+        a.lens = c->lens;
+        a.status = d_status ? d_status : c->status;
+        int threads;
+        size_t smem;
+        adaptive_geometry(c, p, n_chunks, 0, a, threads, smem);
+        const unsigned blocks = (unsigned)((n_chunks + a.lanes_per_block - 1) / a.lanes_per_block);
+        auto go = [&](auto kern) {
+            if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            kern<<<blocks, threads, smem, c->stream>>>(a);
+        };
+        if (sym_bytes == 1) go(adaptive_encode_kernel<uint8_t>);
+        else go(adaptive_encode_kernel<uint16_t>);
+        CK_LAUNCH(c);
+        scan_lengths_kernel<<<1, 1024, 0, c->stream>>>(c->lens, a.status, n_chunks, d_offsets, c->d_summary);
+        CK_LAUNCH(c);
+        gather_kernel<<<(unsigned)n_chunks, 256, 0, c->stream>>>(c->staging, pitch, c->lens, d_offsets, d_out, out_cap);
+        CK_LAUNCH(c);
+        c->pending_out_cap = out_cap;
+        c->pending_offsets = d_offsets;
+        c->pending_n_chunks = n_chunks;
+        uint64_t need = 0;
+        r = encode_result(c, h_out_bytes, &need);
+        if (r == RCB_ERR_OUT_CAPACITY && need && attempt == 0) {
+            pitch = need;  // a staging row was too small for this data: once more with the exact need
+            continue;
+        }
+        return r;
+    }
+    return RCB_ERR_OUT_CAPACITY;
+}
+
+extern "C" int rcb_adaptive_decode_chunks(rcb_ctx* c, const uint8_t* d_stream, const uint64_t* d_offsets,
+                                          uint64_t n_syms, int sym_bytes, uint64_t chunk_syms,
+                                          const rcb_adaptive_params* p, void* d_syms_out, uint32_t* d_status) {
+    if (!c || !d_offsets || chunk_syms == 0) return RCB_ERR_INVALID_ARGUMENT;
+    if (n_syms && (!d_stream || !d_syms_out)) return RCB_ERR_INVALID_ARGUMENT;
+    if (sym_bytes != 1 && sym_bytes != 2) return RCB_ERR_UNSUPPORTED;
+    if (!adaptive_params_ok(p) || (sym_bytes == 1 && p->K > 256)) return RCB_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(d_stream) & 15u) || (reinterpret_cast<uintptr_t>(d_syms_out) & 15u) ||
+        (reinterpret_cast<uintptr_t>(d_offsets) & 7u))
+        return RCB_ERR_INVALID_ARGUMENT;
+    if (chunk_syms > 0x40000000ull || n_syms > (1ull << 62)) return RCB_ERR_UNSUPPORTED;
+    const uint64_t n_chunks = (n_syms + chunk_syms - 1) / chunk_syms;
+    if (n_chunks > 0x7FFFFFFFull) return RCB_ERR_UNSUPPORTED;
+    ON_DEVICE(c);
+    if (n_chunks == 0) return RCB_OK;
+    int r = ensure_chunks(c, n_chunks);
+    if (r) return r;
+    AdaptiveArgs a;
+    memset(&a, 0, sizeof a);
+    a.K = p->K;
+    a.inc = p->inc;
+    a.limit = p->limit;
+    a.n_syms = n_syms;
+    a.chunk_syms = chunk_syms;
+    a.n_chunks = n_chunks;
+    a.stream = d_stream;
+    a.offsets = d_offsets;
+    a.out = d_syms_out;
+    a.status = d_status ? d_status : c->status;
+    int threads;
+    size_t smem;
+    adaptive_geometry(c, p, n_chunks, RING_STRIDE, a, threads, smem);
+    const unsigned blocks = (unsigned)((n_chunks + a.lanes_per_block - 1) / a.lanes_per_block);
+    auto go = [&](auto kern) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<blocks, threads, smem, c->stream>>>(a);
+    };
+    if (sym_bytes == 1) go(adaptive_decode_kernel<uint8_t>);
+    else go(adaptive_decode_kernel<uint16_t>);
+    CK_LAUNCH(c);
+    status_summary_kernel<<<1, 1024, 0, c->stream>>>(a.status, n_chunks, c->d_summary + 4);
+    CK_LAUNCH(c);
+    return rcb_decode_result(c);
 }
 
 // ------------------------------------------------------------------ multi-GPU

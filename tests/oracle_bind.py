@@ -55,6 +55,14 @@ def lib():
         L.rco_encode_chunks.argtypes = [_vp, _u64, _ci, _u64, _u32, _vp, _vp, _vp, _ci, _vp, _u64, _vp, _ci]
         L.rco_decode_chunks.restype = _ci
         L.rco_decode_chunks.argtypes = [_vp, _vp, _u64, _ci, _u64, _u32, _vp, _vp, _vp, _ci, _vp, _vp, _ci]
+        L.rco_adaptive_encode.restype = _i64
+        L.rco_adaptive_encode.argtypes = [_vp, _u64, _ci, _u32, _u32, _u32, _vp, _u64]
+        L.rco_adaptive_decode.restype = _i64
+        L.rco_adaptive_decode.argtypes = [_vp, _u64, _u64, _ci, _u32, _u32, _u32, _vp]
+        L.rco_adaptive_encode_chunks.restype = _ci
+        L.rco_adaptive_encode_chunks.argtypes = [_vp, _u64, _ci, _u64, _u32, _u32, _u32, _vp, _u64, _vp, _ci]
+        L.rco_adaptive_decode_chunks.restype = _ci
+        L.rco_adaptive_decode_chunks.argtypes = [_vp, _vp, _u64, _ci, _u64, _u32, _u32, _u32, _vp, _vp, _ci]
         L.rco_generate.restype = None
         L.rco_generate.argtypes = [_vp, _u64, _u64, _ci, _u32, _u64, _vp, _u32, _u64, _ci]
         L.rco_hardware_threads.restype = _ci
@@ -169,6 +177,59 @@ def decode_chunks(stream, offsets, n_syms, chunk_syms, c, cum, total, sym_bytes=
     if bad:
         first = int(np.argmax(used < 0))
         raise ValueError(f"{bad} chunks failed; chunk {first}: {RCO_ERR.get(int(used[first]), used[first])}")
+    return out, used
+
+
+def adaptive_encode(syms, K, inc, limit, cap=None):
+    """f4: whole Encoder run over a table that follows the symbols (rc_oracle.h)."""
+    syms = np.ascontiguousarray(syms)
+    cap = cap or 16 * syms.size + 64
+    out = np.zeros(cap, dtype=np.uint8)
+    n = lib().rco_adaptive_encode(_p(syms), syms.size, syms.dtype.itemsize, K, inc, limit, _p(out), cap)
+    if n < 0:
+        raise ValueError(RCO_ERR.get(n, str(n)))
+    return out[:n].tobytes()
+
+
+def adaptive_decode(code, n_syms, K, inc, limit, sym_bytes=1):
+    code = np.ascontiguousarray(np.frombuffer(bytes(code), dtype=np.uint8) if not isinstance(code, np.ndarray) else code)
+    out = np.zeros(n_syms, dtype=np.uint8 if sym_bytes == 1 else np.uint16)
+    used = lib().rco_adaptive_decode(_p(code), code.size, n_syms, sym_bytes, K, inc, limit, _p(out))
+    if used < 0:
+        raise ValueError(RCO_ERR.get(used, str(used)))
+    return out, int(used)
+
+
+def adaptive_encode_chunks(syms, chunk_syms, K, inc, limit, threads=None):
+    """(stream, offsets) like encode_chunks; every chunk restarts coder and table."""
+    syms = np.ascontiguousarray(syms)
+    n = syms.size
+    n_chunks = (n + chunk_syms - 1) // chunk_syms
+    pitch = 4 * chunk_syms * syms.dtype.itemsize + 64
+    out = np.zeros(n_chunks * pitch, dtype=np.uint8)
+    lens = np.zeros(n_chunks, dtype=np.int64)
+    bad = lib().rco_adaptive_encode_chunks(_p(syms), n, syms.dtype.itemsize, chunk_syms, K, inc, limit, _p(out), pitch,
+                                           _p(lens), threads or hardware_threads())
+    if bad:
+        raise ValueError(f"{bad} chunks failed")
+    offsets = np.zeros(n_chunks + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum(lens)
+    stream = np.empty(int(offsets[-1]), dtype=np.uint8)
+    for i in range(n_chunks):
+        stream[int(offsets[i]):int(offsets[i + 1])] = out[i * pitch:i * pitch + int(lens[i])]
+    return stream, offsets
+
+
+def adaptive_decode_chunks(stream, offsets, n_syms, chunk_syms, K, inc, limit, sym_bytes=1, threads=None):
+    stream = np.ascontiguousarray(stream, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n_chunks = (n_syms + chunk_syms - 1) // chunk_syms
+    out = np.zeros(n_syms, dtype=np.uint8 if sym_bytes == 1 else np.uint16)
+    used = np.zeros(n_chunks, dtype=np.int64)
+    bad = lib().rco_adaptive_decode_chunks(_p(stream), _p(offsets), n_syms, sym_bytes, chunk_syms, K, inc, limit,
+                                           _p(out), _p(used), threads or hardware_threads())
+    if bad:
+        raise ValueError(f"{bad} chunks failed")
     return out, used
 
 

@@ -762,3 +762,50 @@ def test_comm_two_gpus_share_one_table(oracle):
         k.close()
     for c in ctxs:
         c.close()
+
+
+# ------------------------------------------ f4: adaptive-per-symbol table on the GPU
+@pytest.mark.parametrize("K,inc,limit,chunk,n", [(256, 24, 60000, 65536, 40 * 65536 + 777), (256, 32, 4096, 4096, 300_000),
+                                                  (10, 5, 200, 1000, 123_456), (1000, 24, 65000, 8192, 200_000),
+                                                  (256, 24, 60000, 1, 50), (2, 1, 2, 100, 10_000)])
+def test_adaptive_per_symbol_model_matches_oracle(ctx, oracle, K, inc, limit, chunk, n):
+    """the table changes after every symbol (counts from 1, +inc, halving at `limit`) and
+    restarts with every chunk; rcb_adaptive_encode_chunks / decode_chunks against the oracle's caller-side
+    loop over the reference semantics -- bytes per chunk, symbols back, and the oracle's stream decoded on
+    the GPU."""
+    rng = np.random.default_rng(K + chunk)
+    sb = 2 if K > 256 else 1
+    w = np.arange(1, K + 1, dtype=np.float64) ** -1.2
+    syms = rng.choice(K, size=n, p=w / w.sum()).astype(np.uint16 if sb == 2 else np.uint8)
+    syms[n // 3: n // 2] = K - 1 - syms[n // 3: n // 2]  # moving statistics
+    d_syms = to_dev(ctx, syms)
+    stream, offsets, nbytes = ctx.adaptive_encode_chunks(d_syms, chunk, K, inc, limit)
+    ref_stream, ref_offsets = oracle.adaptive_encode_chunks(syms, chunk, K, inc, limit)
+    assert_streams_equal(stream, offsets, nbytes, ref_stream, ref_offsets)
+    out = ctx.adaptive_decode_chunks(stream, offsets, n, chunk, K, inc, limit, sym_bytes=sb)
+    assert np.array_equal(dev_to_np(out, dtype=syms.dtype), syms)
+    pad = np.zeros(((ref_stream.size + 31) // 16) * 16, dtype=np.uint8)
+    pad[:ref_stream.size] = ref_stream
+    out2 = ctx.adaptive_decode_chunks(to_dev(ctx, pad), to_dev(ctx, ref_offsets.view(np.int64)), n, chunk, K, inc, limit,
+                                      sym_bytes=sb)
+    assert np.array_equal(dev_to_np(out2, dtype=syms.dtype), syms)
+
+
+def test_adaptive_per_symbol_errors(ctx, oracle):
+    import range_coder_rust_b200 as rcb
+    from range_coder_rust_b200 import _lib
+
+    syms = np.array([0, 1, 2, 9, 1], dtype=np.uint8)
+    with pytest.raises(rcb.RcbError) as e:  # symbol >= K
+        ctx.adaptive_encode_chunks(to_dev(ctx, syms), 5, 4, 8, 1000)
+    assert e.value.code == _lib.RCB_ERR_SYMBOL_OUT_OF_RANGE
+    with pytest.raises(rcb.RcbError) as e:  # u16 counters: limit + inc must fit
+        ctx.adaptive_encode_chunks(to_dev(ctx, syms), 5, 16, 100, 65500)
+    assert e.value.code == _lib.RCB_ERR_UNSUPPORTED
+    good = np.arange(200, dtype=np.uint8) % 16
+    stream, offsets, nbytes = ctx.adaptive_encode_chunks(to_dev(ctx, good), 50, 16, 8, 1000)
+    offs = dev_to_np(offsets).copy()
+    offs[-1] -= 2  # truncated last chunk
+    with pytest.raises(rcb.RcbError) as e:
+        ctx.adaptive_decode_chunks(stream, to_dev(ctx, offs), good.size, 50, 16, 8, 1000)
+    assert e.value.code == _lib.RCB_ERR_TRUNCATED_STREAM
