@@ -267,6 +267,63 @@ std::vector<Sym> decode_chunks(Context& ctx, const ModelSnapshot& snap, const En
     return out;
 }
 
+// the table follows the symbols -- what a caller of the reference gets by updating its
+// FreqTable between Encoder::encode calls (`&T` per call, src/encoder.rs:24): counts start at 1, the coded
+// symbol gains `inc`, all counts are halved (rounding up) when the total would pass `limit`.  One
+// independent Encoder + table per chunk.  (rcb_adaptive_encode_chunks works on device buffers.)
+struct AdaptiveFreq {
+    uint32_t K, inc = 24, limit = 60000;
+};
+template <class Sym>
+Encoded adaptive_encode_chunks(Context& ctx, const AdaptiveFreq& m, const std::vector<Sym>& syms, uint64_t chunk_syms) {
+    const rcb_adaptive_params p{m.K, m.inc, m.limit};
+    const uint64_t n = syms.size(), n_chunks = (n + chunk_syms - 1) / chunk_syms;
+    const uint64_t cap = rcb_adaptive_encode_bound(&p, n, chunk_syms);
+    if (!cap) throw RangeCoderPanic(RCB_ERR_UNSUPPORTED, "gpu::adaptive_encode_chunks");
+    void *d_syms = nullptr, *d_out = nullptr, *d_off = nullptr;
+    check(rcb_device_alloc(ctx.handle(), n * sizeof(Sym), &d_syms), "rcb_device_alloc");
+    check(rcb_device_alloc(ctx.handle(), cap, &d_out), "rcb_device_alloc");
+    check(rcb_device_alloc(ctx.handle(), (n_chunks + 1) * 8, &d_off), "rcb_device_alloc");
+    check(rcb_copy_to_device(ctx.handle(), d_syms, syms.data(), n * sizeof(Sym)), "rcb_copy_to_device");
+    uint64_t bytes = 0;
+    const int rc = rcb_adaptive_encode_chunks(ctx.handle(), d_syms, n, (int)sizeof(Sym), chunk_syms, &p, (uint8_t*)d_out,
+                                              cap, (uint64_t*)d_off, nullptr, &bytes);
+    Encoded e;
+    if (rc == RCB_OK) {
+        e.stream.resize(bytes);
+        e.offsets.resize(n_chunks + 1);
+        rcb_copy_to_host(ctx.handle(), e.stream.data(), d_out, bytes);
+        rcb_copy_to_host(ctx.handle(), e.offsets.data(), d_off, (n_chunks + 1) * 8);
+    }
+    rcb_device_free(ctx.handle(), d_syms);
+    rcb_device_free(ctx.handle(), d_out);
+    rcb_device_free(ctx.handle(), d_off);
+    check(rc, "gpu::adaptive_encode_chunks");
+    return e;
+}
+template <class Sym>
+std::vector<Sym> adaptive_decode_chunks(Context& ctx, const AdaptiveFreq& m, const Encoded& e, uint64_t n_syms,
+                                        uint64_t chunk_syms) {
+    const rcb_adaptive_params p{m.K, m.inc, m.limit};
+    const uint64_t n_chunks = (n_syms + chunk_syms - 1) / chunk_syms;
+    const uint64_t padded = (e.stream.size() + 31) & ~uint64_t(15);
+    void *d_st = nullptr, *d_off = nullptr, *d_out = nullptr;
+    check(rcb_device_alloc(ctx.handle(), padded, &d_st), "rcb_device_alloc");
+    check(rcb_device_alloc(ctx.handle(), (n_chunks + 1) * 8, &d_off), "rcb_device_alloc");
+    check(rcb_device_alloc(ctx.handle(), n_syms * sizeof(Sym), &d_out), "rcb_device_alloc");
+    check(rcb_copy_to_device(ctx.handle(), d_st, e.stream.data(), e.stream.size()), "rcb_copy_to_device");
+    check(rcb_copy_to_device(ctx.handle(), d_off, e.offsets.data(), (n_chunks + 1) * 8), "rcb_copy_to_device");
+    std::vector<Sym> out(n_syms);
+    const int rc = rcb_adaptive_decode_chunks(ctx.handle(), (const uint8_t*)d_st, (const uint64_t*)d_off, n_syms,
+                                              (int)sizeof(Sym), chunk_syms, &p, d_out, nullptr);
+    if (rc == RCB_OK) rcb_copy_to_host(ctx.handle(), out.data(), d_out, n_syms * sizeof(Sym));
+    rcb_device_free(ctx.handle(), d_st);
+    rcb_device_free(ctx.handle(), d_off);
+    rcb_device_free(ctx.handle(), d_out);
+    check(rc, "gpu::adaptive_decode_chunks");
+    return out;
+}
+
 // A static table shared by chunks that live on several GPUs, one host thread driving all
 // of them: GPU g owns the chunks [n_chunks*g/G, n_chunks*(g+1)/G).  The frequency table is what the
 // reference's caller builds with FreqTable::add_alphabet_freq over ALL the data + calc_cum

@@ -122,3 +122,67 @@ fn golden_vectors_match_the_reference_crate() {
         std::fs::write(out, serde_json::to_string_pretty(&Value::Array(written)).unwrap()).unwrap();
     }
 }
+
+/// a table the caller updates between calls (`&T` per call, src/encoder.rs:24) -- counts start
+/// at 1, the coded symbol gains `inc` after it was coded, all counts are halved (rounding up) when the total
+/// would pass `limit`; calc_cum after every change (examples/sample_impl.rs:61-69).
+struct AdaptiveTable {
+    t: Table,
+    inc: u32,
+    limit: u32,
+}
+
+impl AdaptiveTable {
+    fn new(k: usize, inc: u32, limit: u32) -> Self {
+        let mut a = AdaptiveTable { t: Table { c: vec![1u32; k], cum: vec![0u32; k], total: 0 }, inc, limit };
+        a.calc_cum();
+        a
+    }
+    fn calc_cum(&mut self) {
+        let mut run = 0u32;
+        for i in 0..self.t.c.len() {
+            self.t.cum[i] = run;
+            run += self.t.c[i];
+        }
+        self.t.total = run;
+    }
+    fn update(&mut self, s: usize) {
+        self.t.c[s] += self.inc;
+        if self.t.total as u64 + self.inc as u64 > self.limit as u64 {
+            for x in self.t.c.iter_mut() {
+                *x = (*x + 1) >> 1;
+            }
+        }
+        self.calc_cum();
+    }
+}
+
+#[test]
+fn adaptive_vectors_match_the_reference_crate() {
+    let path = concat!(env!("CARGO_MANIFEST_DIR"), "/../../tests/golden/adaptive_vectors.json");
+    let vectors: Value = serde_json::from_str(&std::fs::read_to_string(path).unwrap()).unwrap();
+    for v in vectors.as_array().unwrap() {
+        let name = v["name"].as_str().unwrap();
+        let k = v["K"].as_u64().unwrap() as usize;
+        let inc = v["adaptive"]["inc"].as_u64().unwrap() as u32;
+        let limit = v["adaptive"]["limit"].as_u64().unwrap() as u32;
+        let symbols = symbols_of(v, k);
+        let mut table = AdaptiveTable::new(k, inc, limit);
+        let mut encoder = Encoder::new();
+        for &s in &symbols {
+            encoder.encode(&table.t, s); // the table as it is before the update
+            table.update(s);
+        }
+        let code: Vec<u8> = encoder.finish().into_iter().collect();
+        assert_eq!(code.len() as u64, v["code_len"].as_u64().unwrap(), "{}: code length", name);
+        assert_eq!(hex::encode(Sha256::digest(&code)), v["code_sha256"].as_str().unwrap(), "{}: code bytes", name);
+        let mut table = AdaptiveTable::new(k, inc, limit);
+        let mut decoder = Decoder::new(code);
+        for &s in &symbols {
+            let got = decoder.decode(&table.t);
+            assert_eq!(got, s, "{}: round trip", name);
+            table.update(got);
+        }
+        println!("pinned {:24} {:6} symbols (adaptive table)", name, symbols.len());
+    }
+}

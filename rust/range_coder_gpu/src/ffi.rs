@@ -15,6 +15,15 @@ pub struct RcbComm {
 }
 pub const RCB_UNIQUE_ID_BYTES: usize = 128;
 
+/// `rcb_adaptive_params`: counts start at 1, the coded symbol gains `inc`, halving at `limit`.
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct RcbAdaptiveParams {
+    pub k: u32,
+    pub inc: u32,
+    pub limit: u32,
+}
+
 /// `rcb_stream_state`: RangeCoder { lower_bound, range } (src/range_coder.rs:7-12 of the reference)
 /// + Decoder::data (src/decoder.rs:8-12) + bookkeeping.
 #[repr(C)]
@@ -130,6 +139,33 @@ extern "C" {
         d_offsets: *mut u64,
         d_status: *mut u32,
         h_out_bytes: *mut u64,
+    ) -> c_int;
+
+    // adaptive-per-symbol table: device buffers
+    pub fn rcb_adaptive_encode_bound(p: *const RcbAdaptiveParams, n_syms: u64, chunk_syms: u64) -> u64;
+    pub fn rcb_adaptive_encode_chunks(
+        ctx: *mut RcbCtx,
+        d_syms: *const c_void,
+        n_syms: u64,
+        sym_bytes: c_int,
+        chunk_syms: u64,
+        p: *const RcbAdaptiveParams,
+        d_out: *mut u8,
+        out_cap: u64,
+        d_offsets: *mut u64,
+        d_status: *mut u32,
+        h_out_bytes: *mut u64,
+    ) -> c_int;
+    pub fn rcb_adaptive_decode_chunks(
+        ctx: *mut RcbCtx,
+        d_stream: *const u8,
+        d_offsets: *const u64,
+        n_syms: u64,
+        sym_bytes: c_int,
+        chunk_syms: u64,
+        p: *const RcbAdaptiveParams,
+        d_syms_out: *mut c_void,
+        d_status: *mut u32,
     ) -> c_int;
 
     // the path's only exchange step: one NCCL all-reduce of the K u64 counts (include/rcb200.h)

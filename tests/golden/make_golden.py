@@ -96,6 +96,25 @@ def main():
     with open(path, "w") as f:
         json.dump(out, f, indent=1)
     print("wrote", path, len(out), "vectors")
+    # the table follows the symbols (rc_pyref.AdaptiveFreqTable); separate file, same pinning
+    arng = np.random.default_rng(4242)
+    adaptive = []
+    for name, K, inc, limit, n in (("adaptive_k16", 16, 8, 200, 300), ("adaptive_k256", 256, 24, 60000, 3000),
+                                   ("adaptive_k3_tight", 3, 1, 3, 64), ("adaptive_k1000_u16", 1000, 24, 65000, 1500)):
+        w = np.arange(1, K + 1, dtype=np.float64) ** -1.3
+        syms = arng.choice(K, size=n, p=w / w.sum())
+        syms[n // 2:] = K - 1 - syms[n // 2:]
+        code = rc_pyref.adaptive_encode(syms.tolist(), K, inc, limit)
+        assert rc_pyref.adaptive_decode(code, n, K, inc, limit) == syms.tolist()
+        adaptive.append({"name": name, "K": K, "adaptive": {"inc": inc, "limit": limit}, "n_symbols": n,
+                         "symbols_hex": (np.asarray(syms, dtype="<u2").tobytes() if K > 256
+                                         else bytes(int(x) for x in syms)).hex(),
+                         "code_len": len(code), "code_sha256": hashlib.sha256(code).hexdigest(),
+                         "code_hex": code.hex() if len(code) <= 512 else None})
+    apath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "adaptive_vectors.json")
+    with open(apath, "w") as f:
+        json.dump(adaptive, f, indent=1)
+    print("wrote", apath, len(adaptive), "vectors")
 
 
 if __name__ == "__main__":

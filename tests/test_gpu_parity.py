@@ -809,3 +809,17 @@ def test_adaptive_per_symbol_errors(ctx, oracle):
     with pytest.raises(rcb.RcbError) as e:
         ctx.adaptive_decode_chunks(stream, to_dev(ctx, offs), good.size, 50, 16, 8, 1000)
     assert e.value.code == _lib.RCB_ERR_TRUNCATED_STREAM
+
+
+def test_adaptive_golden_vectors_on_gpu(ctx):
+    import hashlib as hl
+
+    for v in json.load(open(os.path.join(ROOT, "tests", "golden", "adaptive_vectors.json"))):
+        K, a = v["K"], v["adaptive"]
+        syms = np.frombuffer(bytes.fromhex(v["symbols_hex"]), dtype="<u2" if K > 256 else np.uint8).copy()
+        stream, offsets, nbytes = ctx.adaptive_encode_chunks(to_dev(ctx, syms), syms.size, K, a["inc"], a["limit"])
+        code = dev_to_np(stream, nbytes).tobytes()
+        assert nbytes == v["code_len"] and hl.sha256(code).hexdigest() == v["code_sha256"], v["name"]
+        out = ctx.adaptive_decode_chunks(stream, offsets, syms.size, syms.size, K, a["inc"], a["limit"],
+                                         sym_bytes=syms.dtype.itemsize)
+        assert np.array_equal(dev_to_np(out, dtype=syms.dtype), syms)

@@ -74,12 +74,30 @@ def run(ctx, name, n_bytes, K, chunk, mode, zipf, reps, odd_total=False):
     torch.cuda.empty_cache()
 
 
+def run_f4(ctx, n_bytes, chunk, reps, inc=24, limit=60000):
+    """the table follows the symbols (counts from 1, +inc, halving at limit), restart per chunk."""
+    K = 256
+    thr = np.stack([rcb.zipf_thresholds(K, s) for s in S_CYCLE])
+    d = ctx.generate(n_bytes, K, 0x5EED0002, thr, sym_bytes=1, chunk_syms=chunk)
+    n_chunks = (n_bytes + chunk - 1) // chunk
+    stream, offsets, nbytes = ctx.adaptive_encode_chunks(d, chunk, K, inc, limit)
+    res = {"config": f"f4: adaptive-per-symbol table, mixed entropy, K=256, chunk {chunk // 1024} KiB", "bytes": n_bytes,
+           "K": K, "chunk_syms": chunk, "model": "per-symbol", "lanes": n_chunks, "ratio": nbytes / n_bytes}
+    res["encode_ms"] = timed(lambda: ctx.adaptive_encode_chunks(d, chunk, K, inc, limit, out=stream, offsets=offsets), reps)
+    back = torch.empty_like(d)
+    res["decode_ms"] = timed(lambda: ctx.adaptive_decode_chunks(stream, offsets, n_bytes, chunk, K, inc, limit, out=back), reps)
+    res["round_trip_ok"] = bool(torch.equal(back, d))
+    res["encode_gbs"] = n_bytes / res["encode_ms"] / 1e6
+    res["decode_gbs"] = n_bytes / res["decode_ms"] / 1e6
+    print(json.dumps(res), flush=True)
+
+
 def main():
     p = argparse.ArgumentParser()
     p.add_argument("--reps", type=int, default=3)
     p.add_argument("--gib", type=float, default=1.0)
     p.add_argument("--big", action="store_true", help="also an 8 GiB many-lane batch (config 5's per-GPU shard)")
-    p.add_argument("--only", default="", help="comma-separated config tags to run (2,3-16,3-64,3-256,4,2b,2c)")
+    p.add_argument("--only", default="", help="comma-separated config tags to run (2,3-16,3-64,3-256,4,2b,2c,f4)")
     a = p.parse_args()
     only = set(x for x in a.only.split(",") if x)
 
@@ -100,6 +118,8 @@ def main():
             odd_total=True)
     if want("2c"):
         run(ctx, "2c: static global table, 16 KiB chunks (65536 lanes)", nb, 256, 16384, "static", 1.1, a.reps)
+    if want("f4"):
+        run_f4(ctx, nb, 65536, a.reps)
     if a.big:
         run(ctx, "5: 8 GiB per-GPU shard, static table, 64 KiB chunks (131072 lanes)", 8 << 30, 256, 65536, "static",
             1.1, max(1, a.reps - 1))
