@@ -12,7 +12,9 @@
  * cannot be run.  The oracle is pinned only by (1) the source semantics cited
  * per function below, (2) the hand-checkable `sample_impl` vector in
  * tests/golden/, (3) an independent pure-Python transliteration
- * (oracle/rc_pyref.py) that must agree byte for byte.
+ * (oracle/rc_pyref.py) that must agree byte for byte.  rust/pin_reference/ is
+ * the one-command pin for anyone with cargo: it runs the unmodified crate over
+ * the same golden vectors (it cannot run here).
  *
  * Citations are path:line under /root/reference/.
  */
