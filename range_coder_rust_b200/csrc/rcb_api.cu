@@ -26,6 +26,7 @@ static_assert((int)RCB_MODEL_REGULAR == (int)MODEL_REGULAR, "model flags");
 #define LUT_CAP 4096u       // buckets of the shared-model decode LUT (64 KiB of shared memory)
 #define MAX_K_SHARED 4096u  // table + LUT must fit 227 KiB of shared memory
 #define MAX_K 65536u
+#define MAX_SLICES 16       // slices of one host batch in flight (rcb_encode_host / rcb_decode_host)
 
 struct rcb_ctx {
     int device = 0;
@@ -48,16 +49,16 @@ struct rcb_ctx {
     uint64_t pending_pitch = 0, pending_out_cap = 0, pending_n_chunks = 0;
     const uint64_t* pending_offsets = nullptr;
     // host-buffer pipeline: slices of one batch on their own streams (copies overlap the coder kernels)
-    cudaStream_t slice_stream[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t slice_stream[MAX_SLICES] = {};
     // all host->device copies of a batch go through one stream and all device->host copies through
     // another, in slice order: copies issued on several streams share the bus and every slice would
     // arrive late; in order, slice k is complete after (k+1)/S of the transfer time
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     DecResume* d_resume = nullptr;  // lane states between the segment launches of rcb_decode_host
     size_t resume_cap = 0;
-    cudaEvent_t in_ready[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t out_ready[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    unsigned long long* d_slice_summary = nullptr;  // [8][8]
+    cudaEvent_t in_ready[MAX_SLICES] = {};
+    cudaEvent_t out_ready[MAX_SLICES] = {};
+    unsigned long long* d_slice_summary = nullptr;  // [MAX_SLICES][8]
     unsigned long long* h_slice_summary = nullptr;  // pinned mirror
     bool timing = false;
     cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -224,7 +225,7 @@ extern "C" int rcb_ctx_destroy(rcb_ctx* c) {
     cudaFree(c->h2d);
     for (int i = 0; i < 7; i++)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-    for (int i = 0; i < 8; i++) {
+    for (int i = 0; i < MAX_SLICES; i++) {
         if (c->slice_stream[i]) cudaStreamDestroy(c->slice_stream[i]);
         if (c->in_ready[i]) cudaEventDestroy(c->in_ready[i]);
         if (c->out_ready[i]) cudaEventDestroy(c->out_ready[i]);
@@ -1140,8 +1141,8 @@ static int ensure_slices(rcb_ctx* c, int n) {
     if (!c->h2d_stream) CK(c, cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
     if (!c->d2h_stream) CK(c, cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
     if (!c->d_slice_summary) {
-        CK(c, cudaMalloc(&c->d_slice_summary, 64 * sizeof(unsigned long long)));
-        CK(c, cudaMallocHost(&c->h_slice_summary, 64 * sizeof(unsigned long long)));
+        CK(c, cudaMalloc(&c->d_slice_summary, MAX_SLICES * 8 * sizeof(unsigned long long)));
+        CK(c, cudaMallocHost(&c->h_slice_summary, MAX_SLICES * 8 * sizeof(unsigned long long)));
     }
     return RCB_OK;
 }
@@ -1167,7 +1168,15 @@ static double now_ms() {
 }
 
 static int pick_slices(uint64_t n_chunks, uint64_t bytes) {
-    int s = 8;
+    // more slices = shorter pipeline fill and drain (the first copy-in and the last copy-out run alone);
+    // a slice still has to be a few MiB so that per-copy overheads stay invisible
+    static int cap = 0;
+    if (!cap) {
+        const char* e = getenv("RCB_MAX_SLICES");
+        cap = e ? atoi(e) : MAX_SLICES;
+        if (cap < 1 || cap > MAX_SLICES) cap = MAX_SLICES;
+    }
+    int s = cap;
     while (s > 1 && (n_chunks / s < 64 || bytes / s < (8u << 20))) s >>= 1;
     return s;
 }
@@ -1214,7 +1223,7 @@ extern "C" int rcb_encode_host(rcb_ctx* c, const void* h_syms, uint64_t n_syms, 
     if (r) return r;
     CK(c, cudaStreamSynchronize(c->stream));
     cudaStream_t user_stream = c->stream;
-    uint64_t first[9];
+    uint64_t first[MAX_SLICES + 1];
     for (int k = 0; k <= S; k++) first[k] = n_chunks * k / S;
     int rc = RCB_OK;
     for (int k = 0; k < S && rc == RCB_OK; k++) {
@@ -1247,7 +1256,7 @@ extern "C" int rcb_encode_host(rcb_ctx* c, const void* h_syms, uint64_t n_syms, 
         }
     }
     uint64_t base = 0;
-    uint64_t bases[8];
+    uint64_t bases[MAX_SLICES];
     bool staging_overflow = false;
     const double t_issue = now_ms();
     if (trace_on()) fprintf(stderr, "[rcb] encode_host: %d slices issued\n", S);
@@ -1372,12 +1381,12 @@ extern "C" int rcb_decode_host(rcb_ctx* c, const uint8_t* h_stream, const uint64
     }
     cudaStream_t user_stream = c->stream;
     int rc = RCB_OK;
-    uint64_t first[9];
+    uint64_t first[MAX_SLICES + 1];
     for (int k = 0; k <= S; k++) first[k] = n_chunks * k / S;
-    cudaEvent_t tr_start = nullptr, tr_k[8][4], tr_c[8][4], tr_in[8];
+    cudaEvent_t tr_start = nullptr, tr_k[MAX_SLICES][4], tr_c[MAX_SLICES][4], tr_in[MAX_SLICES];
     if (trace_on()) {
         cudaEventCreate(&tr_start);
-        for (int k = 0; k < 8; k++) {
+        for (int k = 0; k < MAX_SLICES; k++) {
             cudaEventCreate(&tr_in[k]);
             for (int q = 0; q < 4; q++) {
                 cudaEventCreate(&tr_k[k][q]);
@@ -1473,7 +1482,7 @@ extern "C" int rcb_decode_host(rcb_ctx* c, const uint8_t* h_stream, const uint64
             fprintf(stderr, "\n");
         }
         cudaEventDestroy(tr_start);
-        for (int k = 0; k < 8; k++) {
+        for (int k = 0; k < MAX_SLICES; k++) {
             cudaEventDestroy(tr_in[k]);
             for (int q = 0; q < 4; q++) {
                 cudaEventDestroy(tr_k[k][q]);
