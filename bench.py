@@ -56,9 +56,14 @@ def parse_args():
     p.add_argument("--trace-steps", action="store_true", help="per-step phase times of this rank on stderr")
     p.add_argument("--enc-threads", type=int, default=0)
     p.add_argument("--dec-threads", type=int, default=0)
+    p.add_argument("--restart", type=int, default=-1,
+                   help="restart points every this many symbols of a chunk (several decoder lanes per chunk); "
+                        "0 = none, -1 = a quarter of the chunk")
     a = p.parse_args()
     if a.alphabet > 256 and a.chunk == 65536:
         a.chunk = 32768  # 64 KiB chunks of u16 symbols
+    if a.restart < 0:
+        a.restart = a.chunk // 4 if a.chunk % 256 == 0 else 0
     if a.seed is None:
         a.seed = 0x5EED0002 if a.mode == "adaptive" else (0x5EED0003 if a.alphabet > 256 else 0x5EED0001)
     return a
@@ -390,6 +395,9 @@ def run_ours(a):
     d_stream = torch.empty(cap, dtype=torch.uint8, device=dev)
     d_offsets = torch.empty(n_chunks + 1, dtype=torch.int64, device=dev)
     d_back = torch.empty_like(d_syms)
+    # restart points: the encoder records its state every a.restart symbols, the decoder runs that many more lanes
+    d_restart = ctx.restart_points(n_chunks, chunk, a.restart) if a.restart else None
+    rs_kw = {"restart_syms": a.restart, "restart": d_restart} if d_restart is not None else {}
 
     ev = {k: [] for k in ("start", "hist", "model", "enc", "dec")}
     kern = {"encode_kernel": [], "scan": [], "gather": [], "decode_kernel": []}
@@ -403,9 +411,10 @@ def run_ours(a):
             ctx.allreduce_counts(counts, comm)
         ctx.model_from_counts(counts, model=model)
         e[2].record()
-        ctx.encode_chunks(d_syms, chunk, model, out=d_stream, offsets=d_offsets, sync=False)
+        ctx.encode_chunks(d_syms, chunk, model, out=d_stream, offsets=d_offsets, sync=False, **rs_kw)
         e[3].record()
-        ctx.decode_chunks(d_stream, d_offsets, n_syms, chunk, model, sym_bytes=sym_bytes, out=d_back, sync=False)
+        ctx.decode_chunks(d_stream, d_offsets, n_syms, chunk, model, sym_bytes=sym_bytes, out=d_back, sync=False,
+                          **rs_kw)
         e[4].record()
         if timed:
             for k, x in zip(("start", "hist", "model", "enc", "dec"), e):
@@ -435,6 +444,20 @@ def run_ours(a):
     nbytes = ctx.encode_result()
     ctx.decode_result()
     assert torch.equal(d_back, d_syms), "round trip failed"
+
+    # the same stream through the plain decoder (one lane per chunk, no side information), outside the timed
+    # region: what a decoder that was handed the reference's bytes alone achieves
+    plain = None
+    if d_restart is not None:
+        d_back.zero_()
+        ts = []
+        for _ in range(3):
+            ctx.decode_chunks(d_stream, d_offsets, n_syms, chunk, model, sym_bytes=sym_bytes, out=d_back, sync=False)
+            ts.append(ctx.timings()["decode_kernel"])
+        ctx.decode_result()
+        assert torch.equal(d_back, d_syms), "round trip (plain decoder) failed"
+        plain = {"decode_kernel_ms": max_over_ranks(min(ts)),
+                 "what": "rcb_decode_chunks on the same stream: one lane per chunk, no restart points (untimed leg)"}
 
     def phase(a_, b_):
         return sum(x.elapsed_time(y) for x, y in zip(ev[a_], ev[b_])) / len(ev[a_])
@@ -481,12 +504,13 @@ def run_ours(a):
         mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
         sym_rate = n_syms / (kavg[dom] * 1e-3)
         ceiling = 4 * sm_count * mhz * 1e6 * 32 / cap_issue["inst_per_symbol"]  # symbols/s with every scheduler busy
-        warps = (n_chunks + 31) // 32
+        lanes_per_chunk = (chunk + a.restart - 1) // a.restart if (d_restart is not None and dom == "decode_kernel") else 1
+        warps = (n_chunks * lanes_per_chunk + 31) // 32
         issue = dict(cap_issue)
         issue.update({"symbols_per_s": sym_rate, "issue_ceiling_symbols_per_s": ceiling,
                       "frac_of_issue_ceiling": sym_rate / ceiling,
                       "warps_per_scheduler": warps / (4 * sm_count),
-                      "cycles_per_symbol_per_lane": kavg[dom] * 1e-3 * mhz * 1e6 / min(chunk, n_syms)})
+                      "cycles_per_symbol_per_lane": kavg[dom] * 1e-3 * mhz * 1e6 / (min(chunk, n_syms) / lanes_per_chunk)})
     roofline = {"bound": "issue", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": tr.get("source") if traffic else None, "peak_source": peak_src,
@@ -683,13 +707,16 @@ def run_ours(a):
             "dtype": "u64", "data": "synthetic",
             "config": {"workload": workload_name(a), "chunk_syms": chunk, "alphabet": K, "zipf_s": a.zipf, "mode": a.mode,
                        "bytes_per_gpu": n, "n_chunks_per_gpu": n_chunks, "compressed_over_input": ratio,
+                       "restart_syms": a.restart if d_restart is not None else 0,
+                       "decoder_lanes_per_chunk": (chunk + a.restart - 1) // a.restart if d_restart is not None else 1,
+                       "restart_bytes_over_input": (d_restart.numel() * 8 / n) if d_restart is not None else 0.0,
                        "l2": "inputs larger than L2 (1 GiB batch + 0.72 GiB stream per GPU vs 126 MB); no flush",
                        "parallelism": par},
             "encode_gbs": world * n / (ms["encode"] * 1e-3) / 1e9,
             "decode_gbs": world * n / (ms["decode"] * 1e-3) / 1e9,
             "phase_ms": ms,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "parity": parity,
+            "clocks": clocks, "parity": parity, "plain_decoder": plain,
         }
         print(json.dumps(line))
     if comm is not None:

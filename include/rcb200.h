@@ -52,7 +52,8 @@ typedef enum rcb_error {
     RCB_ERR_INVALID_MODEL = -10,   /* table has cum_freq > total_freq (outside the path) */
     RCB_ERR_UNSUPPORTED = -11,
     RCB_ERR_NO_DEVICE = -12,       /* no CUDA device: there is no CPU fallback */
-    RCB_ERR_NCCL = -13             /* an NCCL call failed or libnccl.so.2 is missing; see rcb_comm_last_error */
+    RCB_ERR_NCCL = -13,            /* an NCCL call failed or libnccl.so.2 is missing; see rcb_comm_last_error */
+    RCB_ERR_RESTART_POINT = -14    /* a restart point does not match the code stream (see rcb_restart_point) */
 } rcb_error;
 
 /* per-chunk status words written to d_status (0 = ok) */
@@ -63,7 +64,8 @@ enum {
     RCB_ST_UPPER_OVERFLOW = 3,
     RCB_ST_SYMBOL_RANGE = 4,
     RCB_ST_OUT_CAPACITY = 5,
-    RCB_ST_TRUNCATED = 6
+    RCB_ST_TRUNCATED = 6,
+    RCB_ST_RESTART = 7
 };
 
 /* model flags reported by rcb_model_info */
@@ -176,6 +178,50 @@ int rcb_decode_chunks_async(rcb_ctx *ctx, const uint8_t *d_stream, const uint64_
                             uint64_t n_syms, int sym_bytes, uint64_t chunk_syms,
                             const rcb_model *m, void *d_syms_out, uint32_t *d_status);
 int rcb_decode_result(rcb_ctx *ctx);
+
+/* ---- restart points: several decoder lanes per chunk ------------------------
+ * Not in the reference (its Decoder walks one stream front to back,
+ * src/decoder.rs:38-54); side information next to the offsets, the code bytes
+ * stay exactly the reference's.  The reference decoder keeps the encoder's
+ * (lower_bound, range) (src/decoder.rs:42-52 runs the same param_update) and its
+ * `data` is the 8 code bytes at the current position (src/decoder.rs:31-35), so
+ * the state in front of symbol j of a chunk is (lower_bound, range, code bytes
+ * emitted so far) -- which the ENCODER knows.  rcb_encode_chunks_restart records
+ * it every restart_syms symbols; rcb_decode_chunks_restart then decodes each
+ * chunk with ceil(chunk_syms / restart_syms) lanes instead of one (64 KiB chunks
+ * are too few lanes to fill a B200).  A lane that arrives at
+ * the next record in a different state reports RCB_ST_RESTART, so a damaged
+ * record or stream is detected, not silently decoded.
+ *   d_restart = rcb_restart_point[n_chunks][rcb_restart_points_per_chunk()],
+ *   record r of chunk i = state in front of symbol (r + 1) * restart_syms of it
+ *   (range == 0: absent, ragged last chunk).  restart_syms: multiple of 64, at
+ *   most 64 parts per chunk; restart_syms == 0 or d_restart == NULL = the plain
+ *   calls above.  `range` may be rounded down to a multiple of total_freq (only
+ *   range / total_freq is used before the next update, src/range_coder.rs:62). */
+typedef struct rcb_restart_point {
+    uint64_t lower_bound; /* RangeCoder::lower_bound, src/range_coder.rs:9  */
+    uint64_t range;       /* RangeCoder::range,       src/range_coder.rs:11 */
+    uint32_t code_bytes;  /* bytes Encoder::encode has returned so far (src/encoder.rs:24-37) */
+    uint32_t reserved;
+} rcb_restart_point;
+uint64_t rcb_restart_points_per_chunk(uint64_t chunk_syms, uint64_t restart_syms);
+int rcb_encode_chunks_restart(rcb_ctx *ctx, const void *d_syms, uint64_t n_syms, int sym_bytes,
+                              uint64_t chunk_syms, const rcb_model *m, uint8_t *d_out,
+                              uint64_t out_cap, uint64_t *d_offsets, uint32_t *d_status,
+                              uint64_t restart_syms, rcb_restart_point *d_restart,
+                              uint64_t *h_out_bytes);
+int rcb_encode_chunks_restart_async(rcb_ctx *ctx, const void *d_syms, uint64_t n_syms, int sym_bytes,
+                                    uint64_t chunk_syms, const rcb_model *m, uint8_t *d_out,
+                                    uint64_t out_cap, uint64_t *d_offsets, uint32_t *d_status,
+                                    uint64_t restart_syms, rcb_restart_point *d_restart);
+int rcb_decode_chunks_restart(rcb_ctx *ctx, const uint8_t *d_stream, const uint64_t *d_offsets,
+                              uint64_t n_syms, int sym_bytes, uint64_t chunk_syms,
+                              const rcb_model *m, void *d_syms_out, uint32_t *d_status,
+                              uint64_t restart_syms, const rcb_restart_point *d_restart);
+int rcb_decode_chunks_restart_async(rcb_ctx *ctx, const uint8_t *d_stream, const uint64_t *d_offsets,
+                                    uint64_t n_syms, int sym_bytes, uint64_t chunk_syms,
+                                    const rcb_model *m, void *d_syms_out, uint32_t *d_status,
+                                    uint64_t restart_syms, const rcb_restart_point *d_restart);
 
 /* ---- host-buffer convenience (H2D, encode/decode, D2H inside the call) -----
  * What a Rust `gpu::encode_chunks(&pmodel, K, &symbols, chunk_syms)` binds.

@@ -146,6 +146,29 @@ int64_t rco_encode(const void *syms, uint64_t n, int sym_bytes, uint32_t K,
     return (int64_t)len;
 }
 
+/* The Encoder's state after n symbols and before finish(): (lower_bound, range) of its RangeCoder
+ * (src/encoder.rs:7-11, src/range_coder.rs:7-12) and the number of bytes encode() has returned so far
+ * (src/encoder.rs:24-37).  Checker for the restart points of the GPU path (include/rcb200.h). */
+int64_t rco_encode_state(const void *syms, uint64_t n, int sym_bytes, uint32_t K,
+                         const uint32_t *c, const uint32_t *cum, uint32_t total,
+                         uint64_t *lower, uint64_t *range) {
+    rco_range_coder rc;
+    rco_rc_new(&rc);
+    uint64_t len = 0;
+    uint8_t tmp[16];
+    for (uint64_t i = 0; i < n; i++) {
+        uint32_t index = load_sym(syms, i, sym_bytes);
+        if (index >= K) return RCO_ERR_SYMBOL_RANGE;
+        int k;
+        int e = rco_param_update(&rc, c[index], cum[index], total, tmp, &k);
+        if (e) return e;
+        len += (uint64_t)k;
+    }
+    *lower = rc.lower_bound;
+    *range = rc.range;
+    return (int64_t)len;
+}
+
 /* src/decoder.rs:6-12 */
 typedef struct {
     rco_range_coder range_coder;

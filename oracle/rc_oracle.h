@@ -62,6 +62,13 @@ int64_t rco_encode(const void *syms, uint64_t n, int sym_bytes, uint32_t K,
                    const uint32_t *c, const uint32_t *cum, uint32_t total,
                    uint8_t *out, uint64_t cap);
 
+/* The same run stopped after n symbols, before finish(): lower_bound and range of the Encoder's
+ * RangeCoder (src/encoder.rs:7-11) and, as the return value, the bytes encode() has returned so
+ * far -- what the GPU path's restart points record (include/rcb200.h: rcb_restart_point). */
+int64_t rco_encode_state(const void *syms, uint64_t n, int sym_bytes, uint32_t K,
+                         const uint32_t *c, const uint32_t *cum, uint32_t total,
+                         uint64_t *lower, uint64_t *range);
+
 /* src/decoder.rs:14-54 with examples/sample_impl.rs:27-45 as find_index.
  * Returns the number of code bytes consumed (8 + sum n) or a negative error. */
 int64_t rco_decode(const uint8_t *code, uint64_t len, uint64_t n_syms,

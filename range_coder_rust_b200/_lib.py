@@ -50,6 +50,11 @@ SIGNATURES = {
     "rcb_decode_chunks": (ci, [vp, vp, vp, u64, ci, u64, vp, vp, vp]),
     "rcb_decode_chunks_async": (ci, [vp, vp, vp, u64, ci, u64, vp, vp, vp]),
     "rcb_decode_result": (ci, [vp]),
+    "rcb_restart_points_per_chunk": (u64, [u64, u64]),
+    "rcb_encode_chunks_restart": (ci, [vp, vp, u64, ci, u64, vp, vp, u64, vp, vp, u64, vp, u64p]),
+    "rcb_encode_chunks_restart_async": (ci, [vp, vp, u64, ci, u64, vp, vp, u64, vp, vp, u64, vp]),
+    "rcb_decode_chunks_restart": (ci, [vp, vp, vp, u64, ci, u64, vp, vp, vp, u64, vp]),
+    "rcb_decode_chunks_restart_async": (ci, [vp, vp, vp, u64, ci, u64, vp, vp, vp, u64, vp]),
     "rcb_encode_host": (ci, [vp, vp, u64, ci, u64, vp, vp, u64, vp, u64p]),
     "rcb_decode_host": (ci, [vp, vp, vp, u64, ci, u64, vp, vp]),
     "rcb_stream_state_init": (None, [vp]),

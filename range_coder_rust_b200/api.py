@@ -275,9 +275,19 @@ class Context:
     def encode_bound(self, model, n_syms, sym_bytes, chunk_syms):
         return int(self.lib.rcb_encode_bound(self.h, model.h, n_syms, sym_bytes, chunk_syms))
 
-    def encode_chunks(self, syms, chunk_syms, model, out=None, offsets=None, status=None, sync=True):
+    def restart_points(self, n_chunks, chunk_syms, restart_syms):
+        """Device buffer for the restart points of a call: rcb_restart_point[n_chunks][per chunk] as
+        int64[n_chunks * per_chunk * 3] (24-byte records), or None when the chunk has a single part."""
+        per = int(self.lib.rcb_restart_points_per_chunk(chunk_syms, restart_syms))
+        if per == 0:
+            return None
+        return torch.zeros(n_chunks * per * 3, dtype=torch.int64, device=self.device)
+
+    def encode_chunks(self, syms, chunk_syms, model, out=None, offsets=None, status=None, sync=True,
+                      restart_syms=0, restart=None):
         """Every chunk through Encoder::encode ... finish (src/encoder.rs:24-46).
-        Returns (stream uint8[cap], offsets int64[n_chunks+1], n_bytes or None)."""
+        Returns (stream uint8[cap], offsets int64[n_chunks+1], n_bytes or None).
+        restart_syms / restart (see restart_points): also record the coder state every restart_syms symbols."""
         n = syms.numel()
         sb = self._sym_bytes(syms)
         n_chunks = (n + chunk_syms - 1) // chunk_syms
@@ -286,14 +296,16 @@ class Context:
                               device=self.device)
         if offsets is None:
             offsets = torch.empty(n_chunks + 1, dtype=torch.int64, device=self.device)
+        rs = int(restart_syms) if restart is not None else 0
         if sync:
             nbytes = ctypes.c_uint64()
-            rc = self.lib.rcb_encode_chunks(self.h, _ptr(syms), n, sb, chunk_syms, model.h, _ptr(out),
-                                            out.numel(), _ptr(offsets), _ptr(status), ctypes.byref(nbytes))
+            rc = self.lib.rcb_encode_chunks_restart(self.h, _ptr(syms), n, sb, chunk_syms, model.h, _ptr(out),
+                                                    out.numel(), _ptr(offsets), _ptr(status), rs, _ptr(restart),
+                                                    ctypes.byref(nbytes))
             self._check(rc, "rcb_encode_chunks")
             return out, offsets, int(nbytes.value)
-        rc = self.lib.rcb_encode_chunks_async(self.h, _ptr(syms), n, sb, chunk_syms, model.h, _ptr(out),
-                                              out.numel(), _ptr(offsets), _ptr(status))
+        rc = self.lib.rcb_encode_chunks_restart_async(self.h, _ptr(syms), n, sb, chunk_syms, model.h, _ptr(out),
+                                                      out.numel(), _ptr(offsets), _ptr(status), rs, _ptr(restart))
         self._check(rc, "rcb_encode_chunks_async")
         return out, offsets, None
 
@@ -303,14 +315,16 @@ class Context:
         return int(nbytes.value)
 
     def decode_chunks(self, stream, offsets, n_syms, chunk_syms, model, sym_bytes=1, out=None, status=None,
-                      sync=True):
-        """Every chunk through Decoder::new + decode (src/decoder.rs:14-54)."""
+                      sync=True, restart_syms=0, restart=None):
+        """Every chunk through Decoder::new + decode (src/decoder.rs:14-54); with restart points
+        (restart_syms, restart as written by encode_chunks) several lanes per chunk."""
         if out is None:
             dt = torch.uint8 if sym_bytes == 1 else torch.int16
             out = torch.empty(n_syms, dtype=dt, device=self.device)
-        fn = self.lib.rcb_decode_chunks if sync else self.lib.rcb_decode_chunks_async
+        rs = int(restart_syms) if restart is not None else 0
+        fn = self.lib.rcb_decode_chunks_restart if sync else self.lib.rcb_decode_chunks_restart_async
         rc = fn(self.h, _ptr(stream), _ptr(offsets), n_syms, sym_bytes, chunk_syms, model.h, _ptr(out),
-                _ptr(status))
+                _ptr(status), rs, _ptr(restart))
         self._check(rc, "rcb_decode_chunks")
         return out
 

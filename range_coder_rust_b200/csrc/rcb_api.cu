@@ -21,6 +21,8 @@ using namespace rcb;
 static_assert(sizeof(ModelHdr) == 48, "ModelHdr layout");
 static_assert(sizeof(LutEntry) == 16, "LutEntry layout");
 static_assert((int)RCB_ST_TRUNCATED == (int)ST_TRUNCATED, "status codes");
+static_assert((int)RCB_ST_RESTART == (int)ST_RESTART, "status codes");
+static_assert(sizeof(rcb_restart_point) == sizeof(Restart) && sizeof(Restart) == 24, "restart point layout");
 static_assert((int)RCB_MODEL_REGULAR == (int)MODEL_REGULAR, "model flags");
 
 #define LUT_CAP 4096u       // buckets of the shared-model decode LUT (64 KiB of shared memory)
@@ -151,6 +153,7 @@ extern "C" const char* rcb_strerror(int err) {
         case RCB_ERR_UNSUPPORTED: return "unsupported configuration";
         case RCB_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
         case RCB_ERR_NCCL: return "NCCL error (or libnccl.so.2 not found)";
+        case RCB_ERR_RESTART_POINT: return "restart point inconsistent with the code stream";
         default: return "unknown error";
     }
 }
@@ -172,6 +175,7 @@ static int status_to_error(uint32_t st) {
         case ST_SYMBOL_RANGE: return RCB_ERR_SYMBOL_OUT_OF_RANGE;
         case ST_OUT_CAPACITY: return RCB_ERR_OUT_CAPACITY;
         case ST_TRUNCATED: return RCB_ERR_TRUNCATED_STREAM;
+        case ST_RESTART: return RCB_ERR_RESTART_POINT;
         default: return RCB_ERR_INVALID_ARGUMENT;
     }
 }
@@ -627,6 +631,35 @@ static bool make_symbol_tensor_map(CUtensorMap* tm, const void* base, uint64_t r
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Restart points of a call (rcb_core.cuh: Restart): every `syms` symbols of a chunk, per_chunk records per chunk.
+struct RestartSpec {
+    Restart* pts = nullptr;
+    uint64_t syms = 0;
+    uint32_t per_chunk = 0;
+    bool on() const { return pts != nullptr && per_chunk > 0; }
+};
+
+// Validates (restart_syms, d_restart) of an entry point.  Off (whole chunks) when either is 0 or the chunk has
+// a single part; restart_syms must be a multiple of 64 (whole input vectors and output words per part).
+static int make_restart_spec(uint64_t chunk_syms, uint64_t restart_syms, const void* d_restart, RestartSpec* out) {
+    *out = RestartSpec();
+    if (!restart_syms || !d_restart) return RCB_OK;
+    if (restart_syms % 64) return RCB_ERR_INVALID_ARGUMENT;
+    if (reinterpret_cast<uintptr_t>(d_restart) & 7u) return RCB_ERR_INVALID_ARGUMENT;
+    const uint64_t parts = (chunk_syms + restart_syms - 1) / restart_syms;
+    if (parts > 64) return RCB_ERR_UNSUPPORTED;  // lanes per chunk (a block of the row kernel holds whole chunks)
+    if (parts <= 1) return RCB_OK;
+    out->pts = static_cast<Restart*>(const_cast<void*>(d_restart));
+    out->syms = restart_syms;
+    out->per_chunk = (uint32_t)(parts - 1);
+    return RCB_OK;
+}
+
+extern "C" uint64_t rcb_restart_points_per_chunk(uint64_t chunk_syms, uint64_t restart_syms) {
+    if (!chunk_syms || !restart_syms) return 0;
+    return (chunk_syms + restart_syms - 1) / restart_syms - 1;
+}
+
 struct EncPlan {
     int table;      // TAB_*
     int fmode;      // FM_*
@@ -739,10 +772,13 @@ static void launch_encode_variant(rcb_ctx* c, const rcb_model* m, const EncodeAr
 static int encode_issue(rcb_ctx* c, const void* d_syms, uint64_t n_syms, int sym_bytes, uint64_t chunk_syms,
                         const rcb_model* m, uint64_t model_first, uint8_t* staging, uint64_t pitch, uint32_t* lens,
                         uint32_t* status, uint8_t* d_out, uint64_t out_cap, uint64_t* d_offsets,
-                        unsigned long long* d_summary, bool timed) {
+                        unsigned long long* d_summary, bool timed, const RestartSpec* rs = nullptr) {
     const uint64_t n_chunks = (n_syms + chunk_syms - 1) / chunk_syms;
     const bool shared = m->n_models == 1;
     EncodeArgs a;
+    a.restart = rs && rs->on() ? rs->pts : nullptr;
+    a.restart_syms = rs && rs->on() ? rs->syms : 0;
+    a.restart_per_chunk = rs && rs->on() ? rs->per_chunk : 0u;
     a.syms = d_syms;
     a.n_syms = n_syms;
     a.chunk_syms = chunk_syms;
@@ -783,8 +819,11 @@ static int encode_issue(rcb_ctx* c, const void* d_syms, uint64_t n_syms, int sym
 
 static int encode_launch(rcb_ctx* c, const void* d_syms, uint64_t n_syms, int sym_bytes, uint64_t chunk_syms,
                          const rcb_model* m, uint8_t* d_out, uint64_t out_cap, uint64_t* d_offsets,
-                         uint32_t* d_status, uint64_t pitch_override) {
+                         uint32_t* d_status, uint64_t pitch_override, uint64_t restart_syms = 0,
+                         void* d_restart = nullptr) {
     if (!c || !m || !m->ready || m->ctx != c || !d_offsets || chunk_syms == 0) return RCB_ERR_INVALID_ARGUMENT;
+    RestartSpec rs;
+    if (int rr = make_restart_spec(chunk_syms, restart_syms, d_restart, &rs)) return rr;
     if (n_syms && !d_syms) return RCB_ERR_INVALID_ARGUMENT;
     if (sym_bytes != 1 && sym_bytes != 2) return RCB_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(d_syms) & 15u) || (reinterpret_cast<uintptr_t>(d_out) & 15u) ||
@@ -816,7 +855,7 @@ static int encode_launch(rcb_ctx* c, const void* d_syms, uint64_t n_syms, int sy
 
     EV(c, 0);
     r = encode_issue(c, d_syms, n_syms, sym_bytes, chunk_syms, m, 0, c->staging, pitch, c->lens,
-                     d_status ? d_status : c->status, d_out, out_cap, d_offsets, c->d_summary, true);
+                     d_status ? d_status : c->status, d_out, out_cap, d_offsets, c->d_summary, true, &rs);
     if (r) return r;
     c->ev_enc = c->timing;
     return RCB_OK;
@@ -867,6 +906,32 @@ extern "C" int rcb_encode_chunks(rcb_ctx* c, const void* d_syms, uint64_t n_syms
     return r;
 }
 
+extern "C" int rcb_encode_chunks_restart_async(rcb_ctx* c, const void* d_syms, uint64_t n_syms, int sym_bytes,
+                                               uint64_t chunk_syms, const rcb_model* m, uint8_t* d_out,
+                                               uint64_t out_cap, uint64_t* d_offsets, uint32_t* d_status,
+                                               uint64_t restart_syms, rcb_restart_point* d_restart) {
+    return encode_launch(c, d_syms, n_syms, sym_bytes, chunk_syms, m, d_out, out_cap, d_offsets, d_status, 0,
+                         restart_syms, d_restart);
+}
+
+extern "C" int rcb_encode_chunks_restart(rcb_ctx* c, const void* d_syms, uint64_t n_syms, int sym_bytes,
+                                         uint64_t chunk_syms, const rcb_model* m, uint8_t* d_out, uint64_t out_cap,
+                                         uint64_t* d_offsets, uint32_t* d_status, uint64_t restart_syms,
+                                         rcb_restart_point* d_restart, uint64_t* h_out_bytes) {
+    int r = encode_launch(c, d_syms, n_syms, sym_bytes, chunk_syms, m, d_out, out_cap, d_offsets, d_status, 0,
+                          restart_syms, d_restart);
+    if (r) return r;
+    uint64_t need = 0;
+    r = encode_result(c, h_out_bytes, &need);
+    if (r == RCB_ERR_OUT_CAPACITY && need) {  // staging row too small: rerun once (rewrites the restart points too)
+        r = encode_launch(c, d_syms, n_syms, sym_bytes, chunk_syms, m, d_out, out_cap, d_offsets, d_status, need,
+                          restart_syms, d_restart);
+        if (r) return r;
+        r = encode_result(c, h_out_bytes, nullptr);
+    }
+    return r;
+}
+
 extern "C" int rcb_encode_result(rcb_ctx* c, uint64_t* h_out_bytes) {
     if (!c || !c->pending_offsets) return RCB_ERR_INVALID_ARGUMENT;
     return encode_result(c, h_out_bytes, nullptr);
@@ -884,13 +949,14 @@ struct DecPlan {
     size_t smem;
 };
 
-static DecPlan plan_decode(const rcb_ctx* c, const rcb_model* m, uint64_t n_chunks) {
+// parts: lanes per chunk (restart points; 1 = whole chunks).  p.lanes is a multiple of it for the row kernel.
+static DecPlan plan_decode(const rcb_ctx* c, const rcb_model* m, uint64_t n_chunks, uint32_t parts = 1) {
     DecPlan p;
     memset(&p, 0, sizeof p);
     const bool shared = m->n_models == 1;
     p.checked = (m->bad_bits & 4u) != 0;
     const bool regular = (m->bad_bits & 8u) == 0;
-    p.threads = pick_threads(c, c->dec_threads, n_chunks);
+    p.threads = pick_threads(c, c->dec_threads, n_chunks * parts);
     p.lanes = (uint32_t)p.threads;
     const size_t budget = 216 * 1024;
     const size_t row = ((size_t)m->K + ROW_PAD) * sizeof(uint32_t);  // rcb_decode_row.cuh
@@ -934,6 +1000,7 @@ static DecPlan plan_decode(const rcb_ctx* c, const rcb_model* m, uint64_t n_chun
                 p.nb = nb;
                 p.fmode = p.pow2 ? (shift >= 24 ? FM_BIG : FM_POW2) : FM_GEN;
                 p.smem = (size_t)p.threads * RING_STRIDE + row + (size_t)nb * lut_elem;
+                p.lanes = (uint32_t)p.threads / parts * parts;  // whole chunks per block
                 return p;
             }
         }
@@ -944,25 +1011,28 @@ static DecPlan plan_decode(const rcb_ctx* c, const rcb_model* m, uint64_t n_chun
         p.smem = (size_t)p.threads * RING_STRIDE + (size_t)nbg * sizeof(LutEntry) + (size_t)m->K * sizeof(uint2);
         return p;
     }
-    // per-chunk models: each lane owns a cum row + a thin LUT in shared memory when they fit
-    const size_t lane_min = RING_STRIDE + row + 256 * lut_elem;
-    const uint32_t lmax = (uint32_t)(budget / lane_min);
-    if (!p.checked && regular && lmax >= 32) {
-        uint32_t L = lmax < 512u ? lmax : 512u;
+    // per-chunk models: each chunk owns a cum row + a thin LUT in shared memory (shared by its `parts` lanes,
+    // each of which has its own code-byte ring) when they fit
+    const size_t chunk_min = (size_t)parts * RING_STRIDE + row + 256 * lut_elem;
+    const uint32_t cmax = (uint32_t)(budget / chunk_min);
+    if (!p.checked && regular && (uint64_t)cmax * parts >= 32) {
+        uint32_t CB = cmax * parts < 512u ? cmax : 512u / parts;  // chunks per block
         const uint64_t sms = (uint64_t)(c->sm_count > 0 ? c->sm_count : 148);
         const uint64_t even = (n_chunks + sms - 1) / sms;  // one wave over all SMs when it fits
-        if (even <= L) L = (uint32_t)(even ? even : 1);
-        if (c->dec_threads && (uint32_t)c->dec_threads < L) L = (uint32_t)c->dec_threads;
+        if (even <= CB) CB = (uint32_t)(even ? even : 1);
+        if (c->dec_threads && (uint32_t)c->dec_threads < CB * parts) CB = (uint32_t)c->dec_threads / parts;
+        if (CB == 0) CB = 1;
+        const uint32_t L = CB * parts;
         p.threads = (int)((L + 31) / 32 * 32);
-        const size_t fixed = (size_t)p.threads * RING_STRIDE + (size_t)L * row;
-        size_t per_lane = (budget - fixed) / L / lut_elem;
-        uint32_t nb = (uint32_t)(per_lane > 4096 ? 4096 : per_lane) & ~15u;
+        const size_t fixed = (size_t)p.threads * RING_STRIDE + (size_t)CB * row;
+        size_t per_row = (budget - fixed) / CB / lut_elem;
+        uint32_t nb = (uint32_t)(per_row > 4096 ? 4096 : per_row) & ~15u;
         p.kind = 1;
         p.table = TAB_LANE;
         p.fmode = FM_LANE;
         p.lanes = L;
         p.nb = nb;
-        p.smem = fixed + (size_t)L * nb * lut_elem;
+        p.smem = fixed + (size_t)CB * nb * lut_elem;
         return p;
     }
     p.kind = 0;
@@ -1022,10 +1092,17 @@ static void launch_decode_row(rcb_ctx* c, const DecodeRowArgs& a, const DecPlan&
 static int decode_issue(rcb_ctx* c, const uint8_t* d_stream, const uint64_t* d_offsets, uint64_t n_syms,
                         int sym_bytes, uint64_t chunk_syms, const rcb_model* m, uint64_t model_first,
                         void* d_syms_out, uint32_t* status, unsigned long long* d_summary, bool timed,
-                        const DecSegment* seg = nullptr) {
+                        const DecSegment* seg = nullptr, const RestartSpec* rs = nullptr) {
     const uint64_t n_chunks = (n_syms + chunk_syms - 1) / chunk_syms;
     const bool shared = m->n_models == 1;
     DecodeArgs a;
+    const bool restart = rs && rs->on() && !seg;
+    const uint32_t parts = restart ? rs->per_chunk + 1u : 1u;
+    a.restart = restart ? rs->pts : nullptr;
+    a.restart_syms = restart ? rs->syms : 0;
+    a.parts = parts;
+    // several lanes per chunk report errors only (atomicMax): the status words start at 0
+    if (restart) CK(c, cudaMemsetAsync(status, 0, n_chunks * sizeof(uint32_t), c->stream));
     if (seg) a.seg = *seg;
     else a.seg = DecSegment{0, 0, nullptr, 0u, 0u};
     a.stream = d_stream;
@@ -1041,8 +1118,9 @@ static int decode_issue(rcb_ctx* c, const uint8_t* d_stream, const uint64_t* d_o
     a.per_chunk = !shared;
     a.out = d_syms_out;
     a.status = status;
-    const DecPlan plan = plan_decode(c, m, n_chunks);
-    const unsigned blocks = (unsigned)((n_chunks + plan.lanes - 1) / plan.lanes);
+    const DecPlan plan = plan_decode(c, m, n_chunks, parts);
+    const uint64_t n_lanes = n_chunks * parts;
+    const unsigned blocks = (unsigned)((n_lanes + plan.lanes - 1) / plan.lanes);  // row kernel: lanes % parts == 0
     if (plan.kind == 0) {
         if (sym_bytes == 1)
             launch_decode_variant<uint8_t>(c, m, a, plan, blocks);
@@ -1063,6 +1141,9 @@ static int decode_issue(rcb_ctx* c, const uint8_t* d_stream, const uint64_t* d_o
         ra.out = a.out;
         ra.status = a.status;
         ra.seg = a.seg;
+        ra.restart = a.restart;
+        ra.restart_syms = a.restart_syms;
+        ra.parts = a.parts;
         if (sym_bytes == 1) {
             if (plan.lut16) launch_decode_row<uint8_t, uint16_t>(c, ra, plan, blocks);
             else launch_decode_row<uint8_t, uint8_t>(c, ra, plan, blocks);
@@ -1080,10 +1161,12 @@ static int decode_issue(rcb_ctx* c, const uint8_t* d_stream, const uint64_t* d_o
     return RCB_OK;
 }
 
-extern "C" int rcb_decode_chunks_async(rcb_ctx* c, const uint8_t* d_stream, const uint64_t* d_offsets,
-                                       uint64_t n_syms, int sym_bytes, uint64_t chunk_syms,
-                                       const rcb_model* m, void* d_syms_out, uint32_t* d_status) {
+static int decode_launch(rcb_ctx* c, const uint8_t* d_stream, const uint64_t* d_offsets, uint64_t n_syms,
+                         int sym_bytes, uint64_t chunk_syms, const rcb_model* m, void* d_syms_out,
+                         uint32_t* d_status, uint64_t restart_syms, const void* d_restart) {
     if (!c || !m || !m->ready || m->ctx != c || !d_offsets || chunk_syms == 0) return RCB_ERR_INVALID_ARGUMENT;
+    RestartSpec rs;
+    if (int rr = make_restart_spec(chunk_syms, restart_syms, d_restart, &rs)) return rr;
     if (n_syms && (!d_stream || !d_syms_out)) return RCB_ERR_INVALID_ARGUMENT;
     if (sym_bytes != 1 && sym_bytes != 2) return RCB_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(d_stream) & 15u) || (reinterpret_cast<uintptr_t>(d_syms_out) & 15u) ||
@@ -1103,10 +1186,34 @@ extern "C" int rcb_decode_chunks_async(rcb_ctx* c, const uint8_t* d_stream, cons
     if (r) return r;
     EV(c, 4);
     r = decode_issue(c, d_stream, d_offsets, n_syms, sym_bytes, chunk_syms, m, 0, d_syms_out,
-                     d_status ? d_status : c->status, c->d_summary + 4, true);
+                     d_status ? d_status : c->status, c->d_summary + 4, true, nullptr, &rs);
     if (r) return r;
     c->ev_dec = c->timing;
     return RCB_OK;
+}
+
+extern "C" int rcb_decode_chunks_async(rcb_ctx* c, const uint8_t* d_stream, const uint64_t* d_offsets,
+                                       uint64_t n_syms, int sym_bytes, uint64_t chunk_syms,
+                                       const rcb_model* m, void* d_syms_out, uint32_t* d_status) {
+    return decode_launch(c, d_stream, d_offsets, n_syms, sym_bytes, chunk_syms, m, d_syms_out, d_status, 0, nullptr);
+}
+
+extern "C" int rcb_decode_chunks_restart_async(rcb_ctx* c, const uint8_t* d_stream, const uint64_t* d_offsets,
+                                               uint64_t n_syms, int sym_bytes, uint64_t chunk_syms,
+                                               const rcb_model* m, void* d_syms_out, uint32_t* d_status,
+                                               uint64_t restart_syms, const rcb_restart_point* d_restart) {
+    return decode_launch(c, d_stream, d_offsets, n_syms, sym_bytes, chunk_syms, m, d_syms_out, d_status,
+                         restart_syms, d_restart);
+}
+
+extern "C" int rcb_decode_chunks_restart(rcb_ctx* c, const uint8_t* d_stream, const uint64_t* d_offsets,
+                                         uint64_t n_syms, int sym_bytes, uint64_t chunk_syms, const rcb_model* m,
+                                         void* d_syms_out, uint32_t* d_status, uint64_t restart_syms,
+                                         const rcb_restart_point* d_restart) {
+    int r = decode_launch(c, d_stream, d_offsets, n_syms, sym_bytes, chunk_syms, m, d_syms_out, d_status,
+                          restart_syms, d_restart);
+    if (r) return r;
+    return rcb_decode_result(c);
 }
 
 extern "C" int rcb_decode_result(rcb_ctx* c) {

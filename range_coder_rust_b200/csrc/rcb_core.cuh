@@ -46,7 +46,24 @@ enum : uint32_t {
     ST_UPPER_OVERFLOW = 3,   // range_coder.rs:111,138-146
     ST_SYMBOL_RANGE = 4,     // symbol >= K (sample_impl.rs:19 would panic)
     ST_OUT_CAPACITY = 5,     // staging row too small; the reported length is the needed size
-    ST_TRUNCATED = 6         // decoder.rs:33 pop_front on an empty buffer
+    ST_TRUNCATED = 6,        // decoder.rs:33 pop_front on an empty buffer
+    ST_RESTART = 7           // a restart point does not fit its chunk, or the lane before it ended elsewhere
+};
+
+// ---------------------------------------------------------------------------
+// Restart point (build-defined side information, absent from the reference): the coder state in
+// front of symbol r * restart_syms of a chunk, as the ENCODER saw it -- lower_bound and range
+// (src/range_coder.rs:9-11) and the number of code bytes the chunk's Encoder had emitted by then.
+// The reference decoder mirrors the encoder's (lower_bound, range) exactly (src/decoder.rs:42-52)
+// and its `data` is the 8 code bytes from that position on (src/decoder.rs:31-35), so a decoder
+// lane can enter the chunk there: the chunk's bytes stay the reference's bytes, and one chunk is
+// decoded by several lanes.  `rg` may be the lane's range rounded down to a multiple of total_freq
+// (the only use of range before the next update is range / total_freq, src/range_coder.rs:62).
+// ---------------------------------------------------------------------------
+struct Restart {
+    uint64_t lo, rg;
+    uint32_t pos;  // code bytes emitted before the symbol = offset of the decoder's 8-byte window
+    uint32_t pad;
 };
 
 RCB_HD uint64_t umul64hi(uint64_t a, uint64_t b) {

@@ -56,7 +56,32 @@ struct DecodeArgs {
     void* out;
     uint32_t* status;
     DecSegment seg;
+    // restart points (rcb_core.cuh: Restart): `parts` lanes per chunk, lane p > 0 enters at record p-1
+    const Restart* restart;  // [n_chunks][parts - 1]
+    uint64_t restart_syms;
+    uint32_t parts;          // 1: one lane per chunk (no restart points)
 };
+
+// Which part of which chunk a lane decodes, and from which state (restart points).
+struct LanePart {
+    uint64_t chunk, first, chunk_cnt;
+    uint32_t part;
+    bool has;  // the lane has symbols to decode
+};
+__device__ __forceinline__ LanePart lane_part(uint64_t lane_id, uint32_t parts, uint64_t n_chunks, uint64_t n_syms,
+                                              uint64_t chunk_syms, uint64_t restart_syms) {
+    LanePart l;
+    l.chunk = parts > 1 ? lane_id / parts : lane_id;
+    l.part = parts > 1 ? (uint32_t)(lane_id - l.chunk * parts) : 0u;
+    l.first = l.chunk * chunk_syms;
+    l.has = l.chunk < n_chunks;
+    l.chunk_cnt = 0;
+    if (l.has) {
+        l.chunk_cnt = (n_syms - l.first < chunk_syms) ? (n_syms - l.first) : chunk_syms;
+        l.has = l.part == 0 || (uint64_t)l.part * restart_syms < l.chunk_cnt;  // ragged last chunk: fewer parts
+    }
+    return l;
+}
 
 constexpr uint32_t RING_PIECES = 8;                   // 16-byte pieces per lane
 constexpr uint32_t RING_STRIDE = RING_PIECES * 16 + 16;  // 144 bytes: 16-byte aligned, spreads banks
@@ -308,16 +333,22 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
         for (uint32_t i = threadIdx.x; i < a.K; i += blockDim.x) s_tab[i] = a.tabs[i];
         __syncthreads();
     }
-    const uint64_t chunk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned live = __ballot_sync(0xFFFFFFFFu, chunk < a.n_chunks);  // lanes of this warp that hold a chunk
-    if (chunk >= a.n_chunks) return;
-    const uint64_t first = chunk * a.chunk_syms;
-    const uint64_t chunk_cnt = (a.n_syms - first < a.chunk_syms) ? (a.n_syms - first) : a.chunk_syms;
-    // this launch's part of the chunk (the whole chunk unless the host pipeline segments it)
+    const uint32_t parts = a.parts;
+    const LanePart lp = lane_part((uint64_t)blockIdx.x * blockDim.x + threadIdx.x, parts, a.n_chunks, a.n_syms,
+                                  a.chunk_syms, a.restart_syms);
+    const unsigned live = __ballot_sync(0xFFFFFFFFu, lp.has);  // lanes of this warp that have symbols to decode
+    if (!lp.has) return;
+    const uint64_t chunk = lp.chunk, first = lp.first, chunk_cnt = lp.chunk_cnt;
+    // this lane's part of the chunk: the whole chunk, one of `parts` pieces between restart points, or (host
+    // pipeline) this launch's segment
     const bool seg_load = a.seg.state && a.seg.load, seg_save = a.seg.state && a.seg.save;
-    const uint64_t seg_begin = a.seg.state ? (a.seg.first < chunk_cnt ? a.seg.first : chunk_cnt) : 0;
-    const uint64_t seg_end =
+    uint64_t seg_begin = a.seg.state ? (a.seg.first < chunk_cnt ? a.seg.first : chunk_cnt) : 0;
+    uint64_t seg_end =
         seg_save ? (a.seg.first + a.seg.syms < chunk_cnt ? a.seg.first + a.seg.syms : chunk_cnt) : chunk_cnt;
+    if (parts > 1) {
+        seg_begin = (uint64_t)lp.part * a.restart_syms;
+        seg_end = seg_begin + a.restart_syms < chunk_cnt ? seg_begin + a.restart_syms : chunk_cnt;
+    }
     uint64_t cnt = seg_end - seg_begin;
     SYM* dst = reinterpret_cast<SYM*>(a.out) + first + seg_begin;
 
@@ -336,12 +367,25 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
     // Decoder::new pops (src/decoder.rs:14-23) and lies inside the stream.  A lane whose offsets break
     // that decodes nothing and reports ST_TRUNCATED; it stays in the warp (the loops below vote), reads
     // no global memory (no piece is requested, no symbol decoded) and writes nothing.
-    const bool offsets_ok = off0 <= off1 && off1 - off0 >= 8 && off1 <= total_bytes;
+    bool offsets_ok = off0 <= off1 && off1 - off0 >= 8 && off1 <= total_bytes;
+    // a lane that enters at a restart point starts its 8-byte window `pos` bytes into the chunk; the record is
+    // caller data like the offsets: it must leave room for the window, else the lane decodes nothing (ST_RESTART)
+    Restart rp{0ull, ~0ull, 0u, 0u};
+    bool restart_ok = true;
+    if (lp.part) {
+        rp = a.restart[chunk * (parts - 1u) + (lp.part - 1u)];
+        restart_ok = offsets_ok && rp.rg != 0 && (uint64_t)rp.pos + 8 <= off1 - off0;
+        if (!restart_ok) {
+            offsets_ok = false;
+            rp.pos = 0;
+        }
+    }
     if (!offsets_ok) off0 = off1 = 0;
-    const uint64_t pb = off0 & ~15ull;                               // piece base (byte offset)
+    const uint64_t start = off0 + rp.pos;                            // first byte of the lane's window
+    const uint64_t pb = start & ~15ull;                              // piece base (byte offset)
     const uint64_t readable = ((total_bytes + 15) & ~15ull) - pb;    // rcb200.h: readable to the next 16
-    const uint32_t skip = (uint32_t)(off0 & 3u);
-    const uint32_t rd0 = (uint32_t)((off0 - pb) >> 2);
+    const uint32_t skip = (uint32_t)(start & 3u);
+    const uint32_t rd0 = (uint32_t)((start - pb) >> 2);
 
     RingFill fill;
     fill.pbase = a.stream + pb;
@@ -372,7 +416,7 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
     fill.resync(rf);  // fill the ring from the read position, wait, load the current word
     DecSink<RingFetch> sink(rf);
 
-    uint64_t lo = 0, rg = ~0ull;
+    uint64_t lo = rp.lo, rg = rp.rg;  // RangeCoder::new (src/range_coder.rs:13-20) unless a restart point says otherwise
     uint32_t err = 0;
     if (seg_load) {
         const DecResume st = a.seg.state[chunk];
@@ -387,7 +431,7 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
     } else {
         sink.prime(skip);  // src/decoder.rs:14-23
     }
-    if (!offsets_ok) err = ST_TRUNCATED;  // src/decoder.rs:33: pop_front on an empty buffer
+    if (!offsets_ok) err = restart_ok ? ST_TRUNCATED : ST_RESTART;  // src/decoder.rs:33: pop_front on an empty buffer
 
     constexpr uint32_t PER = 4 / sizeof(SYM);  // symbols per 32-bit store
     constexpr uint32_t SYM_BITS = 8 * sizeof(SYM);
@@ -597,7 +641,22 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
         a.seg.state[chunk] = DecResume{lo, rg, sink.dh, sink.dl, sink.wh, sink.wl, sink.cnt, sink.f.rd, err, 0u};
         return;
     }
-    const uint32_t used = sink.used(sink.f.rd - rd0, skip);
+    const uint32_t used = sink.used(sink.f.rd - rd0, skip);  // bytes shifted into data by this lane (8 of them priming)
+    if (parts > 1) {
+        // several lanes per chunk: the status word was zeroed by the host, a lane reports only an error.  A lane
+        // that ends at a restart point must have arrived at that record's state (a damaged stream or record
+        // shows up here); the chunk's last lane checks the length like a whole-chunk lane.
+        if (!err) {
+            if (seg_end == chunk_cnt) {
+                if ((uint64_t)rp.pos + used > off1 - off0) err = ST_TRUNCATED;
+            } else {
+                const Restart nx = a.restart[chunk * (parts - 1u) + lp.part];
+                if (nx.lo != lo || nx.pos != rp.pos + used - 8u) err = ST_RESTART;
+            }
+        }
+        if (err) atomicMax(a.status + chunk, err);
+        return;
+    }
     if (!err && (uint64_t)used > off1 - off0) err = ST_TRUNCATED;  // src/decoder.rs:33
     a.status[chunk] = err;
 }

@@ -38,6 +38,9 @@ struct DecodeRowArgs {
     void* out;
     uint32_t* status;
     DecSegment seg;           // rcb_decode.cuh
+    const Restart* restart;   // restart points (rcb_decode.cuh: DecodeArgs)
+    uint64_t restart_syms;
+    uint32_t parts;           // lanes per chunk; lanes_per_block is a multiple of it
 };
 
 // Literal renormalisation loops for a symbol that is already chosen (s.lo / s.rg hold lower' and
@@ -66,10 +69,12 @@ __global__ void __launch_bounds__(512, 1) decode_row_kernel(DecodeRowArgs a) {
     extern __shared__ __align__(16) uint8_t s_raw[];
     __shared__ ModelHdr s_hdr;
     const uint32_t K = a.K, L = a.lanes_per_block, nb = a.nb;
-    const uint64_t block_first = (uint64_t)blockIdx.x * L;
+    const uint32_t parts = a.parts;                              // lanes per chunk (restart points), 1 = whole chunks
+    const uint32_t CB = L / parts;                               // chunks per block
+    const uint64_t block_first = (uint64_t)blockIdx.x * CB;      // first chunk of this block
     const uint32_t row_words = K + ROW_PAD;  // cum[0..K-1], then total ROW_PAD times: candidates past K never verify
-    const uint32_t n_rows = TABLE == TAB_LANE ? L : 1u;
-    // shared layout: rings[blockDim.x][RING_STRIDE] | rows[n_rows][K+1] u32 | luts[n_rows][nb] LUT_T
+    const uint32_t n_rows = TABLE == TAB_LANE ? CB : 1u;         // the lanes of one chunk share its row and LUT
+    // shared layout: rings[blockDim.x][RING_STRIDE] | rows[n_rows][K+ROW_PAD] u32 | luts[n_rows][nb] LUT_T
     uint8_t* s_ring = s_raw;
     uint32_t* s_rows = reinterpret_cast<uint32_t*>(s_raw + (size_t)blockDim.x * RING_STRIDE);
     LUT_T* s_luts = reinterpret_cast<LUT_T*>(s_rows + (size_t)n_rows * row_words);
@@ -77,7 +82,7 @@ __global__ void __launch_bounds__(512, 1) decode_row_kernel(DecodeRowArgs a) {
     // ---- prologue: cum rows (coalesced) and bucket LUTs
     {
         const uint64_t left = a.n_chunks - block_first;
-        const uint32_t lanes = TABLE == TAB_LANE ? (left < L ? (uint32_t)left : L) : 1u;
+        const uint32_t lanes = TABLE == TAB_LANE ? (left < CB ? (uint32_t)left : CB) : 1u;  // rows to build
         for (uint32_t l = 0; l < lanes; l++) {
             const uint64_t model = TABLE == TAB_LANE ? block_first + l : 0;
             const uint2* t = a.tabs + model * K;
@@ -128,19 +133,24 @@ __global__ void __launch_bounds__(512, 1) decode_row_kernel(DecodeRowArgs a) {
         __syncthreads();
     }
     if (threadIdx.x >= L) return;
-    const uint64_t chunk = block_first + threadIdx.x;
-    if (chunk >= a.n_chunks) return;
-    const uint64_t first = chunk * a.chunk_syms;
-    const uint64_t chunk_cnt = (a.n_syms - first < a.chunk_syms) ? (a.n_syms - first) : a.chunk_syms;
+    const LanePart lp = lane_part(block_first * parts + threadIdx.x, parts, a.n_chunks, a.n_syms, a.chunk_syms,
+                                  a.restart_syms);
+    if (!lp.has) return;
+    const uint64_t chunk = lp.chunk, first = lp.first, chunk_cnt = lp.chunk_cnt;
+    const uint32_t my_row = (uint32_t)(chunk - block_first);
     const bool seg_load = a.seg.state && a.seg.load, seg_save = a.seg.state && a.seg.save;
-    const uint64_t seg_begin = a.seg.state ? (a.seg.first < chunk_cnt ? a.seg.first : chunk_cnt) : 0;
-    const uint64_t seg_end =
+    uint64_t seg_begin = a.seg.state ? (a.seg.first < chunk_cnt ? a.seg.first : chunk_cnt) : 0;
+    uint64_t seg_end =
         seg_save ? (a.seg.first + a.seg.syms < chunk_cnt ? a.seg.first + a.seg.syms : chunk_cnt) : chunk_cnt;
+    if (parts > 1) {
+        seg_begin = (uint64_t)lp.part * a.restart_syms;
+        seg_end = seg_begin + a.restart_syms < chunk_cnt ? seg_begin + a.restart_syms : chunk_cnt;
+    }
     const uint64_t cnt_all = seg_end - seg_begin;
     SYM* dst = reinterpret_cast<SYM*>(a.out) + first + seg_begin;
 
-    const uint32_t* row = s_rows + (TABLE == TAB_LANE ? (size_t)threadIdx.x * row_words : 0);
-    const LUT_T* lut = s_luts + (TABLE == TAB_LANE ? (size_t)threadIdx.x * nb : 0);
+    const uint32_t* row = s_rows + (TABLE == TAB_LANE ? (size_t)my_row * row_words : 0);
+    const LUT_T* lut = s_luts + (TABLE == TAB_LANE ? (size_t)my_row * nb : 0);
     const ModelHdr hdr = TABLE == TAB_SHARED ? s_hdr : a.hdrs[chunk];
     const DivParams div = hdr.div;
     const bool pow2 = (hdr.flags & MODEL_POW2) != 0;
@@ -148,12 +158,23 @@ __global__ void __launch_bounds__(512, 1) decode_row_kernel(DecodeRowArgs a) {
     const uint64_t total_bytes = a.offsets[a.n_chunks];
     uint64_t off0 = a.offsets[chunk], off1 = a.offsets[chunk + 1];
     // caller-supplied offsets are validated per lane (see decode_kernel): a bad lane decodes nothing
-    const bool offsets_ok = off0 <= off1 && off1 - off0 >= 8 && off1 <= total_bytes;
+    bool offsets_ok = off0 <= off1 && off1 - off0 >= 8 && off1 <= total_bytes;
+    Restart rp{0ull, ~0ull, 0u, 0u};  // entry state: RangeCoder::new, or a restart point (see decode_kernel)
+    bool restart_ok = true;
+    if (lp.part) {
+        rp = a.restart[chunk * (parts - 1u) + (lp.part - 1u)];
+        restart_ok = offsets_ok && rp.rg != 0 && (uint64_t)rp.pos + 8 <= off1 - off0;
+        if (!restart_ok) {
+            offsets_ok = false;
+            rp.pos = 0;
+        }
+    }
     if (!offsets_ok) off0 = off1 = 0;
-    const uint64_t pb = off0 & ~15ull;
+    const uint64_t start = off0 + rp.pos;
+    const uint64_t pb = start & ~15ull;
     const uint64_t readable = ((total_bytes + 15) & ~15ull) - pb;
-    const uint32_t skip = (uint32_t)(off0 & 3u);
-    const uint32_t rd0 = (uint32_t)((off0 - pb) >> 2);
+    const uint32_t skip = (uint32_t)(start & 3u);
+    const uint32_t rd0 = (uint32_t)((start - pb) >> 2);
 
     RingFill fill;
     fill.pbase = a.stream + pb;
@@ -182,7 +203,7 @@ __global__ void __launch_bounds__(512, 1) decode_row_kernel(DecodeRowArgs a) {
     fill.resync(rf);
     DecSink<RingFetch> sink(rf);
 
-    uint64_t lo = 0, rg = ~0ull;
+    uint64_t lo = rp.lo, rg = rp.rg;
     uint32_t err = 0;
     if (seg_load) {
         const DecResume st = a.seg.state[chunk];
@@ -197,7 +218,7 @@ __global__ void __launch_bounds__(512, 1) decode_row_kernel(DecodeRowArgs a) {
     } else {
         sink.prime(skip);  // src/decoder.rs:14-23
     }
-    if (!offsets_ok) err = ST_TRUNCATED;  // src/decoder.rs:33
+    if (!offsets_ok) err = restart_ok ? ST_TRUNCATED : ST_RESTART;  // src/decoder.rs:33
     constexpr uint32_t PER = 4 / sizeof(SYM);
     constexpr uint32_t SYM_BITS = 8 * sizeof(SYM);
     const FusedParams fp = make_fused(div);
@@ -315,6 +336,18 @@ __global__ void __launch_bounds__(512, 1) decode_row_kernel(DecodeRowArgs a) {
         return;
     }
     const uint32_t used = sink.used(sink.f.rd - rd0, skip);
+    if (parts > 1) {  // see decode_kernel: zeroed status, errors only; arrival state checked against the next record
+        if (!err) {
+            if (seg_end == chunk_cnt) {
+                if ((uint64_t)rp.pos + used > off1 - off0) err = ST_TRUNCATED;
+            } else {
+                const Restart nx = a.restart[chunk * (parts - 1u) + lp.part];
+                if (nx.lo != lo || nx.pos != rp.pos + used - 8u) err = ST_RESTART;
+            }
+        }
+        if (err) atomicMax(a.status + chunk, err);
+        return;
+    }
     if (!err && (uint64_t)used > off1 - off0) err = ST_TRUNCATED;  // src/decoder.rs:33
     a.status[chunk] = err;
 }

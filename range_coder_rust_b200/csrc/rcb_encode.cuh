@@ -93,6 +93,10 @@ struct EncodeArgs {
     uint64_t pitch;
     uint32_t* lens;         // [n_chunks]
     uint32_t* status;       // [n_chunks]
+    // restart points (rcb_core.cuh: Restart): record r of a chunk = state in front of symbol (r+1)*restart_syms
+    Restart* restart;       // [n_chunks][restart_per_chunk] or nullptr
+    uint64_t restart_syms;  // multiple of 64
+    uint32_t restart_per_chunk;  // ceil(chunk_syms / restart_syms) - 1
 };
 
 struct RowStore {
@@ -278,6 +282,9 @@ __device__ __forceinline__ void encode_body(const EncodeArgs& a, const CUtensorM
     uint32_t err = 0;
     RowStore rs{a.staging + chunk * a.pitch};
     EncSink<RowStore, true> sink(rs, cap);
+    // restart points of this chunk: rp_n written so far, the next one is due in front of symbol (rp_n+1)*restart_syms
+    Restart* const rpts = a.restart ? a.restart + chunk * a.restart_per_chunk : nullptr;
+    uint32_t rp_n = 0;
 
     constexpr int SPW = 4 / sizeof(SYM);  // symbols per 32-bit word
     using Entries = typename std::conditional<CS, EncEntries4<SPW>, EncEntries<SPW>>::type;
@@ -429,12 +436,20 @@ __device__ __forceinline__ void encode_body(const EncodeArgs& a, const CUtensorM
                             err = r.err;
                         }
                     };
+                    // vectors up to the next restart point (or the end); the hot loop itself is unchanged
+                    const uint64_t rvec = rpts ? a.restart_syms / PER : nvec;
+                    uint64_t lim = rvec < nvec ? rvec : nvec;
+                    for (;;) {
+                    bool full = false;
 #pragma unroll 1
-                    for (; i < nvec; i++) {
+                    for (; i < lim; i++) {
                         uint4 nxt;
                         if constexpr (TMA_IN) {
                             // the warp leaves together (lane 0 issues the loads the others wait for)
-                            if (__any_sync(wmask, fs.pos + 320u > cap)) break;
+                            if (__any_sync(wmask, fs.pos + 320u > cap)) {
+                                full = true;
+                                break;
+                            }
                             const uint32_t k = (uint32_t)i & 3u, col = (uint32_t)(i >> 2);
                             if (k == 0 && col >= 1) {
                                 // every vector of column col-1 has been consumed (the last one was `cur` of the
@@ -446,7 +461,10 @@ __device__ __forceinline__ void encode_body(const EncodeArgs& a, const CUtensorM
                             if (k == 3 && i + 1 < nvec) tma_wait(col + 1);  // vector i+1 opens the next column
                             nxt = i + 1 < nvec ? tma_vec(i + 1) : make_uint4(0u, 0u, 0u, 0u);
                         } else {
-                        if (fs.pos + 320u > cap) break;  // finish this chunk on the capacity-checked path
+                        if (fs.pos + 320u > cap) {  // finish this chunk on the capacity-checked path
+                            full = true;
+                            break;
+                        }
                         // request piece i+AHEAD (its slot held piece i-2), retire all but the newest AHEAD-1
                         // groups: pieces <= i+1 have landed
                         const uint64_t q = i + ENC_RING_AHEAD;
@@ -464,6 +482,13 @@ __device__ __forceinline__ void encode_body(const EncodeArgs& a, const CUtensorM
                         eA = lookup(i + 1 < nvec ? nxt.x : 0u);  // word 0 of the next vector (unused past the end)
                         code(eB);
                         cur = nxt;
+                    }
+                    if (full || i >= nvec) break;
+                    // restart point in front of vector i: lower as it stands, range as rpt * total, and the
+                    // bytes emitted so far = stored + pending in the sink + the previous symbol's deferred ones
+                    rpts[rp_n++] = Restart{lo, MODE == FUSE_GEN ? rpt * (uint64_t)div.total : rpt << fp.s,
+                                           fs.pos + (fs.nb >> 3) + (em_sh >> 3), 0u};
+                    lim = nvec - i > rvec ? i + rvec : nvec;
                     }
                     // back to the generic (lower, range) form: range = rpt * total keeps range / total
                     // == rpt, the only way `range` is used before the next update
@@ -501,6 +526,8 @@ __device__ __forceinline__ void encode_body(const EncodeArgs& a, const CUtensorM
 #pragma unroll 1
                 for (; i < nvec; i++) {
                     prefetch_block(i);
+                    if (rpts && i * PER == (uint64_t)(rp_n + 1u) * a.restart_syms)
+                        rpts[rp_n++] = Restart{lo, rg, sink.pos + (sink.nb >> 3), 0u};
                     const uint4 nxt = (i + 1 < nvec) ? ldg_stream_v4(v + i + 1) : make_uint4(0, 0, 0, 0);
                     Entries eB = lookup(cur.y);
                     code(eA);
@@ -517,7 +544,13 @@ __device__ __forceinline__ void encode_body(const EncodeArgs& a, const CUtensorM
         }
     }
 #pragma unroll 1
-    for (uint64_t i = done; i < cnt; i++) generic_symbol(entry((uint32_t)src[i]));
+    for (uint64_t i = done; i < cnt; i++) {
+        if (rpts && i == (uint64_t)(rp_n + 1u) * a.restart_syms)
+            rpts[rp_n++] = Restart{lo, rg, sink.pos + (sink.nb >> 3), 0u};
+        generic_symbol(entry((uint32_t)src[i]));
+    }
+    if (rpts)  // a ragged last chunk has fewer restart points: the rest are marked absent (range 0)
+        for (; rp_n < a.restart_per_chunk; rp_n++) rpts[rp_n] = Restart{0ull, 0ull, 0u, 0u};
 
     uint32_t len = sink.finish(lo);  // src/encoder.rs:40-46
     if (!err && sink.overflowed()) err = ST_OUT_CAPACITY;

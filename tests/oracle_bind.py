@@ -43,6 +43,8 @@ def lib():
         L = ctypes.CDLL(ORACLE_LIB)
         L.rco_encode.restype = _i64
         L.rco_encode.argtypes = [_vp, _u64, _ci, _u32, _vp, _vp, _u32, _vp, _u64]
+        L.rco_encode_state.restype = _i64
+        L.rco_encode_state.argtypes = [_vp, _u64, _ci, _u32, _vp, _vp, _u32, _vp, _vp]
         L.rco_decode.restype = _i64
         L.rco_decode.argtypes = [_vp, _u64, _u64, _ci, _u32, _vp, _vp, _u32, _vp]
         L.rco_histogram.restype = None
@@ -118,6 +120,19 @@ def encode(syms, c, cum, total, cap=None):
     if n < 0:
         raise ValueError(RCO_ERR.get(n, str(n)))
     return out[:n].tobytes()
+
+
+def encode_state(syms, c, cum, total):
+    """Encoder state after `syms` and before finish(): (lower_bound, range, bytes emitted so far)."""
+    syms = np.ascontiguousarray(syms)
+    c = np.ascontiguousarray(c, dtype=np.uint32)
+    cum = np.ascontiguousarray(cum, dtype=np.uint32)
+    lo = np.zeros(1, dtype=np.uint64)
+    rg = np.zeros(1, dtype=np.uint64)
+    n = lib().rco_encode_state(_p(syms), syms.size, syms.dtype.itemsize, c.size, _p(c), _p(cum), total, _p(lo), _p(rg))
+    if n < 0:
+        raise ValueError(RCO_ERR.get(n, str(n)))
+    return int(lo[0]), int(rg[0]), int(n)
 
 
 def decode(code, n_syms, c, cum, total, sym_bytes=1):
