@@ -944,6 +944,7 @@ struct DecPlan {
     int table;      // TAB_*
     int fmode;      // FM_* (row kernel), FM_BIG / FM_GENERIC (kind 0)
     bool checked, pow2, lut16, m2;
+    bool win;       // fused loop with the position window (rcb_decode.cuh)
     int threads;
     uint32_t lanes, nb;
     size_t smem;
@@ -958,6 +959,10 @@ static DecPlan plan_decode(const rcb_ctx* c, const rcb_model* m, uint64_t n_chun
     const bool regular = (m->bad_bits & 8u) == 0;
     p.threads = pick_threads(c, c->dec_threads, n_chunks * parts);
     p.lanes = (uint32_t)p.threads;
+    {
+        const char* w = getenv("RCB_DEC_WIN");
+        p.win = w ? atoi(w) != 0 : parts > 1;
+    }
     const size_t budget = 216 * 1024;
     const size_t row = ((size_t)m->K + ROW_PAD) * sizeof(uint32_t);  // rcb_decode_row.cuh
     p.lut16 = m->K > 256;
@@ -1052,7 +1057,11 @@ static void launch_decode_variant(rcb_ctx* c, const rcb_model* m, const DecodeAr
     };
     (void)m;
     if (p.table == TAB_SHARED) {
-        if (p.fmode == FM_BIG) go(decode_kernel<SYM, true, true, false, FUSE_BIG>);
+        if (p.fmode == FM_BIG && p.win) go(decode_kernel<SYM, true, true, false, FUSE_BIG, true>);
+        else if (p.fmode == FM_POW2 && p.win) go(decode_kernel<SYM, true, true, false, FUSE_POW2, true>);
+        else if (p.fmode == FM_GEN && p.m2 && p.win) go(decode_kernel<SYM, true, false, false, FUSE_GEN_M2, true>);
+        else if (p.fmode == FM_GEN && p.win) go(decode_kernel<SYM, true, false, false, FUSE_GEN, true>);
+        else if (p.fmode == FM_BIG) go(decode_kernel<SYM, true, true, false, FUSE_BIG>);
         else if (p.fmode == FM_POW2) go(decode_kernel<SYM, true, true, false, FUSE_POW2>);
         else if (p.fmode == FM_GEN && p.m2) go(decode_kernel<SYM, true, false, false, FUSE_GEN_M2>);
         else if (p.fmode == FM_GEN) go(decode_kernel<SYM, true, false, false, FUSE_GEN>);

@@ -670,7 +670,24 @@ struct FusedDec {
     bool ok;      // ... and the fast renormalisation applies
 };
 
-template <int MODE = FUSE_BIG>
+// TPUT = true: the same step tuned for instruction count instead of latency (several warps per scheduler:
+// restart points).  The shift comes from one count-leading-zeros (sh = clz(xh) & 24; equal high words --
+// n1 >= 4 -- give sh = 0) and "loop 2 stays idle" is tested on the shifted range itself, range' << sh >= 2^48,
+// which is exact for n1 <= 3 and fails for n1 >= 4 (range' < 2^32): 3-4 integer instructions instead of 8.
+RCB_HD uint32_t tput_shift(uint32_t xh) {
+#if defined(__CUDA_ARCH__)
+    uint32_t f;  // position of the leading one, 0xFFFFFFFF for 0: clz & 24 == ~f & 24 (one find + one logic op)
+    asm("bfind.u32 %0, %1;" : "=r"(f) : "r"(xh));
+    return ~f & 24u;
+#else
+    return clz32(xh) & 24u;
+#endif
+}
+RCB_HD bool tput_loop2_idle(uint64_t rgp, uint32_t sh) {
+    return funnel_l(lo32(rgp), hi32(rgp), sh) >= (1u << 16);  // hi32(range' << sh) >= 2^16
+}
+
+template <int MODE = FUSE_BIG, bool TPUT = false>
 RCB_HD FusedDec fused_decode_step(uint64_t lo, uint64_t rpt, uint64_t data, const LutEntry& e,
                                   const FusedParams& fp) {
     FusedDec r;
@@ -685,6 +702,21 @@ RCB_HD FusedDec fused_decode_step(uint64_t lo, uint64_t rpt, uint64_t data, cons
     const bool inside = (data - r.nlo) < (up - r.nlo);
     r.rgp = up - r.nlo;
     const uint32_t xh = hi32(r.nlo) ^ hi32(up);
+    if (TPUT) {
+        r.sh = tput_shift(xh);
+        r.takeB = takeB;
+        r.inside = inside;
+        if (MODE == FUSE_BIG) {
+            // rpt_next = range' >> (s - sh); range' << sh >= 2^48  <=>  rpt_next >= 2^(48 - s)  (s >= 24)
+            r.nrpt = r.rgp >> ((fp.k0 + 24u) - r.sh);
+            r.ok = inside & (r.nrpt >= (uint64_t)(1u << (24u - fp.k0)));
+        } else {
+            const uint64_t y = r.rgp << r.sh;
+            r.nrpt = fused_rpt<MODE>(y, fp);
+            r.ok = inside & (hi32(y) >= (1u << 16));
+        }
+        return r;
+    }
     const bool p1 = xh < (1u << 24), p2 = xh < (1u << 16), p3 = xh < (1u << 8);
     if (MODE == FUSE_BIG) {
         const uint32_t k = p2 ? (p3 ? fp.k0 : fp.k0 + 8u) : (p1 ? fp.k0 + 16u : fp.k0 + 24u);
@@ -704,6 +736,7 @@ RCB_HD FusedDec fused_decode_step(uint64_t lo, uint64_t rpt, uint64_t data, cons
 
 // The same step for a general total with divide-free rpt_next: (csA, csB) are recip_of_freq of the
 // entry's two candidates.
+template <bool TPUT = false>
 RCB_HD FusedDec fused_decode_step_cs(uint64_t lo, uint64_t rpt, uint64_t data, const LutEntry& e, uint64_t csA,
                                      uint64_t csB) {
     FusedDec r;
@@ -717,6 +750,14 @@ RCB_HD FusedDec fused_decode_step_cs(uint64_t lo, uint64_t rpt, uint64_t data, c
     const bool inside = (data - r.nlo) < (up - r.nlo);
     r.rgp = up - r.nlo;
     const uint32_t xh = hi32(r.nlo) ^ hi32(up);
+    if (TPUT) {
+        r.sh = tput_shift(xh);
+        const bool exact = fused_rpt_cs(rpt, takeB ? csB : csA, r.sh, r.nrpt);
+        r.takeB = takeB;
+        r.inside = inside;
+        r.ok = inside & exact & tput_loop2_idle(r.rgp, r.sh);
+        return r;
+    }
     const bool p1 = xh < (1u << 24), p2 = xh < (1u << 16), p3 = xh < (1u << 8);
     r.sh = p2 ? (p3 ? 24u : 16u) : (p1 ? 8u : 0u);
     const bool exact = fused_rpt_cs(rpt, takeB ? csB : csA, r.sh, r.nrpt);
@@ -729,6 +770,7 @@ RCB_HD FusedDec fused_decode_step_cs(uint64_t lo, uint64_t rpt, uint64_t data, c
 
 
 // ... and with the table-wide constant (totals >= 2^25): no per-candidate constants to look up
+template <bool TPUT = false>
 RCB_HD FusedDec fused_decode_step_m2(uint64_t lo, uint64_t rpt, uint64_t data, const LutEntry& e, const Recip2& k) {
     FusedDec r;
     const uint64_t loA = mad64x32(rpt, e.cumA, lo);
@@ -741,6 +783,14 @@ RCB_HD FusedDec fused_decode_step_m2(uint64_t lo, uint64_t rpt, uint64_t data, c
     const bool inside = (data - r.nlo) < (up - r.nlo);
     r.rgp = up - r.nlo;
     const uint32_t xh = hi32(r.nlo) ^ hi32(up);
+    if (TPUT) {
+        r.sh = tput_shift(xh);
+        const bool exact = fused_rpt_m2(r.rgp, r.sh, k, r.nrpt);
+        r.takeB = takeB;
+        r.inside = inside;
+        r.ok = inside & exact & tput_loop2_idle(r.rgp, r.sh);
+        return r;
+    }
     const bool p1 = xh < (1u << 24), p2 = xh < (1u << 16), p3 = xh < (1u << 8);
     r.sh = p2 ? (p3 ? 24u : 16u) : (p1 ? 8u : 0u);
     const bool exact = fused_rpt_m2(r.rgp, r.sh, k, r.nrpt);

@@ -110,7 +110,11 @@ struct RingFetch {
 };
 
 // Ring producer side (per lane): pieces [.., wr) have been requested.
-struct RingFill {
+// MIRROR: a piece that goes to slot 0 is also copied behind slot 7 (the 16 bytes of padding of RING_STRIDE), so
+// that 16 contiguous bytes can be read from ANY word of the ring without wrapping the address (position window
+// of the fused loop).
+template <bool MIRROR>
+struct RingFillT {
     const uint8_t* pbase;  // 16-byte aligned
     uint32_t wr;           // pieces requested so far
     uint32_t npieces;      // pieces that exist in the readable stream
@@ -122,7 +126,22 @@ struct RingFill {
             :
             : "r"(saddr), "l"(g), "r"((uint32_t)p)
             : "memory");
+        if (MIRROR) {
+            const bool m = p & ((wr & (RING_PIECES - 1)) == 0u);
+            asm volatile(
+                "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q cp.async.cg.shared.global.L2::256B [%0], [%1], 16;\n\t}"
+                :
+                : "r"(ring + RING_PIECES * 16), "l"(g), "r"((uint32_t)m)
+                : "memory");
+        }
         wr += p ? 1u : 0u;
+    }
+    // Position-window form of round1(): `pos` = first byte (from pbase) the lane has not shifted into data yet.
+    __device__ __forceinline__ void round1_pos(uint32_t pos, uint32_t ring) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        const uint32_t occ = wr * 16 - pos;
+        issue_if((occ <= RING_PIECES * 16 - 16) & (wr < npieces), ring);
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
     // Once per output word, all lanes together: retire older groups, top the ring up (<= 2 pieces).
     __device__ __forceinline__ void round(RingFetch& f) {
@@ -179,6 +198,7 @@ struct RingFill {
         f.reload();
     }
 };
+using RingFill = RingFillT<false>;
 
 // ---------------------------------------------------------------------------
 // Fetch for the exact out-of-line path: the current word is cached; a new word comes from the
@@ -295,9 +315,15 @@ __device__ __noinline__ DecLaneState dec_exact(DecLaneState s, const uint2* tab,
 // FMODE: -1 = generic per-symbol loop (bucket LUT + exact search); FUSE_BIG / FUSE_POW2 / FUSE_GEN = the fused
 // word-speculative loop over the fat LUT for a power-of-two total >= 2^24 / any power of two / any total
 // (FUSE_GEN: divide-free rpt_next from the candidates' reciprocal constants, rcb_core.cuh).
-template <typename SYM, bool SHARED, bool POW2, bool CHECKED, int FMODE>
+// WIN (fused loops only): the code-byte window of the hot loop is addressed by byte position -- `data` is
+// carried by funnel shifts as before, but the bytes that follow it are re-read from the lane's ring once per
+// output word (four 32-bit loads + three byte permutes) and shifted along without any refill bookkeeping:
+// 14 shifts + ~8 other integer instructions per word instead of ~56, on the pipe that bounds the kernel
+// once several lanes per chunk fill the schedulers (restart points).
+template <typename SYM, bool SHARED, bool POW2, bool CHECKED, int FMODE, bool WIN = false>
 __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
     constexpr bool FUSED = FMODE >= 0;
+    static_assert(!WIN || FUSED, "the position window belongs to the fused loops");
     constexpr bool CSM = FMODE == FUSE_GEN;     // general total, per-candidate reciprocal constants (third array)
     constexpr bool M2M = FMODE == FUSE_GEN_M2;  // general total >= 2^25, one table-wide constant
     constexpr bool GENM = CSM || M2M;
@@ -387,7 +413,7 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
     const uint32_t skip = (uint32_t)(start & 3u);
     const uint32_t rd0 = (uint32_t)((start - pb) >> 2);
 
-    RingFill fill;
+    RingFillT<WIN> fill;
     fill.pbase = a.stream + pb;
     fill.wr = 0;
     fill.npieces = !offsets_ok ? 0u : readable > (0xFFFFFFF0ull << 4) ? 0xFFFFFFF0u : (uint32_t)(readable >> 4);
@@ -395,6 +421,12 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
     RingFetch rf;
     rf.ring = (uint32_t)__cvta_generic_to_shared(s_ring + (size_t)threadIdx.x * RING_STRIDE);
     rf.rd = seg_load ? a.seg.state[chunk].rd : rd0;
+    if (WIN && seg_load) {
+        // the position window re-reads the bytes a resumed lane still held in registers: fill the ring from
+        // the word of the first byte that is not in data yet
+        const DecResume st = a.seg.state[chunk];
+        rf.rd = (st.rd * 4u - (st.cnt >> 3)) >> 2;
+    }
     rf.cur = 0;
     const uint32_t last_word = fill.npieces ? fill.npieces * 4 - 1 : 0u;
 
@@ -427,6 +459,7 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
         sink.wh = st.wh;
         sink.wl = st.wl;
         sink.cnt = st.cnt;
+        sink.f.rd = st.rd;  // with (wh, wl, cnt): the position st.rd * 4 - cnt / 8 the fused loop starts from
         err = st.err;
     } else {
         sink.prime(skip);  // src/decoder.rs:14-23
@@ -510,21 +543,8 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
         auto checkpoint = [&]() -> WordChk {
             return WordChk{lo, rpt, sink.dh, sink.dl, sink.wh, sink.wl, sink.cnt, sink.f.rd};
         };
-        auto redo_word = [&](const WordChk& chk) -> uint32_t {
-            lo = chk.lo;
-            rpt = chk.rpt;
-            sink.dh = chk.dh;
-            sink.dl = chk.dl;
-            sink.wh = chk.wh;
-            sink.wl = chk.wl;
-            sink.cnt = chk.cnt;
-            sink.f.rd = chk.rd;
-            // Everything requested has landed (the newest piece was issued a whole word ago: no wait in
-            // practice).  The re-decode reads at most 4 x 14 bytes beyond the checkpoint, so with >= 64 bytes
-            // in the ring it needs no new piece -- and no round trip to memory; otherwise (a run of unclean
-            // words, the start of a chunk) fill the ring to the brim first.  Either way the invariant of
-            // round1() (enough landed bytes for a clean word) holds again afterwards.
-            fill.redo_ready(sink.f);
+        // the symbols of an unclean word, one at a time on the generic sink (lo / rpt / sink at the checkpoint)
+        auto redo_symbols = [&]() -> uint32_t {
             uint32_t acc = 0;
 #pragma unroll 1
             for (uint32_t b = 0; b < PER; b++) {
@@ -555,36 +575,178 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
             bf = lut_bf16_init(sink.data() - lo, rg, lut_scale);
             return acc;
         };
-        // Main loop: the words every live lane of the warp has (all of them, except in a warp holding the
-        // ragged last chunk).  Its only branch in the common case is the back edge, and that branch is
-        // warp-uniform (vote): a taken branch costs ~35 cycles on this one-warp-per-scheduler kernel, and a
-        // per-lane exit would park the lane at the reconvergence point until its whole warp left the loop.
+        auto redo_word = [&](const WordChk& chk) -> uint32_t {
+            lo = chk.lo;
+            rpt = chk.rpt;
+            sink.dh = chk.dh;
+            sink.dl = chk.dl;
+            sink.wh = chk.wh;
+            sink.wl = chk.wl;
+            sink.cnt = chk.cnt;
+            sink.f.rd = chk.rd;
+            // Everything requested has landed (the newest piece was issued a whole word ago: no wait in
+            // practice).  The re-decode reads at most 4 x 14 bytes beyond the checkpoint, so with >= 64 bytes
+            // in the ring it needs no new piece -- and no round trip to memory; otherwise (a run of unclean
+            // words, the start of a chunk) fill the ring to the brim first.  Either way the invariant of
+            // round1() (enough landed bytes for a clean word) holds again afterwards.
+            fill.redo_ready(sink.f);
+            return redo_symbols();
+        };
         const uint32_t nw_warp = __reduce_min_sync(live, (uint32_t)(nw < 0xFFFFFFFFull ? nw : 0xFFFFFFFFull));
         uint64_t i = 0;
-        while (i < nw_warp) {
-            WordChk chk;
-            uint32_t acc;
-            bool bad, leave;
+        if constexpr (WIN) {
+            // ---- position window.  (dh:dl) = data, pos = first byte (from pbase) not yet shifted into it.
+            uint32_t dh = sink.dh, dl = sink.dl;
+            uint32_t pos = sink.f.rd * 4u - (sink.cnt >> 3);
+            const uint32_t ring = sink.f.ring;
+            // the generic sink (exact re-decode, tail symbols) re-attached at `pos`: like prime() without the 8
+            // bytes that are already in data; the word at pos / 4 has landed (callers make sure)
+            auto attach = [&]() {
+                sink.dh = dh;
+                sink.dl = dl;
+                sink.f.rd = pos >> 2;
+                sink.f.reload();
+                const uint32_t skipb = pos & 3u;
+                const uint32_t first = sink.f.peek_be32();
+                sink.f.advance_if(true);
+                sink.wh = first << (8u * skipb);
+                sink.wl = 0;
+                sink.cnt = 32u - 8u * skipb;
+                sink.refill();
+            };
+            auto detach = [&]() {
+                dh = sink.dh;
+                dl = sink.dl;
+                pos = sink.f.rd * 4u - (sink.cnt >> 3);
+            };
+            struct WordChkW {
+                uint64_t lo, rpt;
+                uint32_t dh, dl, pos;
+            };
+            auto decode_word_w = [&](uint32_t& acc, bool& bad) {
+                acc = 0;
+                bad = false;
+                // the 3 * PER bytes that follow data, big-endian, from the (mirrored) ring: no address wrap
+                const uint32_t a0 = ring + (pos & (RING_PIECES * 16u - 4u));
+                const uint32_t sel = (pos & 3u) * 0x1111u + 0x0123u;  // bytes o .. o+3 of a word pair, reversed
+                uint32_t x0, x1, x2, x3 = 0;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x0) : "r"(a0) : "memory");
+                asm volatile("ld.shared.b32 %0, [%1+4];" : "=r"(x1) : "r"(a0) : "memory");
+                asm volatile("ld.shared.b32 %0, [%1+8];" : "=r"(x2) : "r"(a0) : "memory");
+                if (PER > 2) asm volatile("ld.shared.b32 %0, [%1+12];" : "=r"(x3) : "r"(a0) : "memory");
+                uint32_t w0 = __byte_perm(x0, x1, sel), w1 = __byte_perm(x1, x2, sel);
+                uint32_t w2 = PER > 2 ? __byte_perm(x2, x3, sel) : 0u;
+                uint32_t tot = 0;
+#pragma unroll
+                for (uint32_t b = 0; b < PER; b++) {
+                    const uint64_t data = ((uint64_t)dh << 32) | dl;
+                    const uint32_t off = lut_offset16(bf);
+                    const LutEntry e = lds_lut(lut_saddr + off);
+                    const float2 rc = lds_f2(rc_saddr + (off >> 1));
+                    FusedDec r;
+                    if constexpr (CSM) {
+                        const LutEntry k = lds_lut(cs_saddr + off);  // {csA lo, csA hi, csB lo, csB hi}
+                        r = fused_decode_step_cs<true>(lo, rpt, data, e, ((uint64_t)k.cumB << 32) | k.cumA,
+                                                 ((uint64_t)k.syms << 32) | k.cumC);
+                    } else if constexpr (M2M) {
+                        r = fused_decode_step_m2<true>(lo, rpt, data, e, k2);
+                    } else {
+                        r = fused_decode_step<MODE, true>(lo, rpt, data, e, fp);
+                    }
+                    bf = u64_to_float(data - r.nlo) * (q * (r.takeB ? rc.y : rc.x));
+                    // shift the window: a symbol takes <= 3 bytes on the fast path, so of the bytes behind data
+                    // only 3 * (symbols still to come) matter -- one register fewer per symbol
+                    dh = funnel_l(dl, dh, r.sh);
+                    dl = funnel_l(w0, dl, r.sh);
+                    if (b + 1 < PER) w0 = funnel_l(w1, w0, r.sh);
+                    if (b + 2 < PER) w1 = funnel_l(w2, w1, r.sh);
+                    if (b + 3 < PER) w2 <<= r.sh;
+                    tot += r.sh;
+                    lo = r.nlo << r.sh;
+                    rpt = r.nrpt;
+                    q = q_of(rpt);
+                    acc |= r.sym << (SYM_BITS * b);
+                    bad |= !r.ok;
+                }
+                pos += tot >> 3;
+            };
+            auto redo_word_w = [&](const WordChkW& chk) -> uint32_t {
+                lo = chk.lo;
+                rpt = chk.rpt;
+                dh = chk.dh;
+                dl = chk.dl;
+                pos = chk.pos;
+                sink.f.rd = pos >> 2;
+                fill.redo_ready(sink.f);  // everything requested has landed; >= 64 bytes from the checkpoint on
+                attach();
+                const uint32_t acc = redo_symbols();
+                detach();
+                // the next clean word reads 16 bytes from the word of `pos`: top the ring up if the exact path ate
+                // into that margin (the per-word round adds at most one piece)
+                if ((int32_t)(fill.wr * 16u - pos) < 48 && fill.wr < fill.npieces) {
+                    sink.f.rd = pos >> 2;
+                    fill.resync(sink.f);
+                }
+                return acc;
+            };
+            while (i < nw_warp) {
+                WordChkW chk;
+                uint32_t acc;
+                bool bad, leave;
 #pragma unroll 1
-            do {
+                do {
+                    fill.round1_pos(pos, ring);
+                    chk = WordChkW{lo, rpt, dh, dl, pos};
+                    decode_word_w(acc, bad);
+                    dw[i] = acc;  // speculative as well: rewritten below when the word was not clean
+                    ++i;
+                    leave = __any_sync(live, bad) | (i >= nw_warp);
+                } while (!leave);
+                if (bad) dw[i - 1] = redo_word_w(chk);
+            }
+#pragma unroll 1
+            for (; i < nw; i++) {  // ragged warp only
+                fill.round1_pos(pos, ring);
+                const WordChkW chk{lo, rpt, dh, dl, pos};
+                uint32_t acc;
+                bool bad;
+                decode_word_w(acc, bad);
+                if (RCB_UNLIKELY(bad)) acc = redo_word_w(chk);
+                dw[i] = acc;
+            }
+            // back to the generic sink for the tail symbols and the final accounting
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            attach();
+        } else {
+            // Main loop: the words every live lane of the warp has (all of them, except in a warp holding the
+            // ragged last chunk).  Its only branch in the common case is the back edge, and that branch is
+            // warp-uniform (vote): a taken branch costs ~35 cycles on this one-warp-per-scheduler kernel, and a
+            // per-lane exit would park the lane at the reconvergence point until its whole warp left the loop.
+            while (i < nw_warp) {
+                WordChk chk;
+                uint32_t acc;
+                bool bad, leave;
+    #pragma unroll 1
+                do {
+                    fill.round1(sink.f);
+                    chk = checkpoint();
+                    decode_word(acc, bad);
+                    dw[i] = acc;  // speculative as well: rewritten below when the word was not clean
+                    ++i;
+                    leave = __any_sync(live, bad) | (i >= nw_warp);
+                } while (!leave);
+                if (bad) dw[i - 1] = redo_word(chk);
+            }
+    #pragma unroll 1
+            for (; i < nw; i++) {  // ragged warp only
                 fill.round1(sink.f);
-                chk = checkpoint();
+                const WordChk chk = checkpoint();
+                uint32_t acc;
+                bool bad;
                 decode_word(acc, bad);
-                dw[i] = acc;  // speculative as well: rewritten below when the word was not clean
-                ++i;
-                leave = __any_sync(live, bad) | (i >= nw_warp);
-            } while (!leave);
-            if (bad) dw[i - 1] = redo_word(chk);
-        }
-#pragma unroll 1
-        for (; i < nw; i++) {  // ragged warp only
-            fill.round1(sink.f);
-            const WordChk chk = checkpoint();
-            uint32_t acc;
-            bool bad;
-            decode_word(acc, bad);
-            if (RCB_UNLIKELY(bad)) acc = redo_word(chk);
-            dw[i] = acc;
+                if (RCB_UNLIKELY(bad)) acc = redo_word(chk);
+                dw[i] = acc;
+            }
         }
         done = nw * PER;
         rg = range_of(rpt);

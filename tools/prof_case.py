@@ -20,6 +20,7 @@ def main():
     p = argparse.ArgumentParser()
     p.add_argument("--case", default="2", choices=["2", "2b", "3-16", "3-64", "3-256", "4"])
     p.add_argument("--gib", type=float, default=1.0)
+    p.add_argument("--restart", type=int, default=0, help="restart points every this many symbols (0 = none)")
     a = p.parse_args()
     ctx = rcb.Context(0)
     nb = int(a.gib * (1 << 30))
@@ -43,9 +44,11 @@ def main():
     stream = torch.empty(cap, dtype=torch.uint8, device=ctx.device)
     offsets = torch.empty(n_chunks + 1, dtype=torch.int64, device=ctx.device)
     back = torch.empty_like(d)
+    restart = ctx.restart_points(n_chunks, chunk, a.restart) if a.restart else None
+    kw = {"restart_syms": a.restart, "restart": restart} if restart is not None else {}
     for _ in range(2):
-        ctx.encode_chunks(d, chunk, model, out=stream, offsets=offsets)
-        ctx.decode_chunks(stream, offsets, n, chunk, model, sym_bytes=sb, out=back)
+        ctx.encode_chunks(d, chunk, model, out=stream, offsets=offsets, **kw)
+        ctx.decode_chunks(stream, offsets, n, chunk, model, sym_bytes=sb, out=back, **kw)
     assert torch.equal(back, d)
     print("ok", a.case)
 

@@ -31,7 +31,7 @@ def timed(fn, reps):
     return best
 
 
-def run(ctx, name, n_bytes, K, chunk, mode, zipf, reps, odd_total=False):
+def run(ctx, name, n_bytes, K, chunk, mode, zipf, reps, odd_total=False, parts=(1,)):
     sb = 1 if K <= 256 else 2
     n = n_bytes // sb
     if mode == "adaptive":
@@ -69,6 +69,23 @@ def run(ctx, name, n_bytes, K, chunk, mode, zipf, reps, odd_total=False):
     res["round_trip_ok"] = bool(torch.equal(back, d))
     res["encode_gbs"] = n_bytes / res["encode_ms"] / 1e6
     res["decode_gbs"] = n_bytes / res["decode_ms"] / 1e6
+    # restart points: `p` decoder lanes per chunk (the encoder records its state every chunk / p symbols)
+    for p in parts:
+        if p <= 1 or chunk % (64 * p):
+            continue
+        rs = chunk // p
+        pts = ctx.restart_points(n_chunks, chunk, rs)
+        kw = {"restart_syms": rs, "restart": pts}
+        ctx.encode_chunks(d, chunk, model, out=stream, offsets=offsets, **kw)
+        enc = timed(lambda: ctx.encode_chunks(d, chunk, model, out=stream, offsets=offsets, sync=False, **kw), reps)
+        ctx.encode_result()
+        back.zero_()
+        ctx.decode_chunks(stream, offsets, n, chunk, model, sym_bytes=sb, out=back, **kw)
+        dec = timed(lambda: ctx.decode_chunks(stream, offsets, n, chunk, model, sym_bytes=sb, out=back, sync=False,
+                                              **kw), reps)
+        ctx.decode_result()
+        res[f"restart_x{p}"] = {"restart_syms": rs, "encode_ms": enc, "decode_ms": dec,
+                                "decode_gbs": n_bytes / dec / 1e6, "round_trip_ok": bool(torch.equal(back, d))}
     print(json.dumps(res), flush=True)
     del d, stream, offsets, back, model
     torch.cuda.empty_cache()
@@ -97,32 +114,34 @@ def main():
     p.add_argument("--reps", type=int, default=3)
     p.add_argument("--gib", type=float, default=1.0)
     p.add_argument("--big", action="store_true", help="also an 8 GiB many-lane batch (config 5's per-GPU shard)")
+    p.add_argument("--parts", default="1", help="comma-separated decoder lanes per chunk to add (restart points)")
     p.add_argument("--only", default="", help="comma-separated config tags to run (2,3-16,3-64,3-256,4,2b,2c,f4)")
     a = p.parse_args()
     only = set(x for x in a.only.split(",") if x)
+    parts = tuple(int(x) for x in a.parts.split(",") if x)
 
     def want(tag):
         return not only or tag in only
     ctx = rcb.Context(0)
     nb = int(a.gib * (1 << 30))
     if want("2"):
-        run(ctx, "2: static global table, Zipf 1.1, K=256", nb, 256, 65536, "static", 1.1, a.reps)
+        run(ctx, "2: static global table, Zipf 1.1, K=256", nb, 256, 65536, "static", 1.1, a.reps, parts=parts)
     for chunk in (16384, 65536, 262144):
         if want(f"3-{chunk // 1024}"):
             run(ctx, f"3: adaptive per-chunk, mixed entropy, K=256, chunk {chunk // 1024} KiB", nb, 256, chunk,
-                "adaptive", None, a.reps)
+                "adaptive", None, a.reps, parts=parts)
     if want("4"):
-        run(ctx, "4: K=4096 (u16), Zipf 1.1, static global table", nb, 4096, 32768, "static", 1.1, a.reps)
+        run(ctx, "4: K=4096 (u16), Zipf 1.1, static global table", nb, 4096, 32768, "static", 1.1, a.reps, parts=parts)
     if want("2b"):
         run(ctx, "2b: static table with a non-power-of-two total", nb, 256, 65536, "static", 1.1, a.reps,
-            odd_total=True)
+            odd_total=True, parts=parts)
     if want("2c"):
-        run(ctx, "2c: static global table, 16 KiB chunks (65536 lanes)", nb, 256, 16384, "static", 1.1, a.reps)
+        run(ctx, "2c: static global table, 16 KiB chunks (65536 lanes)", nb, 256, 16384, "static", 1.1, a.reps, parts=parts)
     if want("f4"):
         run_f4(ctx, nb, 65536, a.reps)
     if a.big:
         run(ctx, "5: 8 GiB per-GPU shard, static table, 64 KiB chunks (131072 lanes)", 8 << 30, 256, 65536, "static",
-            1.1, max(1, a.reps - 1))
+            1.1, max(1, a.reps - 1), parts=parts)
 
 
 if __name__ == "__main__":
