@@ -944,7 +944,7 @@ struct DecPlan {
     int table;      // TAB_*
     int fmode;      // FM_* (row kernel), FM_BIG / FM_GENERIC (kind 0)
     bool checked, pow2, lut16, m2;
-    bool win;       // fused loop with the position window (rcb_decode.cuh)
+    bool tp;        // fused loop tuned for throughput (rcb_decode.cuh: TP)
     int threads;
     uint32_t lanes, nb;
     size_t smem;
@@ -960,8 +960,10 @@ static DecPlan plan_decode(const rcb_ctx* c, const rcb_model* m, uint64_t n_chun
     p.threads = pick_threads(c, c->dec_threads, n_chunks * parts);
     p.lanes = (uint32_t)p.threads;
     {
-        const char* w = getenv("RCB_DEC_WIN");
-        p.win = w ? atoi(w) != 0 : parts > 1;
+        // several warps per scheduler (restart points, many chunks): the throughput flavour of the fused loop
+        const char* w = getenv("RCB_DEC_TP");
+        const uint64_t sched = 4ull * (uint64_t)(c->sm_count > 0 ? c->sm_count : 148);
+        p.tp = w ? atoi(w) != 0 : n_chunks * parts >= 2 * 32 * sched;
     }
     const size_t budget = 216 * 1024;
     const size_t row = ((size_t)m->K + ROW_PAD) * sizeof(uint32_t);  // rcb_decode_row.cuh
@@ -1057,10 +1059,10 @@ static void launch_decode_variant(rcb_ctx* c, const rcb_model* m, const DecodeAr
     };
     (void)m;
     if (p.table == TAB_SHARED) {
-        if (p.fmode == FM_BIG && p.win) go(decode_kernel<SYM, true, true, false, FUSE_BIG, true>);
-        else if (p.fmode == FM_POW2 && p.win) go(decode_kernel<SYM, true, true, false, FUSE_POW2, true>);
-        else if (p.fmode == FM_GEN && p.m2 && p.win) go(decode_kernel<SYM, true, false, false, FUSE_GEN_M2, true>);
-        else if (p.fmode == FM_GEN && p.win) go(decode_kernel<SYM, true, false, false, FUSE_GEN, true>);
+        if (p.fmode == FM_BIG && p.tp) go(decode_kernel<SYM, true, true, false, FUSE_BIG, true>);
+        else if (p.fmode == FM_POW2 && p.tp) go(decode_kernel<SYM, true, true, false, FUSE_POW2, true>);
+        else if (p.fmode == FM_GEN && p.m2 && p.tp) go(decode_kernel<SYM, true, false, false, FUSE_GEN_M2, true>);
+        else if (p.fmode == FM_GEN && p.tp) go(decode_kernel<SYM, true, false, false, FUSE_GEN, true>);
         else if (p.fmode == FM_BIG) go(decode_kernel<SYM, true, true, false, FUSE_BIG>);
         else if (p.fmode == FM_POW2) go(decode_kernel<SYM, true, true, false, FUSE_POW2>);
         else if (p.fmode == FM_GEN && p.m2) go(decode_kernel<SYM, true, false, false, FUSE_GEN_M2>);
@@ -1127,7 +1129,9 @@ static int decode_issue(rcb_ctx* c, const uint8_t* d_stream, const uint64_t* d_o
     a.per_chunk = !shared;
     a.out = d_syms_out;
     a.status = status;
-    const DecPlan plan = plan_decode(c, m, n_chunks, parts);
+    DecPlan plan = plan_decode(c, m, n_chunks, parts);
+    // the throughput flavour stores 16 bytes at a time: every lane's part of the output must start 16-byte aligned
+    if ((chunk_syms * (uint64_t)sym_bytes) % 16 || (seg && (seg->first * (uint64_t)sym_bytes) % 16)) plan.tp = false;
     const uint64_t n_lanes = n_chunks * parts;
     const unsigned blocks = (unsigned)((n_lanes + plan.lanes - 1) / plan.lanes);  // row kernel: lanes % parts == 0
     if (plan.kind == 0) {

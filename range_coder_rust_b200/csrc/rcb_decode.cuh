@@ -315,15 +315,19 @@ __device__ __noinline__ DecLaneState dec_exact(DecLaneState s, const uint2* tab,
 // FMODE: -1 = generic per-symbol loop (bucket LUT + exact search); FUSE_BIG / FUSE_POW2 / FUSE_GEN = the fused
 // word-speculative loop over the fat LUT for a power-of-two total >= 2^24 / any power of two / any total
 // (FUSE_GEN: divide-free rpt_next from the candidates' reciprocal constants, rcb_core.cuh).
-// WIN (fused loops only): the code-byte window of the hot loop is addressed by byte position -- `data` is
-// carried by funnel shifts as before, but the bytes that follow it are re-read from the lane's ring once per
-// output word (four 32-bit loads + three byte permutes) and shifted along without any refill bookkeeping:
-// 14 shifts + ~8 other integer instructions per word instead of ~56, on the pipe that bounds the kernel
-// once several lanes per chunk fill the schedulers (restart points).
-template <typename SYM, bool SHARED, bool POW2, bool CHECKED, int FMODE, bool WIN = false>
+// The fused loops address the code bytes by position: `data` is carried by funnel shifts, the bytes that
+// follow it are re-read from the lane's ring once per output word (four 32-bit loads + three byte permutes)
+// and shifted along without any refill bookkeeping (14 shifts + ~8 other integer instructions per word where
+// a counted refill per symbol took ~56).
+// TP (fused loops only) = tuned for throughput instead of latency: with several warps per scheduler (restart
+// points, many chunks) the loop is bound by the integer pipe and by shared-memory / LSU wavefronts, not by the
+// dependency chain -- so the bucket estimate takes its one reciprocal AFTER the symbol is known (no second
+// table: -6 wavefronts per symbol) and output words leave 16 bytes at a time (-24 wavefronts per word).
+template <typename SYM, bool SHARED, bool POW2, bool CHECKED, int FMODE, bool TP = false>
 __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
     constexpr bool FUSED = FMODE >= 0;
-    static_assert(!WIN || FUSED, "the position window belongs to the fused loops");
+    constexpr bool WIN = FUSED;  // mirrored ring
+    static_assert(!TP || FUSED, "TP belongs to the fused loops");
     constexpr bool CSM = FMODE == FUSE_GEN;     // general total, per-candidate reciprocal constants (third array)
     constexpr bool M2M = FMODE == FUSE_GEN_M2;  // general total >= 2^25, one table-wide constant
     constexpr bool GENM = CSM || M2M;
@@ -352,7 +356,7 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
         for (uint32_t i = threadIdx.x; i < nb_pad; i += blockDim.x) {
             const uint4 e = i < nb ? gl[i] : make_uint4(total, total, total, 0u);  // empty interval: never verifies
             sl[i] = e;
-            if (FUSED)  // reciprocals of the candidates' frequencies for the shift-free estimate (rcb_core.cuh)
+            if (FUSED && !TP)  // reciprocals of the candidates' frequencies for the shift-free estimate (rcb_core.cuh)
                 s_rc[i] = make_float2(lut_rc16(e.y - e.x, s_hdr.lut_scale, sr), lut_rc16(e.z - e.y, s_hdr.lut_scale, sr));
             if (CSM) s_cs[i] = i < nb ? a.lut_cs[i] : make_uint4(0u, 0u, 0u, 0u);
         }
@@ -487,8 +491,10 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
     };
 
     uint64_t done = 0;
-    const bool aligned = (reinterpret_cast<uintptr_t>(dst) & 3u) == 0;
     uint32_t* dw = reinterpret_cast<uint32_t*>(dst);
+    // TP stores 16 bytes at a time (hosts pick it only for 16-byte aligned parts; a lane that is not decodes its
+    // symbols one by one below)
+    const bool aligned = (reinterpret_cast<uintptr_t>(dst) & (TP ? 15u : 3u)) == 0;
     const uint64_t nw = aligned ? cnt / PER : 0;
 
     if constexpr (FUSED) {
@@ -503,48 +509,110 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
         const uint32_t lut_saddr = (uint32_t)__cvta_generic_to_shared(s_lut);
         const uint32_t rc_saddr = lut_saddr + 4096u * (uint32_t)sizeof(LutEntry);
         const uint32_t cs_saddr = rc_saddr + 4096u * (uint32_t)sizeof(float2);
+        const uint32_t stage_saddr = rc_saddr;  // TP has no reciprocal table: its 32 KiB hold the staged output words
+
+        // ---- position window.  (dh:dl) = data, pos = first byte (from pbase) not yet shifted into it.
+        uint32_t dh = sink.dh, dl = sink.dl;
+        uint32_t pos = sink.f.rd * 4u - (sink.cnt >> 3);
+        const uint32_t ring = sink.f.ring;
+        // the generic sink (exact re-decode, tail symbols) re-attached at `pos`: like prime() without the 8
+        // bytes that are already in data; the word at pos / 4 has landed (callers make sure)
+        auto attach = [&]() {
+            sink.dh = dh;
+            sink.dl = dl;
+            sink.f.rd = pos >> 2;
+            sink.f.reload();
+            const uint32_t skipb = pos & 3u;
+            const uint32_t first = sink.f.peek_be32();
+            sink.f.advance_if(true);
+            sink.wh = first << (8u * skipb);
+            sink.wl = 0;
+            sink.cnt = 32u - 8u * skipb;
+            sink.refill();
+        };
+        auto detach = [&]() {
+            dh = sink.dh;
+            dl = sink.dl;
+            pos = sink.f.rd * 4u - (sink.cnt >> 3);
+        };
+        struct WordChk {  // lane state at the start of a word: what the re-decode restarts from
+            uint64_t lo, rpt;
+            uint32_t dh, dl, pos;
+        };
         // Four symbols, straight-line and speculative; `bad` = some symbol needs the exact path.
         auto decode_word = [&](uint32_t& acc, bool& bad) {
             acc = 0;
             bad = false;
+            // the 3 * PER bytes that follow data, big-endian, from the (mirrored) ring: no address wrap
+            const uint32_t a0 = ring + (pos & (RING_PIECES * 16u - 4u));
+            const uint32_t sel = (pos & 3u) * 0x1111u + 0x0123u;  // bytes o .. o+3 of a word pair, reversed
+            uint32_t x0, x1, x2, x3 = 0;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x0) : "r"(a0) : "memory");
+            asm volatile("ld.shared.b32 %0, [%1+4];" : "=r"(x1) : "r"(a0) : "memory");
+            asm volatile("ld.shared.b32 %0, [%1+8];" : "=r"(x2) : "r"(a0) : "memory");
+            if (PER > 2) asm volatile("ld.shared.b32 %0, [%1+12];" : "=r"(x3) : "r"(a0) : "memory");
+            uint32_t w0 = __byte_perm(x0, x1, sel), w1 = __byte_perm(x1, x2, sel);
+            uint32_t w2 = PER > 2 ? __byte_perm(x2, x3, sel) : 0u;
+            uint32_t tot = 0;
 #pragma unroll
             for (uint32_t b = 0; b < PER; b++) {
-                const uint64_t data = sink.data();
+                const uint64_t data = ((uint64_t)dh << 32) | dl;
                 const uint32_t off = lut_offset16(bf);
                 const LutEntry e = lds_lut(lut_saddr + off);
-                const float2 rc = lds_f2(rc_saddr + (off >> 1));
+                float2 rc = make_float2(0.f, 0.f);
+                if (!TP) rc = lds_f2(rc_saddr + (off >> 1));
                 FusedDec r;
                 if constexpr (CSM) {
                     const LutEntry k = lds_lut(cs_saddr + off);  // {csA lo, csA hi, csB lo, csB hi}
-                    r = fused_decode_step_cs(lo, rpt, data, e, ((uint64_t)k.cumB << 32) | k.cumA,
-                                             ((uint64_t)k.syms << 32) | k.cumC);
+                    r = fused_decode_step_cs<true>(lo, rpt, data, e, ((uint64_t)k.cumB << 32) | k.cumA,
+                                                   ((uint64_t)k.syms << 32) | k.cumC);
                 } else if constexpr (M2M) {
-                    r = fused_decode_step_m2(lo, rpt, data, e, k2);
+                    r = fused_decode_step_m2<true>(lo, rpt, data, e, k2);
                 } else {
-                    r = fused_decode_step<MODE>(lo, rpt, data, e, fp);
+                    r = fused_decode_step<MODE, true>(lo, rpt, data, e, fp);
                 }
-                // next symbol's entry from the unshifted residue: no dependence on the shift (rcb_core.cuh)
-                bf = u64_to_float(data - r.nlo) * (q * (r.takeB ? rc.y : rc.x));
-                sink.put(0u, r.sh);
+                if (TP) {
+                    // next entry from the unshifted residue and the unshifted new range (both sides of
+                    // (data' - lower') / range' carry the same shift): one reciprocal after the symbol is
+                    // known, no second table -- shared-memory wavefronts, not latency, bound this flavour
+                    bf = lut_bf16_init(data - r.nlo, r.rgp, lut_scale);
+                } else {
+                    // ... with the reciprocal taken BEFORE the symbol is known (1 / rpt while the table load is
+                    // in flight, const / c from a second table): shortest dependency chain (rcb_core.cuh)
+                    bf = u64_to_float(data - r.nlo) * (q * (r.takeB ? rc.y : rc.x));
+                }
+                // shift the window: a symbol takes <= 3 bytes on the fast path, so of the bytes behind data
+                // only 3 * (symbols still to come) matter -- one register fewer per symbol
+                dh = funnel_l(dl, dh, r.sh);
+                dl = funnel_l(w0, dl, r.sh);
+                if (b + 1 < PER) w0 = funnel_l(w1, w0, r.sh);
+                if (b + 2 < PER) w1 = funnel_l(w2, w1, r.sh);
+                if (b + 3 < PER) w2 <<= r.sh;
+                tot += r.sh;
                 lo = r.nlo << r.sh;
                 rpt = r.nrpt;
-                q = q_of(rpt);
+                if (!TP) q = q_of(rpt);
                 acc |= r.sym << (SYM_BITS * b);
                 bad |= !r.ok;
             }
+            pos += tot >> 3;
         };
         // The word was not clean for this lane: back to the checkpoint (register moves) and through the
-        // word one symbol at a time, inline and on the same ring -- the table step where it verifies, the
-        // reference's literal loops / search where it does not.
-        struct WordChk {  // lane state at the start of a word: what the re-decode restarts from
-            uint64_t lo, rpt;
-            uint32_t dh, dl, wh, wl, cnt, rd;
-        };
-        auto checkpoint = [&]() -> WordChk {
-            return WordChk{lo, rpt, sink.dh, sink.dl, sink.wh, sink.wl, sink.cnt, sink.f.rd};
-        };
-        // the symbols of an unclean word, one at a time on the generic sink (lo / rpt / sink at the checkpoint)
-        auto redo_symbols = [&]() -> uint32_t {
+        // word one symbol at a time on the generic sink -- the table step where it verifies, the reference's
+        // literal loops / search where it does not.
+        auto redo_word = [&](const WordChk& chk) -> uint32_t {
+            lo = chk.lo;
+            rpt = chk.rpt;
+            dh = chk.dh;
+            dl = chk.dl;
+            pos = chk.pos;
+            sink.f.rd = pos >> 2;
+            // Everything requested has landed (the newest piece was issued a whole word ago: no wait in
+            // practice).  The re-decode reads at most 4 x 14 bytes beyond the checkpoint, so with >= 64 bytes
+            // in the ring it needs no new piece -- and no round trip to memory; otherwise (a run of unclean
+            // words, the start of a chunk) fill the ring to the brim first.
+            fill.redo_ready(sink.f);
+            attach();
             uint32_t acc = 0;
 #pragma unroll 1
             for (uint32_t b = 0; b < PER; b++) {
@@ -573,181 +641,88 @@ __global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
             rg = range_of(rpt);
             q = q_of(rpt);
             bf = lut_bf16_init(sink.data() - lo, rg, lut_scale);
+            detach();
+            // the next clean word reads 16 bytes from the word of `pos`: top the ring up if the exact path ate
+            // into that margin (the per-word round adds at most one piece)
+            if ((int32_t)(fill.wr * 16u - pos) < 48 && fill.wr < fill.npieces) {
+                sink.f.rd = pos >> 2;
+                fill.resync(sink.f);
+            }
             return acc;
         };
-        auto redo_word = [&](const WordChk& chk) -> uint32_t {
-            lo = chk.lo;
-            rpt = chk.rpt;
-            sink.dh = chk.dh;
-            sink.dl = chk.dl;
-            sink.wh = chk.wh;
-            sink.wl = chk.wl;
-            sink.cnt = chk.cnt;
-            sink.f.rd = chk.rd;
-            // Everything requested has landed (the newest piece was issued a whole word ago: no wait in
-            // practice).  The re-decode reads at most 4 x 14 bytes beyond the checkpoint, so with >= 64 bytes
-            // in the ring it needs no new piece -- and no round trip to memory; otherwise (a run of unclean
-            // words, the start of a chunk) fill the ring to the brim first.  Either way the invariant of
-            // round1() (enough landed bytes for a clean word) holds again afterwards.
-            fill.redo_ready(sink.f);
-            return redo_symbols();
+        // Output (TP): a lane's 32-bit words go to global memory 16 bytes at a time.  Every lane writes its own
+        // part of the output, so a warp's 4-byte stores are 32 separate sectors = 32 wavefronts of the LSU data
+        // pipe per word; three words wait in shared memory ([slot][thread]: conflict-free) and leave with the
+        // fourth as one 16-byte store.  (hosts launch TP kernels only when every part starts 16-byte aligned)
+        const uint32_t stage = stage_saddr + threadIdx.x * 4u, stage_pitch = blockDim.x * 4u;
+        auto put_word = [&](uint64_t w, uint32_t acc) {
+            if (TP) {
+                const uint32_t slot = (uint32_t)w & 3u;
+                asm volatile(
+                    "{\n\t.reg .pred q;\n\t.reg .b32 a, b, c;\n\t"
+                    "setp.eq.b32 q, %0, 3;\n\t"
+                    "@!q st.shared.b32 [%1], %2;\n\t"
+                    "@q ld.shared.b32 a, [%3];\n\t"
+                    "@q ld.shared.b32 b, [%4];\n\t"
+                    "@q ld.shared.b32 c, [%5];\n\t"
+                    "@q st.global.v4.b32 [%6], {a, b, c, %2};\n\t}"
+                    :
+                    : "r"(slot), "r"(stage + slot * stage_pitch), "r"(acc), "r"(stage), "r"(stage + stage_pitch),
+                      "r"(stage + 2u * stage_pitch), "l"(dw + (w & ~3ull))
+                    : "memory");
+            } else {
+                dw[w] = acc;
+            }
         };
+        // a corrected word: into its slot while the group is still staged, else straight to global memory
+        auto fix_word = [&](uint64_t w, uint32_t acc) {
+            if (TP && ((uint32_t)w & 3u) != 3u)
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(stage + ((uint32_t)w & 3u) * stage_pitch), "r"(acc) : "memory");
+            else
+                dw[w] = acc;
+        };
+        // Main loop: the words every live lane of the warp has (all of them, except in a warp holding the
+        // ragged last chunk).  Its only branch in the common case is the back edge, and that branch is
+        // warp-uniform (vote): a taken branch costs ~35 cycles with one warp per scheduler, and a per-lane
+        // exit would park the lane at the reconvergence point until its whole warp left the loop.
         const uint32_t nw_warp = __reduce_min_sync(live, (uint32_t)(nw < 0xFFFFFFFFull ? nw : 0xFFFFFFFFull));
         uint64_t i = 0;
-        if constexpr (WIN) {
-            // ---- position window.  (dh:dl) = data, pos = first byte (from pbase) not yet shifted into it.
-            uint32_t dh = sink.dh, dl = sink.dl;
-            uint32_t pos = sink.f.rd * 4u - (sink.cnt >> 3);
-            const uint32_t ring = sink.f.ring;
-            // the generic sink (exact re-decode, tail symbols) re-attached at `pos`: like prime() without the 8
-            // bytes that are already in data; the word at pos / 4 has landed (callers make sure)
-            auto attach = [&]() {
-                sink.dh = dh;
-                sink.dl = dl;
-                sink.f.rd = pos >> 2;
-                sink.f.reload();
-                const uint32_t skipb = pos & 3u;
-                const uint32_t first = sink.f.peek_be32();
-                sink.f.advance_if(true);
-                sink.wh = first << (8u * skipb);
-                sink.wl = 0;
-                sink.cnt = 32u - 8u * skipb;
-                sink.refill();
-            };
-            auto detach = [&]() {
-                dh = sink.dh;
-                dl = sink.dl;
-                pos = sink.f.rd * 4u - (sink.cnt >> 3);
-            };
-            struct WordChkW {
-                uint64_t lo, rpt;
-                uint32_t dh, dl, pos;
-            };
-            auto decode_word_w = [&](uint32_t& acc, bool& bad) {
-                acc = 0;
-                bad = false;
-                // the 3 * PER bytes that follow data, big-endian, from the (mirrored) ring: no address wrap
-                const uint32_t a0 = ring + (pos & (RING_PIECES * 16u - 4u));
-                const uint32_t sel = (pos & 3u) * 0x1111u + 0x0123u;  // bytes o .. o+3 of a word pair, reversed
-                uint32_t x0, x1, x2, x3 = 0;
-                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x0) : "r"(a0) : "memory");
-                asm volatile("ld.shared.b32 %0, [%1+4];" : "=r"(x1) : "r"(a0) : "memory");
-                asm volatile("ld.shared.b32 %0, [%1+8];" : "=r"(x2) : "r"(a0) : "memory");
-                if (PER > 2) asm volatile("ld.shared.b32 %0, [%1+12];" : "=r"(x3) : "r"(a0) : "memory");
-                uint32_t w0 = __byte_perm(x0, x1, sel), w1 = __byte_perm(x1, x2, sel);
-                uint32_t w2 = PER > 2 ? __byte_perm(x2, x3, sel) : 0u;
-                uint32_t tot = 0;
-#pragma unroll
-                for (uint32_t b = 0; b < PER; b++) {
-                    const uint64_t data = ((uint64_t)dh << 32) | dl;
-                    const uint32_t off = lut_offset16(bf);
-                    const LutEntry e = lds_lut(lut_saddr + off);
-                    const float2 rc = lds_f2(rc_saddr + (off >> 1));
-                    FusedDec r;
-                    if constexpr (CSM) {
-                        const LutEntry k = lds_lut(cs_saddr + off);  // {csA lo, csA hi, csB lo, csB hi}
-                        r = fused_decode_step_cs<true>(lo, rpt, data, e, ((uint64_t)k.cumB << 32) | k.cumA,
-                                                 ((uint64_t)k.syms << 32) | k.cumC);
-                    } else if constexpr (M2M) {
-                        r = fused_decode_step_m2<true>(lo, rpt, data, e, k2);
-                    } else {
-                        r = fused_decode_step<MODE, true>(lo, rpt, data, e, fp);
-                    }
-                    bf = u64_to_float(data - r.nlo) * (q * (r.takeB ? rc.y : rc.x));
-                    // shift the window: a symbol takes <= 3 bytes on the fast path, so of the bytes behind data
-                    // only 3 * (symbols still to come) matter -- one register fewer per symbol
-                    dh = funnel_l(dl, dh, r.sh);
-                    dl = funnel_l(w0, dl, r.sh);
-                    if (b + 1 < PER) w0 = funnel_l(w1, w0, r.sh);
-                    if (b + 2 < PER) w1 = funnel_l(w2, w1, r.sh);
-                    if (b + 3 < PER) w2 <<= r.sh;
-                    tot += r.sh;
-                    lo = r.nlo << r.sh;
-                    rpt = r.nrpt;
-                    q = q_of(rpt);
-                    acc |= r.sym << (SYM_BITS * b);
-                    bad |= !r.ok;
-                }
-                pos += tot >> 3;
-            };
-            auto redo_word_w = [&](const WordChkW& chk) -> uint32_t {
-                lo = chk.lo;
-                rpt = chk.rpt;
-                dh = chk.dh;
-                dl = chk.dl;
-                pos = chk.pos;
-                sink.f.rd = pos >> 2;
-                fill.redo_ready(sink.f);  // everything requested has landed; >= 64 bytes from the checkpoint on
-                attach();
-                const uint32_t acc = redo_symbols();
-                detach();
-                // the next clean word reads 16 bytes from the word of `pos`: top the ring up if the exact path ate
-                // into that margin (the per-word round adds at most one piece)
-                if ((int32_t)(fill.wr * 16u - pos) < 48 && fill.wr < fill.npieces) {
-                    sink.f.rd = pos >> 2;
-                    fill.resync(sink.f);
-                }
-                return acc;
-            };
-            while (i < nw_warp) {
-                WordChkW chk;
-                uint32_t acc;
-                bool bad, leave;
+        while (i < nw_warp) {
+            WordChk chk;
+            uint32_t acc;
+            bool bad, leave;
 #pragma unroll 1
-                do {
-                    fill.round1_pos(pos, ring);
-                    chk = WordChkW{lo, rpt, dh, dl, pos};
-                    decode_word_w(acc, bad);
-                    dw[i] = acc;  // speculative as well: rewritten below when the word was not clean
-                    ++i;
-                    leave = __any_sync(live, bad) | (i >= nw_warp);
-                } while (!leave);
-                if (bad) dw[i - 1] = redo_word_w(chk);
-            }
-#pragma unroll 1
-            for (; i < nw; i++) {  // ragged warp only
+            do {
                 fill.round1_pos(pos, ring);
-                const WordChkW chk{lo, rpt, dh, dl, pos};
-                uint32_t acc;
-                bool bad;
-                decode_word_w(acc, bad);
-                if (RCB_UNLIKELY(bad)) acc = redo_word_w(chk);
-                dw[i] = acc;
-            }
-            // back to the generic sink for the tail symbols and the final accounting
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            attach();
-        } else {
-            // Main loop: the words every live lane of the warp has (all of them, except in a warp holding the
-            // ragged last chunk).  Its only branch in the common case is the back edge, and that branch is
-            // warp-uniform (vote): a taken branch costs ~35 cycles on this one-warp-per-scheduler kernel, and a
-            // per-lane exit would park the lane at the reconvergence point until its whole warp left the loop.
-            while (i < nw_warp) {
-                WordChk chk;
-                uint32_t acc;
-                bool bad, leave;
-    #pragma unroll 1
-                do {
-                    fill.round1(sink.f);
-                    chk = checkpoint();
-                    decode_word(acc, bad);
-                    dw[i] = acc;  // speculative as well: rewritten below when the word was not clean
-                    ++i;
-                    leave = __any_sync(live, bad) | (i >= nw_warp);
-                } while (!leave);
-                if (bad) dw[i - 1] = redo_word(chk);
-            }
-    #pragma unroll 1
-            for (; i < nw; i++) {  // ragged warp only
-                fill.round1(sink.f);
-                const WordChk chk = checkpoint();
-                uint32_t acc;
-                bool bad;
+                chk = WordChk{lo, rpt, dh, dl, pos};
                 decode_word(acc, bad);
-                if (RCB_UNLIKELY(bad)) acc = redo_word(chk);
-                dw[i] = acc;
+                put_word(i, acc);  // speculative as well: rewritten below when the word was not clean
+                ++i;
+                leave = __any_sync(live, bad) | (i >= nw_warp);
+            } while (!leave);
+            if (bad) fix_word(i - 1, redo_word(chk));
+        }
+        if (TP) {  // words of an unfinished group
+#pragma unroll 1
+            for (uint64_t w = i & ~3ull; w < i; w++) {
+                uint32_t v;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(stage + ((uint32_t)w & 3u) * stage_pitch) : "memory");
+                dw[w] = v;
             }
         }
+#pragma unroll 1
+        for (; i < nw; i++) {  // ragged warp only
+            fill.round1_pos(pos, ring);
+            const WordChk chk{lo, rpt, dh, dl, pos};
+            uint32_t acc;
+            bool bad;
+            decode_word(acc, bad);
+            if (RCB_UNLIKELY(bad)) acc = redo_word(chk);
+            dw[i] = acc;
+        }
+        // back to the generic sink for the tail symbols and the final accounting
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        attach();
         done = nw * PER;
         rg = range_of(rpt);
     }
