@@ -548,7 +548,23 @@ def run_ours(a):
         # double-buffered code streams: batch i's stream is read by the decoder while batch i+1 is encoded
         h_stream2 = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
         streams = (a_stream, h_stream2.numpy())
+        # restart points travel with the code stream (host arrays, one per code-stream buffer)
+        rs_e2e = a.restart if d_restart is not None else 0
+        rs_words = d_restart.numel() if d_restart is not None else 0
+        h_rs = [torch.zeros(max(1, rs_words), dtype=torch.int64, pin_memory=True).numpy().view(np.uint64) for _ in range(2)]
         result = {}
+
+        def enc_host(c_, m_, out_np, slot):
+            if rs_e2e:
+                buf, offs, nb, rs_np = c_.encode_host(a_syms, chunk, m_, out_np=out_np, restart_syms=rs_e2e,
+                                                      restart_np=h_rs[slot])
+                return buf, offs, nb, rs_np
+            buf, offs, nb = c_.encode_host(a_syms, chunk, m_, out_np=out_np)
+            return buf, offs, nb, None
+
+        def dec_host(c_, m_, buf, offs, nb, rs_np):
+            c_.decode_host(buf[:nb], offs, n_syms, chunk, m_, sym_bytes=sym_bytes, out_np=a_back,
+                           restart_syms=rs_e2e, restart_np=rs_np)
 
         def run_steps(k_steps):
             q = queue.Queue()
@@ -560,8 +576,8 @@ def run_ours(a):
                         item = q.get()
                         if item is None:
                             return
-                        buf, offs, nb = item
-                        ctx2.decode_host(buf[:nb], offs, n_syms, chunk, model2, sym_bytes=sym_bytes, out_np=a_back)
+                        buf, offs, nb, rs_np = item
+                        dec_host(ctx2, model2, buf, offs, nb, rs_np)
                         result["nb"], result["offs"] = nb, offs
                         free.release()
 
@@ -569,8 +585,7 @@ def run_ours(a):
             t.start()
             for i in range(k_steps):
                 free.acquire()
-                buf, offs, nb = ctx.encode_host(a_syms, chunk, model, out_np=streams[i & 1])
-                q.put((buf, offs, nb))
+                q.put(enc_host(ctx, model, streams[i & 1], i & 1))
             q.put(None)
             t.join()
 
@@ -585,11 +600,11 @@ def run_ours(a):
         assert np.array_equal(a_back, a_syms)
         # the same two calls back to back on one context (no overlap between steps), for reference
         t1 = time.perf_counter()
-        _, offs1, nb1 = ctx.encode_host(a_syms, chunk, model, out_np=a_stream)
-        ctx.decode_host(a_stream[:nb1], offs1, n_syms, chunk, model, sym_bytes=sym_bytes, out_np=a_back)
+        _, offs1, nb1, rs1 = enc_host(ctx, model, a_stream, 0)
+        dec_host(ctx, model, a_stream, offs1, nb1, rs1)
         dt_serial = max_over_ranks(time.perf_counter() - t1)
         barrier()
-        off_bytes = (n_chunks + 1) * 8
+        off_bytes = (n_chunks + 1) * 8 + rs_words * 8  # offsets + restart points
         # the bus ceiling on this box, every rank copying at once (aggregate over ranks)
         h2d, d2h, duplex = measure_bus(torch, dev, barrier)
         bus = {"h2d_gbs": reduce_ranks(h2d, "sum"), "d2h_gbs": reduce_ranks(d2h, "sum"),
@@ -606,12 +621,13 @@ def run_ours(a):
                              "serial_* = the two calls back to back on one context",
                "bus": bus, "bus_gbs": moved * a.e2e_steps / dt / 1e9,
                "bus_frac": moved * a.e2e_steps / dt / 1e9 / bus["duplex_gbs"],
-               "api": "rcb_encode_host + rcb_decode_host (C ABI, pinned host buffers)"}
+               "api": ("rcb_encode_host_restart + rcb_decode_host_restart" if rs_e2e else
+                       "rcb_encode_host + rcb_decode_host") + " (C ABI, pinned host buffers)"}
         if old_affinity:
             os.sched_setaffinity(0, old_affinity)
         model2.close()
         ctx2.close()
-        del h_syms, h_stream, h_back, h_stream2
+        del h_syms, h_stream, h_back, h_stream2, h_rs
 
     # ---- parity on EVERY rank at every N: a deterministic >= 1 % subset of this rank's chunks (every 64th,
     # starting at 5) re-encoded by the oracle under this rank's table and compared byte for byte

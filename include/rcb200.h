@@ -196,11 +196,11 @@ int rcb_decode_result(rcb_ctx *ctx);
  *   record r of chunk i = state in front of symbol (r + 1) * restart_syms of it
  *   (range == 0: absent, ragged last chunk).  restart_syms: multiple of 64, at
  *   most 64 parts per chunk; restart_syms == 0 or d_restart == NULL = the plain
- *   calls above.  `range` may be rounded down to a multiple of total_freq (only
+ *   calls above.  `range` is stored rounded down to a multiple of total_freq (only
  *   range / total_freq is used before the next update, src/range_coder.rs:62). */
 typedef struct rcb_restart_point {
     uint64_t lower_bound; /* RangeCoder::lower_bound, src/range_coder.rs:9  */
-    uint64_t range;       /* RangeCoder::range,       src/range_coder.rs:11 */
+    uint64_t range;       /* RangeCoder::range (src/range_coder.rs:11) / total_freq * total_freq */
     uint32_t code_bytes;  /* bytes Encoder::encode has returned so far (src/encoder.rs:24-37) */
     uint32_t reserved;
 } rcb_restart_point;
@@ -238,6 +238,16 @@ int rcb_encode_host(rcb_ctx *ctx, const void *h_syms, uint64_t n_syms, int sym_b
 int rcb_decode_host(rcb_ctx *ctx, const uint8_t *h_stream, const uint64_t *h_offsets,
                     uint64_t n_syms, int sym_bytes, uint64_t chunk_syms, const rcb_model *m,
                     void *h_syms_out);
+/* the same with restart points in host memory (h_restart = rcb_restart_point[n_chunks][per chunk],
+ * written by the encoder, read by the decoder; see "restart points" below) */
+int rcb_encode_host_restart(rcb_ctx *ctx, const void *h_syms, uint64_t n_syms, int sym_bytes,
+                            uint64_t chunk_syms, const rcb_model *m, uint8_t *h_out, uint64_t out_cap,
+                            uint64_t *h_offsets, uint64_t *h_out_bytes, uint64_t restart_syms,
+                            rcb_restart_point *h_restart);
+int rcb_decode_host_restart(rcb_ctx *ctx, const uint8_t *h_stream, const uint64_t *h_offsets,
+                            uint64_t n_syms, int sym_bytes, uint64_t chunk_syms, const rcb_model *m,
+                            void *h_syms_out, uint64_t restart_syms,
+                            const rcb_restart_point *h_restart);
 
 /* ---- continued single-stream coder: the reference's per-symbol API ----------
  * Encoder / Decoder keep (lower_bound, range[, data]) between calls
@@ -273,19 +283,31 @@ int rcb_decode_stream(rcb_ctx *ctx, rcb_stream_state *st, const uint8_t *h_code,
  *   | chunk_syms u64 | n_syms u64 | n_chunks u64 | payload_bytes u64
  *   | model: shared    -> total u32, reserved u32, cum[K] u32, c[K] u32
  *            per chunk -> c[n_chunks][K] u32 (cum = exclusive scan, total = sum)
- *   | offsets u64[n_chunks+1] | payload (chunk i = payload[offsets[i]..offsets[i+1]),
- *     exactly the reference's finish() bytes for that chunk)
+ *   | offsets u64[n_chunks+1]
+ *   | version 2 only: restart points, rcb_restart_point[n_chunks][per chunk] (24-byte records,
+ *     little-endian), restart_syms = 64 * the u32 at byte 20 of the header (0 in version 1)
+ *   | payload (chunk i = payload[offsets[i]..offsets[i+1]), exactly the reference's finish()
+ *     bytes for that chunk)
+ * (a u32 of padding follows model_mode: byte 20, the restart field.)
  * Pure host-side byte layout; all coding stays in the entry points above. */
 typedef struct rcb_frame_info {
     uint32_t version, sym_bytes, K, model_mode;
     uint64_t chunk_syms, n_syms, n_chunks, payload_bytes;
     uint64_t model_off, offsets_off, payload_off, frame_bytes;
+    uint64_t restart_syms, restart_off; /* 0, 0: no restart section (version 1) */
 } rcb_frame_info;
 uint64_t rcb_frame_bound(uint32_t K, uint64_t n_chunks, int per_chunk, uint64_t payload_bytes);
+uint64_t rcb_frame_bound_restart(uint32_t K, uint64_t n_chunks, int per_chunk, uint64_t payload_bytes,
+                                 uint64_t chunk_syms, uint64_t restart_syms);
 /* model tables are read back from the device; h_stream/h_offsets as produced by rcb_encode_host */
 int rcb_frame_write(rcb_ctx *ctx, const rcb_model *m, int sym_bytes, uint64_t chunk_syms, uint64_t n_syms,
                     const uint8_t *h_stream, const uint64_t *h_offsets, uint8_t *h_frame,
                     uint64_t frame_cap, uint64_t *h_frame_bytes);
+/* ... with the restart points rcb_encode_host_restart produced (version 2 frame) */
+int rcb_frame_write_restart(rcb_ctx *ctx, const rcb_model *m, int sym_bytes, uint64_t chunk_syms,
+                            uint64_t n_syms, const uint8_t *h_stream, const uint64_t *h_offsets,
+                            uint64_t restart_syms, const rcb_restart_point *h_restart,
+                            uint8_t *h_frame, uint64_t frame_cap, uint64_t *h_frame_bytes);
 /* validates the header and section sizes against len */
 int rcb_frame_parse(const uint8_t *h_frame, uint64_t len, rcb_frame_info *info);
 /* device model from the frame's model section (caller destroys it) */
@@ -294,6 +316,10 @@ int rcb_frame_model(rcb_ctx *ctx, const uint8_t *h_frame, const rcb_frame_info *
 int rcb_frame_encode_host(rcb_ctx *ctx, const void *h_syms, uint64_t n_syms, int sym_bytes,
                           uint64_t chunk_syms, const rcb_model *m, uint8_t *h_frame, uint64_t frame_cap,
                           uint64_t *h_frame_bytes);
+/* rcb_frame_decode_host reads either version and uses a restart section when the frame has one */
+int rcb_frame_encode_host_restart(rcb_ctx *ctx, const void *h_syms, uint64_t n_syms, int sym_bytes,
+                                  uint64_t chunk_syms, const rcb_model *m, uint64_t restart_syms,
+                                  uint8_t *h_frame, uint64_t frame_cap, uint64_t *h_frame_bytes);
 int rcb_frame_decode_host(rcb_ctx *ctx, const uint8_t *h_frame, uint64_t len, void *h_syms_out,
                           uint64_t out_cap_bytes, uint64_t *h_n_syms);
 

@@ -241,16 +241,28 @@ namespace gpu {
 struct Encoded {
     std::vector<uint8_t> stream;     // concatenated Encoder::finish() outputs
     std::vector<uint64_t> offsets;   // chunk i = stream[offsets[i] .. offsets[i+1])
+    // restart points (rcb200.h): the Encoder's state every restart_syms symbols of a chunk -- side information
+    // that lets decode_chunks run several GPU lanes per chunk; the stream above is unchanged by it
+    uint64_t restart_syms = 0;
+    std::vector<rcb_restart_point> restart;
 };
+// restart points every quarter of a chunk when that is a whole number of 64-symbol units (0: none)
+inline uint64_t default_restart_syms(uint64_t chunk_syms) { return chunk_syms % 256 == 0 ? chunk_syms / 4 : 0; }
 template <class Sym>
-Encoded encode_chunks(Context& ctx, const ModelSnapshot& snap, const std::vector<Sym>& syms, uint64_t chunk_syms) {
+Encoded encode_chunks(Context& ctx, const ModelSnapshot& snap, const std::vector<Sym>& syms, uint64_t chunk_syms,
+                      uint64_t restart_syms = ~0ull) {
     const uint64_t n = syms.size(), n_chunks = chunk_syms ? (n + chunk_syms - 1) / chunk_syms : 0;
     Encoded e;
     e.offsets.resize(n_chunks + 1);
     e.stream.resize(rcb_encode_bound(ctx.handle(), snap.handle(), n, (int)sizeof(Sym), chunk_syms) + 16);
+    if (restart_syms == ~0ull) restart_syms = default_restart_syms(chunk_syms);
+    const uint64_t per = rcb_restart_points_per_chunk(chunk_syms, restart_syms);
+    e.restart_syms = per ? restart_syms : 0;
+    e.restart.resize(n_chunks * per);
     uint64_t bytes = 0;
-    check(rcb_encode_host(ctx.handle(), syms.data(), n, (int)sizeof(Sym), chunk_syms, snap.handle(), e.stream.data(),
-                          e.stream.size(), e.offsets.data(), &bytes),
+    check(rcb_encode_host_restart(ctx.handle(), syms.data(), n, (int)sizeof(Sym), chunk_syms, snap.handle(),
+                                  e.stream.data(), e.stream.size(), e.offsets.data(), &bytes, e.restart_syms,
+                                  e.restart.empty() ? nullptr : e.restart.data()),
           "gpu::encode_chunks");
     e.stream.resize(bytes);
     return e;
@@ -261,8 +273,9 @@ std::vector<Sym> decode_chunks(Context& ctx, const ModelSnapshot& snap, const En
     std::vector<Sym> out(n_syms);
     std::vector<uint8_t> padded(e.stream);
     padded.resize((padded.size() + 31) & ~size_t(15));
-    check(rcb_decode_host(ctx.handle(), padded.data(), e.offsets.data(), n_syms, (int)sizeof(Sym), chunk_syms,
-                          snap.handle(), out.data()),
+    check(rcb_decode_host_restart(ctx.handle(), padded.data(), e.offsets.data(), n_syms, (int)sizeof(Sym), chunk_syms,
+                                  snap.handle(), out.data(), e.restart_syms,
+                                  e.restart.empty() ? nullptr : e.restart.data()),
           "gpu::decode_chunks");
     return out;
 }

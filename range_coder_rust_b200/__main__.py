@@ -1,6 +1,6 @@
 """File front end of the RCB2 container: bytes of a file are the symbols (K = 256).
 
-  python -m range_coder_rust_b200 compress   IN OUT [--chunk 65536] [--adaptive] [--device 0]
+  python -m range_coder_rust_b200 compress   IN OUT [--chunk 65536] [--adaptive] [--restart N] [--device 0]
   python -m range_coder_rust_b200 decompress IN OUT
   python -m range_coder_rust_b200 info       IN
 
@@ -24,6 +24,9 @@ def main(argv=None):
     c.add_argument("dst")
     c.add_argument("--chunk", type=int, default=65536, help="symbols per chunk")
     c.add_argument("--adaptive", action="store_true", help="one frequency table per chunk")
+    c.add_argument("--restart", type=int, default=-1,
+                   help="restart points every N symbols of a chunk (several decoder lanes per chunk; multiple of 64); "
+                        "0 = none (version-1 frame), default: a quarter of the chunk when that is a multiple of 64")
     c.add_argument("--device", type=int, default=0)
     d = sub.add_parser("decompress")
     d.add_argument("src")
@@ -42,10 +45,12 @@ def main(argv=None):
         dev = torch.from_numpy(syms).to(ctx.device)
         counts = ctx.histogram(dev, 256, chunk_syms=a.chunk if a.adaptive else 0)
         model = ctx.model_from_counts(counts)
-        frame = ctx.frame_encode(syms, a.chunk, model)
+        restart = a.restart if a.restart >= 0 else (a.chunk // 4 if a.chunk % 256 == 0 else 0)
+        frame = ctx.frame_encode(syms, a.chunk, model, restart_syms=restart)
         frame.tofile(a.dst)
         print(f"{a.src}: {syms.size} -> {frame.size} bytes ({frame.size / syms.size:.4f}), "
-              f"{(syms.size + a.chunk - 1) // a.chunk} chunks, {'per-chunk tables' if a.adaptive else 'one table'}")
+              f"{(syms.size + a.chunk - 1) // a.chunk} chunks, {'per-chunk tables' if a.adaptive else 'one table'}"
+              f"{', restart points every %d symbols' % restart if restart else ''}")
     elif a.cmd == "decompress":
         frame = np.fromfile(a.src, dtype=np.uint8)
         out = ctx.frame_decode(frame)
@@ -56,7 +61,8 @@ def main(argv=None):
         f = ctx.frame_info(frame)
         print(f"RCB2 v{f.version}: {f.n_syms} symbols of {f.sym_bytes} byte(s), K={f.K}, {f.n_chunks} chunks of "
               f"{f.chunk_syms}, {'per-chunk tables' if f.model_mode else 'one table'}, payload {f.payload_bytes} bytes, "
-              f"frame {f.frame_bytes} bytes")
+              f"frame {f.frame_bytes} bytes"
+              f"{', restart points every %d symbols' % f.restart_syms if f.restart_syms else ''}")
 
 
 if __name__ == "__main__":

@@ -57,6 +57,8 @@ SIGNATURES = {
     "rcb_decode_chunks_restart_async": (ci, [vp, vp, vp, u64, ci, u64, vp, vp, vp, u64, vp]),
     "rcb_encode_host": (ci, [vp, vp, u64, ci, u64, vp, vp, u64, vp, u64p]),
     "rcb_decode_host": (ci, [vp, vp, vp, u64, ci, u64, vp, vp]),
+    "rcb_encode_host_restart": (ci, [vp, vp, u64, ci, u64, vp, vp, u64, vp, u64p, u64, vp]),
+    "rcb_decode_host_restart": (ci, [vp, vp, vp, u64, ci, u64, vp, vp, u64, vp]),
     "rcb_stream_state_init": (None, [vp]),
     "rcb_encode_stream": (ci, [vp, vp, vp, u64, ci, vp, vp, u64, u64p, vp, ci]),
     "rcb_decode_stream": (ci, [vp, vp, vp, u64, u64, ci, vp, vp]),
@@ -66,6 +68,9 @@ SIGNATURES = {
     "rcb_frame_model": (ci, [vp, vp, vp, ctypes.POINTER(vp)]),
     "rcb_frame_encode_host": (ci, [vp, vp, u64, ci, u64, vp, vp, u64, u64p]),
     "rcb_frame_decode_host": (ci, [vp, vp, u64, vp, u64, u64p]),
+    "rcb_frame_bound_restart": (u64, [u32, u64, ci, u64, u64, u64]),
+    "rcb_frame_write_restart": (ci, [vp, vp, ci, u64, u64, vp, vp, u64, vp, vp, u64, u64p]),
+    "rcb_frame_encode_host_restart": (ci, [vp, vp, u64, ci, u64, vp, u64, vp, u64, u64p]),
     "rcb_generate": (ci, [vp, vp, u64, u64, ci, u32, u64, vp, u32, u64]),
     "rcb_adaptive_encode_bound": (u64, [vp, u64, u64]),
     "rcb_adaptive_encode_chunks": (ci, [vp, vp, u64, ci, u64, vp, vp, u64, vp, vp, u64p]),

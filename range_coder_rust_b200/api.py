@@ -26,7 +26,8 @@ class FrameInfo(ctypes.Structure):
     """struct rcb_frame_info (include/rcb200.h)."""
     _fields_ = [(n, ctypes.c_uint32) for n in ("version", "sym_bytes", "K", "model_mode")] + \
                [(n, ctypes.c_uint64) for n in ("chunk_syms", "n_syms", "n_chunks", "payload_bytes", "model_off",
-                                               "offsets_off", "payload_off", "frame_bytes")]
+                                               "offsets_off", "payload_off", "frame_bytes", "restart_syms",
+                                               "restart_off")]
 
 
 class Model:
@@ -363,42 +364,61 @@ class Context:
         return out
 
     # ------------------------------------------------- host-buffer entry points
-    def encode_host(self, syms_np, chunk_syms, model, out_np=None):
+    def encode_host(self, syms_np, chunk_syms, model, out_np=None, restart_syms=0, restart_np=None):
+        """rcb_encode_host[_restart]: host symbols in, host code stream + offsets out.  With restart_syms the
+        restart points land in restart_np (uint64[n_chunks * per_chunk * 3], allocated when None) and are
+        returned as a fourth element."""
         syms_np = np.ascontiguousarray(syms_np)
-        sb = syms_np.dtype.itemsize
-        n = syms_np.size
+        sb, n = syms_np.dtype.itemsize, syms_np.size
         n_chunks = (n + chunk_syms - 1) // chunk_syms
         if out_np is None:
             out_np = np.empty(self.encode_bound(model, n, sb, chunk_syms) + 16, dtype=np.uint8)
         offsets = np.zeros(n_chunks + 1, dtype=np.uint64)
         nbytes = ctypes.c_uint64()
+        per = int(self.lib.rcb_restart_points_per_chunk(chunk_syms, restart_syms)) if restart_syms else 0
+        if per:
+            if restart_np is None:
+                restart_np = np.zeros(max(1, n_chunks * per * 3), dtype=np.uint64)
+            rc = self.lib.rcb_encode_host_restart(self.h, _np_ptr(syms_np), n, sb, chunk_syms, model.h,
+                                                  _np_ptr(out_np), out_np.size, _np_ptr(offsets), ctypes.byref(nbytes),
+                                                  restart_syms, _np_ptr(restart_np))
+            self._check(rc, "rcb_encode_host_restart")
+            return out_np, offsets, int(nbytes.value), restart_np
         rc = self.lib.rcb_encode_host(self.h, _np_ptr(syms_np), n, sb, chunk_syms, model.h, _np_ptr(out_np),
                                       out_np.size, _np_ptr(offsets), ctypes.byref(nbytes))
         self._check(rc, "rcb_encode_host")
         return out_np, offsets, int(nbytes.value)
 
-    def decode_host(self, stream_np, offsets_np, n_syms, chunk_syms, model, sym_bytes=1, out_np=None):
+    def decode_host(self, stream_np, offsets_np, n_syms, chunk_syms, model, sym_bytes=1, out_np=None, restart_syms=0,
+                    restart_np=None):
         stream_np = np.ascontiguousarray(stream_np, dtype=np.uint8)
         offsets_np = np.ascontiguousarray(offsets_np, dtype=np.uint64)
         if out_np is None:
             out_np = np.empty(n_syms, dtype=np.uint8 if sym_bytes == 1 else np.uint16)
+        if restart_syms and restart_np is not None:
+            rc = self.lib.rcb_decode_host_restart(self.h, _np_ptr(stream_np), _np_ptr(offsets_np), n_syms, sym_bytes,
+                                                  chunk_syms, model.h, _np_ptr(out_np), restart_syms,
+                                                  _np_ptr(np.ascontiguousarray(restart_np, dtype=np.uint64)))
+            self._check(rc, "rcb_decode_host_restart")
+            return out_np
         rc = self.lib.rcb_decode_host(self.h, _np_ptr(stream_np), _np_ptr(offsets_np), n_syms, sym_bytes,
                                       chunk_syms, model.h, _np_ptr(out_np))
         self._check(rc, "rcb_decode_host")
         return out_np
 
     # ------------------------------------------------------- framed container
-    def frame_encode(self, syms_np, chunk_syms, model):
-        """encode_host + the RCB2 container (rcb200.h); returns the frame as uint8[]."""
+    def frame_encode(self, syms_np, chunk_syms, model, restart_syms=0):
+        """encode_host + the RCB2 container (rcb200.h); returns the frame as uint8[].  restart_syms != 0 writes
+        a version-2 frame that carries restart points (several decoder lanes per chunk)."""
         syms_np = np.ascontiguousarray(syms_np)
         sb, n = syms_np.dtype.itemsize, syms_np.size
         n_chunks = (n + chunk_syms - 1) // chunk_syms
-        cap = self.lib.rcb_frame_bound(model.K, n_chunks, int(model.n_models != 1),
-                                       self.encode_bound(model, n, sb, chunk_syms))
+        cap = self.lib.rcb_frame_bound_restart(model.K, n_chunks, int(model.n_models != 1),
+                                               self.encode_bound(model, n, sb, chunk_syms), chunk_syms, restart_syms)
         frame = np.empty(cap, dtype=np.uint8)
         nbytes = ctypes.c_uint64()
-        rc = self.lib.rcb_frame_encode_host(self.h, _np_ptr(syms_np), n, sb, chunk_syms, model.h, _np_ptr(frame),
-                                            frame.size, ctypes.byref(nbytes))
+        rc = self.lib.rcb_frame_encode_host_restart(self.h, _np_ptr(syms_np), n, sb, chunk_syms, model.h,
+                                                    restart_syms, _np_ptr(frame), frame.size, ctypes.byref(nbytes))
         self._check(rc, "rcb_frame_encode_host")
         return frame[:int(nbytes.value)]
 

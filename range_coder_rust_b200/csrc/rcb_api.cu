@@ -1301,9 +1301,9 @@ static int pick_slices(uint64_t n_chunks, uint64_t bytes) {
     return s;
 }
 
-extern "C" int rcb_encode_host(rcb_ctx* c, const void* h_syms, uint64_t n_syms, int sym_bytes,
-                               uint64_t chunk_syms, const rcb_model* m, uint8_t* h_out, uint64_t out_cap,
-                               uint64_t* h_offsets, uint64_t* h_out_bytes) {
+static int encode_host_impl(rcb_ctx* c, const void* h_syms, uint64_t n_syms, int sym_bytes, uint64_t chunk_syms,
+                            const rcb_model* m, uint8_t* h_out, uint64_t out_cap, uint64_t* h_offsets,
+                            uint64_t* h_out_bytes, uint64_t restart_syms, rcb_restart_point* h_restart) {
     if (!c || !m || !m->ready || chunk_syms == 0 || !h_offsets || !h_out_bytes) return RCB_ERR_INVALID_ARGUMENT;
     if (sym_bytes != 1 && sym_bytes != 2) return RCB_ERR_UNSUPPORTED;
     if (n_syms && !h_syms) return RCB_ERR_INVALID_ARGUMENT;
@@ -1312,25 +1312,34 @@ extern "C" int rcb_encode_host(rcb_ctx* c, const void* h_syms, uint64_t n_syms, 
     const uint64_t in_bytes = (n_syms * sym_bytes + 15) & ~15ull;
     const uint64_t pitch = staging_pitch(m, chunk_syms);
     const uint64_t bound = n_chunks * pitch + 32;
+    // restart points: recorded on the device next to the offsets, copied out slice by slice
+    RestartSpec rs;
+    if (int rr = make_restart_spec(chunk_syms, restart_syms, h_restart, &rs)) return rr;
+    const uint64_t R = rs.per_chunk;
+    const uint64_t rs_bytes = (n_chunks * R * sizeof(Restart) + 15) & ~15ull;
     ON_DEVICE(c);
     const int S = pick_slices(n_chunks, n_syms * sym_bytes);
     const uint64_t off_bytes = ((n_chunks + 1 + S) * sizeof(uint64_t) + 15) & ~15ull;
-    int r = ensure_h2d(c, in_bytes + bound + off_bytes + 64);
+    int r = ensure_h2d(c, in_bytes + bound + off_bytes + rs_bytes + 64);
     if (r) return r;
     uint8_t* d_in = (uint8_t*)c->h2d;
     uint8_t* d_out = d_in + in_bytes;
     uint64_t* d_off = (uint64_t*)(d_out + ((bound + 15) & ~15ull));
+    Restart* d_rs = R ? (Restart*)((uint8_t*)d_off + off_bytes) : nullptr;
     if (S == 1 || (chunk_syms * sym_bytes) % 16 != 0) {
         if (n_syms)
             CK(c, cudaMemcpyAsync(d_in, h_syms, n_syms * sym_bytes, cudaMemcpyHostToDevice, c->stream));
         uint64_t total = 0;
-        r = rcb_encode_chunks(c, d_in, n_syms, sym_bytes, chunk_syms, m, d_out, bound, d_off, nullptr, &total);
+        r = rcb_encode_chunks_restart(c, d_in, n_syms, sym_bytes, chunk_syms, m, d_out, bound, d_off, nullptr,
+                                      R ? restart_syms : 0, (rcb_restart_point*)d_rs, &total);
         *h_out_bytes = total;
         if (r) return r;
         if (total > out_cap) return RCB_ERR_OUT_CAPACITY;
         CK(c, cudaMemcpyAsync(h_offsets, d_off, (n_chunks + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost,
                               c->stream));
         if (total) CK(c, cudaMemcpyAsync(h_out, d_out, total, cudaMemcpyDeviceToHost, c->stream));
+        if (R && n_chunks)
+            CK(c, cudaMemcpyAsync(h_restart, d_rs, n_chunks * R * sizeof(Restart), cudaMemcpyDeviceToHost, c->stream));
         CK(c, cudaStreamSynchronize(c->stream));
         return RCB_OK;
     }
@@ -1360,9 +1369,11 @@ extern "C" int rcb_encode_host(rcb_ctx* c, const void* h_syms, uint64_t n_syms, 
             break;
         }
         // slice-local offsets (k extra slots before it), output region at the slice's worst-case position
+        RestartSpec rsk = rs;
+        if (R) rsk.pts = d_rs + c0 * R;
         rc = encode_issue(c, d_in + s0 * sym_bytes, s1 - s0, sym_bytes, chunk_syms, m, c0, c->staging + c0 * pitch,
                           pitch, c->lens + c0, c->status + c0, d_out + c0 * pitch, nk * pitch, d_off + c0 + k,
-                          c->d_slice_summary + 8 * k, false);
+                          c->d_slice_summary + 8 * k, false, &rsk);
         if (rc) break;
         // the slice's status summary and byte count go straight into pinned host memory from a one-thread
         // kernel: a tiny device->host copy would queue behind the bulk copies on the copy engines
@@ -1404,6 +1415,9 @@ extern "C" int rcb_encode_host(rcb_ctx* c, const void* h_syms, uint64_t n_syms, 
                 // the slice's last entry is the next slice's first: only the final slice copies it
                 e = cudaMemcpyAsync(h_offsets + c0, d_off + c0 + k, (nk + (k == S - 1 ? 1 : 0)) * sizeof(uint64_t),
                                     cudaMemcpyDeviceToHost, c->d2h_stream);
+            if (e == cudaSuccess && R)
+                e = cudaMemcpyAsync(h_restart + c0 * R, d_rs + c0 * R, nk * R * sizeof(Restart), cudaMemcpyDeviceToHost,
+                                    c->d2h_stream);
             if (e != cudaSuccess) {
                 c->last_err = e;
                 rc = RCB_ERR_CUDA;
@@ -1422,13 +1436,15 @@ extern "C" int rcb_encode_host(rcb_ctx* c, const void* h_syms, uint64_t n_syms, 
         if (n_syms)
             CK(c, cudaMemcpyAsync(d_in, h_syms, n_syms * sym_bytes, cudaMemcpyHostToDevice, c->stream));
         uint64_t total = 0;
-        r = rcb_encode_chunks(c, d_in, n_syms, sym_bytes, chunk_syms, m, d_out, bound, d_off, nullptr, &total);
+        r = rcb_encode_chunks_restart(c, d_in, n_syms, sym_bytes, chunk_syms, m, d_out, bound, d_off, nullptr,
+                                      R ? restart_syms : 0, (rcb_restart_point*)d_rs, &total);
         *h_out_bytes = total;
         if (r) return r;
         if (total > out_cap) return RCB_ERR_OUT_CAPACITY;
         CK(c, cudaMemcpyAsync(h_offsets, d_off, (n_chunks + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost,
                               c->stream));
         if (total) CK(c, cudaMemcpyAsync(h_out, d_out, total, cudaMemcpyDeviceToHost, c->stream));
+        if (R) CK(c, cudaMemcpyAsync(h_restart, d_rs, n_chunks * R * sizeof(Restart), cudaMemcpyDeviceToHost, c->stream));
         CK(c, cudaStreamSynchronize(c->stream));
         return RCB_OK;
     }
@@ -1444,9 +1460,24 @@ extern "C" int rcb_encode_host(rcb_ctx* c, const void* h_syms, uint64_t n_syms, 
     return RCB_OK;
 }
 
-extern "C" int rcb_decode_host(rcb_ctx* c, const uint8_t* h_stream, const uint64_t* h_offsets,
-                               uint64_t n_syms, int sym_bytes, uint64_t chunk_syms, const rcb_model* m,
-                               void* h_syms_out) {
+extern "C" int rcb_encode_host(rcb_ctx* c, const void* h_syms, uint64_t n_syms, int sym_bytes,
+                               uint64_t chunk_syms, const rcb_model* m, uint8_t* h_out, uint64_t out_cap,
+                               uint64_t* h_offsets, uint64_t* h_out_bytes) {
+    return encode_host_impl(c, h_syms, n_syms, sym_bytes, chunk_syms, m, h_out, out_cap, h_offsets, h_out_bytes, 0,
+                            nullptr);
+}
+
+extern "C" int rcb_encode_host_restart(rcb_ctx* c, const void* h_syms, uint64_t n_syms, int sym_bytes,
+                                       uint64_t chunk_syms, const rcb_model* m, uint8_t* h_out, uint64_t out_cap,
+                                       uint64_t* h_offsets, uint64_t* h_out_bytes, uint64_t restart_syms,
+                                       rcb_restart_point* h_restart) {
+    return encode_host_impl(c, h_syms, n_syms, sym_bytes, chunk_syms, m, h_out, out_cap, h_offsets, h_out_bytes,
+                            restart_syms, h_restart);
+}
+
+static int decode_host_impl(rcb_ctx* c, const uint8_t* h_stream, const uint64_t* h_offsets, uint64_t n_syms,
+                            int sym_bytes, uint64_t chunk_syms, const rcb_model* m, void* h_syms_out,
+                            uint64_t restart_syms, const rcb_restart_point* h_restart) {
     if (!c || !m || !m->ready || chunk_syms == 0 || !h_offsets) return RCB_ERR_INVALID_ARGUMENT;
     if (sym_bytes != 1 && sym_bytes != 2) return RCB_ERR_UNSUPPORTED;
     if (n_syms && (!h_stream || !h_syms_out)) return RCB_ERR_INVALID_ARGUMENT;
@@ -1463,18 +1494,26 @@ extern "C" int rcb_decode_host(rcb_ctx* c, const uint8_t* h_stream, const uint64
     const uint64_t st_bytes = (total + 47) & ~15ull;
     const uint64_t off_bytes = ((n_chunks + 1) * sizeof(uint64_t) + 15) & ~15ull;
     const uint64_t out_bytes = (n_syms * sym_bytes + 15) & ~15ull;
+    RestartSpec rs;
+    if (int rr = make_restart_spec(chunk_syms, restart_syms, h_restart, &rs)) return rr;
+    const uint64_t R = rs.per_chunk;
+    const uint64_t rs_bytes = (n_chunks * R * sizeof(Restart) + 15) & ~15ull;
     ON_DEVICE(c);
-    int r = ensure_h2d(c, st_bytes + off_bytes + out_bytes + 64);
+    int r = ensure_h2d(c, st_bytes + off_bytes + out_bytes + rs_bytes + 64);
     if (r) return r;
     uint8_t* d_st = (uint8_t*)c->h2d;
     uint64_t* d_off = (uint64_t*)(d_st + st_bytes);
     uint8_t* d_out = (uint8_t*)d_off + off_bytes;
+    Restart* d_rs = R ? (Restart*)(d_out + out_bytes) : nullptr;
+    if (R && n_chunks)  // a few bytes per chunk: one copy ahead of everything else
+        CK(c, cudaMemcpyAsync(d_rs, h_restart, n_chunks * R * sizeof(Restart), cudaMemcpyHostToDevice, c->stream));
     const int S = pick_slices(n_chunks, n_syms * sym_bytes);
     if (S == 1 || (chunk_syms * sym_bytes) % 16 != 0) {
         if (total) CK(c, cudaMemcpyAsync(d_st, h_stream, total, cudaMemcpyHostToDevice, c->stream));
         CK(c, cudaMemcpyAsync(d_off, h_offsets, (n_chunks + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice,
                               c->stream));
-        r = rcb_decode_chunks(c, d_st, d_off, n_syms, sym_bytes, chunk_syms, m, d_out, nullptr);
+        r = rcb_decode_chunks_restart(c, d_st, d_off, n_syms, sym_bytes, chunk_syms, m, d_out, nullptr,
+                                      R ? restart_syms : 0, (const rcb_restart_point*)d_rs);
         if (r) return r;
         if (n_syms)
             CK(c, cudaMemcpyAsync(h_syms_out, d_out, n_syms * sym_bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -1490,7 +1529,8 @@ extern "C" int rcb_decode_host(rcb_ctx* c, const uint8_t* h_stream, const uint64
     CK(c, cudaStreamSynchronize(c->stream));
     // segments per chunk: 4 when a chunk is big enough for the split to pay (>= 32 KiB, quarter a multiple
     // of 16 symbols so that every segment starts on a word of output)
-    const int P = (chunk_syms * sym_bytes >= (32u << 10) && chunk_syms % 64 == 0) ? 4 : 1;
+    // (with restart points the parts of a chunk are decoded side by side instead: one launch per slice)
+    const int P = (!R && chunk_syms * sym_bytes >= (32u << 10) && chunk_syms % 64 == 0) ? 4 : 1;
     const uint64_t seg_syms = chunk_syms / P;
     if (P > 1 && c->resume_cap < n_chunks) {
         cudaFree(c->d_resume);
@@ -1542,8 +1582,10 @@ extern "C" int rcb_decode_host(rcb_ctx* c, const uint8_t* h_stream, const uint64
         for (int ph = 0; ph < P && rc == RCB_OK; ph++) {
             const uint64_t f0 = seg_syms * ph;
             DecSegment seg{f0, seg_syms, P > 1 ? c->d_resume + c0 : nullptr, ph > 0 ? 1u : 0u, ph < P - 1 ? 1u : 0u};
+            RestartSpec rsk = rs;
+            if (R) rsk.pts = d_rs + c0 * R;
             rc = decode_issue(c, d_st, d_off + c0, s1 - s0, sym_bytes, chunk_syms, m, c0, d_out + s0 * sym_bytes,
-                              c->status + c0, c->d_slice_summary + 8 * k, false, &seg);
+                              c->status + c0, c->d_slice_summary + 8 * k, false, R ? nullptr : &seg, R ? &rsk : nullptr);
             if (rc) break;
             if (trace_on()) cudaEventRecord(tr_k[k][ph], c->stream);
             e = cudaEventRecord(c->out_ready[k], c->stream);
@@ -1614,6 +1656,19 @@ extern "C" int rcb_decode_host(rcb_ctx* c, const uint8_t* h_stream, const uint64
     for (int k = 0; k < S; k++)
         if (c->h_slice_summary[8 * k]) return status_to_error((uint32_t)c->h_slice_summary[8 * k + 2]);
     return RCB_OK;
+}
+
+extern "C" int rcb_decode_host(rcb_ctx* c, const uint8_t* h_stream, const uint64_t* h_offsets,
+                               uint64_t n_syms, int sym_bytes, uint64_t chunk_syms, const rcb_model* m,
+                               void* h_syms_out) {
+    return decode_host_impl(c, h_stream, h_offsets, n_syms, sym_bytes, chunk_syms, m, h_syms_out, 0, nullptr);
+}
+
+extern "C" int rcb_decode_host_restart(rcb_ctx* c, const uint8_t* h_stream, const uint64_t* h_offsets,
+                                       uint64_t n_syms, int sym_bytes, uint64_t chunk_syms, const rcb_model* m,
+                                       void* h_syms_out, uint64_t restart_syms, const rcb_restart_point* h_restart) {
+    return decode_host_impl(c, h_stream, h_offsets, n_syms, sym_bytes, chunk_syms, m, h_syms_out, restart_syms,
+                            h_restart);
 }
 
 // ----------------------------------------------------------- synthetic data
@@ -1763,27 +1818,45 @@ extern "C" uint64_t rcb_frame_bound(uint32_t K, uint64_t n_chunks, int per_chunk
     return FRAME_HDR + frame_model_bytes(K, n_chunks, per_chunk) + (n_chunks + 1) * 8 + payload_bytes;
 }
 
+extern "C" uint64_t rcb_frame_bound_restart(uint32_t K, uint64_t n_chunks, int per_chunk, uint64_t payload_bytes,
+                                            uint64_t chunk_syms, uint64_t restart_syms) {
+    return rcb_frame_bound(K, n_chunks, per_chunk, payload_bytes) +
+           n_chunks * rcb_restart_points_per_chunk(chunk_syms, restart_syms) * sizeof(Restart);
+}
+
 extern "C" int rcb_frame_write(rcb_ctx* c, const rcb_model* m, int sym_bytes, uint64_t chunk_syms, uint64_t n_syms,
                                const uint8_t* h_stream, const uint64_t* h_offsets, uint8_t* h_frame,
                                uint64_t frame_cap, uint64_t* h_frame_bytes) {
+    return rcb_frame_write_restart(c, m, sym_bytes, chunk_syms, n_syms, h_stream, h_offsets, 0, nullptr, h_frame,
+                                   frame_cap, h_frame_bytes);
+}
+
+extern "C" int rcb_frame_write_restart(rcb_ctx* c, const rcb_model* m, int sym_bytes, uint64_t chunk_syms,
+                                       uint64_t n_syms, const uint8_t* h_stream, const uint64_t* h_offsets,
+                                       uint64_t restart_syms, const rcb_restart_point* h_restart, uint8_t* h_frame,
+                                       uint64_t frame_cap, uint64_t* h_frame_bytes) {
     if (!c || !m || !m->ready || !h_offsets || !h_frame || !h_frame_bytes || chunk_syms == 0)
         return RCB_ERR_INVALID_ARGUMENT;
+    RestartSpec rs;
+    if (int rr = make_restart_spec(chunk_syms, restart_syms, h_restart, &rs)) return rr;
+    const uint64_t R = rs.per_chunk;
     const uint64_t n_chunks = (n_syms + chunk_syms - 1) / chunk_syms;
     const int per_chunk = m->n_models != 1;
     if (per_chunk && m->n_models != n_chunks) return RCB_ERR_INVALID_ARGUMENT;
     if (per_chunk && (m->bad_bits & 8u)) return RCB_ERR_UNSUPPORTED;  // per-chunk section stores c only
     const uint64_t payload = h_offsets[n_chunks];
     if (payload && !h_stream) return RCB_ERR_INVALID_ARGUMENT;
-    const uint64_t need = rcb_frame_bound(m->K, n_chunks, per_chunk, payload);
+    const uint64_t rs_bytes = n_chunks * R * sizeof(Restart);
+    const uint64_t need = rcb_frame_bound(m->K, n_chunks, per_chunk, payload) + rs_bytes;
     *h_frame_bytes = need;
     if (need > frame_cap) return RCB_ERR_OUT_CAPACITY;
     uint8_t* p = h_frame;
     memcpy(p, "RCB2", 4);
-    put_le<uint32_t>(p + 4, 1);
+    put_le<uint32_t>(p + 4, R ? 2 : 1);  // version 2 = a restart section follows the offsets
     put_le<uint32_t>(p + 8, (uint32_t)sym_bytes);
     put_le<uint32_t>(p + 12, m->K);
     put_le<uint32_t>(p + 16, (uint32_t)per_chunk);
-    put_le<uint32_t>(p + 20, 0);
+    put_le<uint32_t>(p + 20, R ? (uint32_t)(restart_syms / 64) : 0);
     put_le<uint64_t>(p + 24, chunk_syms);
     put_le<uint64_t>(p + 32, n_syms);
     put_le<uint64_t>(p + 40, n_chunks);
@@ -1813,7 +1886,9 @@ extern "C" int rcb_frame_write(rcb_ctx* c, const rcb_model* m, int sym_bytes, ui
     free(tmp);
     uint8_t* os = ms + frame_model_bytes(m->K, n_chunks, per_chunk);
     memcpy(os, h_offsets, (n_chunks + 1) * 8);
-    if (payload) memcpy(os + (n_chunks + 1) * 8, h_stream, payload);
+    uint8_t* rsec = os + (n_chunks + 1) * 8;
+    if (rs_bytes) memcpy(rsec, h_restart, rs_bytes);  // 24-byte little-endian records, as in memory
+    if (payload) memcpy(rsec + rs_bytes, h_stream, payload);
     return RCB_OK;
 }
 
@@ -1829,9 +1904,14 @@ extern "C" int rcb_frame_parse(const uint8_t* h_frame, uint64_t len, rcb_frame_i
     f.n_syms = get_le<uint64_t>(h_frame + 32);
     f.n_chunks = get_le<uint64_t>(h_frame + 40);
     f.payload_bytes = get_le<uint64_t>(h_frame + 48);
-    if (f.version != 1 || (f.sym_bytes != 1 && f.sym_bytes != 2) || f.K == 0 || f.K > MAX_K || f.model_mode > 1 ||
-        f.chunk_syms == 0)
+    const uint32_t restart_units = get_le<uint32_t>(h_frame + 20);
+    if ((f.version != 1 && f.version != 2) || (f.sym_bytes != 1 && f.sym_bytes != 2) || f.K == 0 || f.K > MAX_K ||
+        f.model_mode > 1 || f.chunk_syms == 0)
         return RCB_ERR_INVALID_ARGUMENT;
+    // version 1 has no restart section (the field is reserved, 0); version 2 has one
+    if ((f.version == 1) != (restart_units == 0)) return RCB_ERR_INVALID_ARGUMENT;
+    f.restart_syms = (uint64_t)restart_units * 64;
+    f.restart_off = 0;
     // untrusted header: bound everything before it enters any arithmetic (n_syms * sym_bytes and the
     // ceil-division below must not wrap; chunk_syms has the coder's own limit)
     if (f.n_syms > (1ull << 62) || f.chunk_syms > 0x40000000ull) return RCB_ERR_INVALID_ARGUMENT;
@@ -1840,6 +1920,12 @@ extern "C" int rcb_frame_parse(const uint8_t* h_frame, uint64_t len, rcb_frame_i
     f.model_off = FRAME_HDR;
     f.offsets_off = f.model_off + frame_model_bytes(f.K, f.n_chunks, (int)f.model_mode);
     f.payload_off = f.offsets_off + (f.n_chunks + 1) * 8;
+    if (f.restart_syms) {
+        const uint64_t per = rcb_restart_points_per_chunk(f.chunk_syms, f.restart_syms);
+        if (per == 0 || per > 63) return RCB_ERR_INVALID_ARGUMENT;  // same limits as the coder entry points
+        f.restart_off = f.payload_off;
+        f.payload_off += f.n_chunks * per * sizeof(Restart);  // n_chunks < 2^31, per < 64: no wrap
+    }
     f.frame_bytes = f.payload_off + f.payload_bytes;
     if (f.frame_bytes > len) return RCB_ERR_TRUNCATED_STREAM;
     // offsets: start at 0, every chunk holds at least the 8 bytes of Encoder::finish
@@ -1905,10 +1991,11 @@ extern "C" int rcb_frame_model(rcb_ctx* c, const uint8_t* h_frame, const rcb_fra
     return RCB_OK;
 }
 
-extern "C" int rcb_frame_encode_host(rcb_ctx* c, const void* h_syms, uint64_t n_syms, int sym_bytes,
-                                     uint64_t chunk_syms, const rcb_model* m, uint8_t* h_frame, uint64_t frame_cap,
-                                     uint64_t* h_frame_bytes) {
+extern "C" int rcb_frame_encode_host_restart(rcb_ctx* c, const void* h_syms, uint64_t n_syms, int sym_bytes,
+                                             uint64_t chunk_syms, const rcb_model* m, uint64_t restart_syms,
+                                             uint8_t* h_frame, uint64_t frame_cap, uint64_t* h_frame_bytes) {
     if (!c || !m || !m->ready || !h_frame || !h_frame_bytes || chunk_syms == 0) return RCB_ERR_INVALID_ARGUMENT;
+    if (restart_syms % 64) return RCB_ERR_INVALID_ARGUMENT;
     const uint64_t n_chunks = (n_syms + chunk_syms - 1) / chunk_syms;
     const uint64_t cap = rcb_encode_bound(c, m, n_syms, sym_bytes, chunk_syms) + 64;
     uint8_t* stream = (uint8_t*)malloc(cap);
@@ -1919,12 +2006,32 @@ extern "C" int rcb_frame_encode_host(rcb_ctx* c, const void* h_syms, uint64_t n_
         return RCB_ERR_INVALID_ARGUMENT;
     }
     uint64_t bytes = 0;
-    int r = rcb_encode_host(c, h_syms, n_syms, sym_bytes, chunk_syms, m, stream, cap, offs, &bytes);
+    rcb_restart_point* pts = nullptr;
+    const uint64_t R = rcb_restart_points_per_chunk(chunk_syms, restart_syms);
+    if (R) {
+        pts = (rcb_restart_point*)malloc((size_t)(n_chunks * R ? n_chunks * R : 1) * sizeof(rcb_restart_point));
+        if (!pts) {
+            free(stream);
+            free(offs);
+            return RCB_ERR_INVALID_ARGUMENT;
+        }
+    }
+    int r = rcb_encode_host_restart(c, h_syms, n_syms, sym_bytes, chunk_syms, m, stream, cap, offs, &bytes,
+                                    R ? restart_syms : 0, pts);
     if (r == RCB_OK)
-        r = rcb_frame_write(c, m, sym_bytes, chunk_syms, n_syms, stream, offs, h_frame, frame_cap, h_frame_bytes);
+        r = rcb_frame_write_restart(c, m, sym_bytes, chunk_syms, n_syms, stream, offs, R ? restart_syms : 0, pts,
+                                    h_frame, frame_cap, h_frame_bytes);
     free(stream);
     free(offs);
+    free(pts);
     return r;
+}
+
+extern "C" int rcb_frame_encode_host(rcb_ctx* c, const void* h_syms, uint64_t n_syms, int sym_bytes,
+                                     uint64_t chunk_syms, const rcb_model* m, uint8_t* h_frame, uint64_t frame_cap,
+                                     uint64_t* h_frame_bytes) {
+    return rcb_frame_encode_host_restart(c, h_syms, n_syms, sym_bytes, chunk_syms, m, 0, h_frame, frame_cap,
+                                         h_frame_bytes);
 }
 
 extern "C" int rcb_frame_decode_host(rcb_ctx* c, const uint8_t* h_frame, uint64_t len, void* h_syms_out,
@@ -1950,7 +2057,17 @@ extern "C" int rcb_frame_decode_host(rcb_ctx* c, const uint8_t* h_frame, uint64_
     memcpy(stream, h_frame + f.payload_off, (size_t)f.payload_bytes);
     memset(stream + f.payload_bytes, 0, 64);
     memcpy(offs, h_frame + f.offsets_off, (size_t)(f.n_chunks + 1) * 8);
-    r = rcb_decode_host(c, stream, offs, f.n_syms, (int)f.sym_bytes, f.chunk_syms, m, h_syms_out);
+    rcb_restart_point* pts = nullptr;
+    if (f.restart_syms) {  // records may be unaligned in the frame
+        const size_t nb = (size_t)(f.payload_off - f.restart_off);
+        pts = (rcb_restart_point*)malloc(nb ? nb : 1);
+        if (pts) memcpy(pts, h_frame + f.restart_off, nb);
+    }
+    r = (f.restart_syms && !pts)
+            ? RCB_ERR_INVALID_ARGUMENT
+            : rcb_decode_host_restart(c, stream, offs, f.n_syms, (int)f.sym_bytes, f.chunk_syms, m, h_syms_out,
+                                      f.restart_syms, pts);
+    free(pts);
     free(stream);
     free(offs);
     rcb_model_destroy(m);

@@ -355,13 +355,40 @@ RCB_HD uint64_t fused_rpt(uint64_t range, const FusedParams& fp) {
     return MODE == FUSE_GEN ? range_par_total<false>(range, fp.div) : (range >> fp.s);
 }
 
-template <int MODE = FUSE_BIG>
+// TPUT = true: the same step tuned for instruction count instead of latency (several warps per scheduler:
+// restart points).  The shift comes from one count-leading-zeros (sh = clz(xh) & 24; equal high words --
+// n1 >= 4 -- give sh = 0) and "loop 2 stays idle" is tested on the shifted range itself, range' << sh >= 2^48,
+// which is exact for n1 <= 3 and fails for n1 >= 4 (range' < 2^32): 3-4 integer instructions instead of 8.
+RCB_HD uint32_t tput_shift(uint32_t xh) {
+#if defined(__CUDA_ARCH__)
+    uint32_t f;  // position of the leading one, 0xFFFFFFFF for 0: clz & 24 == ~f & 24 (one find + one logic op)
+    asm("bfind.u32 %0, %1;" : "=r"(f) : "r"(xh));
+    return ~f & 24u;
+#else
+    return clz32(xh) & 24u;
+#endif
+}
+RCB_HD bool tput_loop2_idle(uint64_t rgp, uint32_t sh) {
+    return funnel_l(lo32(rgp), hi32(rgp), sh) >= (1u << 16);  // hi32(range' << sh) >= 2^16
+}
+
+template <int MODE = FUSE_BIG, bool TPUT = false>
 RCB_HD bool fused_step(uint64_t lo, uint64_t rpt, uint32_t cum, uint32_t c, const FusedParams& fp,
                        uint64_t& nlo, uint64_t& rgp, uint64_t& nrpt, uint32_t& sh) {
     nlo = mad64x32(rpt, cum, lo);
     const uint64_t up = mad64x32(rpt, cum + c, lo);
     rgp = mad64x32(rpt, c, 0ull);
     const uint32_t xh = hi32(nlo) ^ hi32(up);
+    if (TPUT) {
+        sh = tput_shift(xh);
+        if (MODE == FUSE_BIG) {
+            nrpt = rgp >> ((fp.k0 + 24u) - sh);
+            return nrpt >= (uint64_t)(1u << (24u - fp.k0));  // range' << sh >= 2^48 (see fused_decode_step)
+        }
+        const uint64_t y = rgp << sh;
+        nrpt = fused_rpt<MODE>(y, fp);
+        return hi32(y) >= (1u << 16);
+    }
     const bool p1 = xh < (1u << 24), p2 = xh < (1u << 16), p3 = xh < (1u << 8);
     if (MODE == FUSE_BIG) {
         const uint32_t k = p2 ? (p3 ? fp.k0 : fp.k0 + 8u) : (p1 ? fp.k0 + 16u : fp.k0 + 24u);
@@ -446,12 +473,18 @@ RCB_HD bool fused_rpt_m2(uint64_t rgp, uint32_t sh, const Recip2& k, uint64_t& n
 }
 
 // fused_step with the divide-free rpt_next (encoder, FUSE_GEN tables that carry cs)
+template <bool TPUT = false>
 RCB_HD bool fused_step_cs(uint64_t lo, uint64_t rpt, uint32_t cum, uint32_t c, uint64_t cs,
                           uint64_t& nlo, uint64_t& rgp, uint64_t& nrpt, uint32_t& sh) {
     nlo = mad64x32(rpt, cum, lo);
     const uint64_t up = mad64x32(rpt, cum + c, lo);
     rgp = mad64x32(rpt, c, 0ull);
     const uint32_t xh = hi32(nlo) ^ hi32(up);
+    if (TPUT) {
+        sh = tput_shift(xh);
+        const bool exact = fused_rpt_cs(rpt, cs, sh, nrpt);
+        return exact & tput_loop2_idle(rgp, sh);
+    }
     const bool p1 = xh < (1u << 24), p2 = xh < (1u << 16), p3 = xh < (1u << 8);
     sh = p2 ? (p3 ? 24u : 16u) : (p1 ? 8u : 0u);
     const bool exact = fused_rpt_cs(rpt, cs, sh, nrpt);
@@ -460,12 +493,18 @@ RCB_HD bool fused_step_cs(uint64_t lo, uint64_t rpt, uint32_t cum, uint32_t c, u
 }
 
 // ... and with the table-wide constant (totals >= 2^25)
+template <bool TPUT = false>
 RCB_HD bool fused_step_m2(uint64_t lo, uint64_t rpt, uint32_t cum, uint32_t c, const Recip2& k,
                           uint64_t& nlo, uint64_t& rgp, uint64_t& nrpt, uint32_t& sh) {
     nlo = mad64x32(rpt, cum, lo);
     const uint64_t up = mad64x32(rpt, cum + c, lo);
     rgp = mad64x32(rpt, c, 0ull);
     const uint32_t xh = hi32(nlo) ^ hi32(up);
+    if (TPUT) {
+        sh = tput_shift(xh);
+        const bool exact = fused_rpt_m2(rgp, sh, k, nrpt);
+        return exact & tput_loop2_idle(rgp, sh);
+    }
     const bool p1 = xh < (1u << 24), p2 = xh < (1u << 16), p3 = xh < (1u << 8);
     sh = p2 ? (p3 ? 24u : 16u) : (p1 ? 8u : 0u);
     const bool exact = fused_rpt_m2(rgp, sh, k, nrpt);
@@ -669,23 +708,6 @@ struct FusedDec {
     bool inside;  // symbol verified: lower' <= data < upper'
     bool ok;      // ... and the fast renormalisation applies
 };
-
-// TPUT = true: the same step tuned for instruction count instead of latency (several warps per scheduler:
-// restart points).  The shift comes from one count-leading-zeros (sh = clz(xh) & 24; equal high words --
-// n1 >= 4 -- give sh = 0) and "loop 2 stays idle" is tested on the shifted range itself, range' << sh >= 2^48,
-// which is exact for n1 <= 3 and fails for n1 >= 4 (range' < 2^32): 3-4 integer instructions instead of 8.
-RCB_HD uint32_t tput_shift(uint32_t xh) {
-#if defined(__CUDA_ARCH__)
-    uint32_t f;  // position of the leading one, 0xFFFFFFFF for 0: clz & 24 == ~f & 24 (one find + one logic op)
-    asm("bfind.u32 %0, %1;" : "=r"(f) : "r"(xh));
-    return ~f & 24u;
-#else
-    return clz32(xh) & 24u;
-#endif
-}
-RCB_HD bool tput_loop2_idle(uint64_t rgp, uint32_t sh) {
-    return funnel_l(lo32(rgp), hi32(rgp), sh) >= (1u << 16);  // hi32(range' << sh) >= 2^16
-}
 
 template <int MODE = FUSE_BIG, bool TPUT = false>
 RCB_HD FusedDec fused_decode_step(uint64_t lo, uint64_t rpt, uint64_t data, const LutEntry& e,

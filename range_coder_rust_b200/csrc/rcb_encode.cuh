@@ -72,6 +72,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tma
         : "memory");
 }
 
+// The hot loop's step can take its shift from one count-leading-zeros + the exact loop-2 test (rcb_core.cuh:
+// TPUT) instead of the compare/select tree: 3 instructions fewer per symbol, but the find sits on the
+// (lower, range) recurrence and the encoder runs one warp per scheduler at configs[1] -- measured 3.35 -> 3.53 ms.
+// Off; the decoder's fused loop uses it (its chain hides it behind the table load).
+#ifndef RCB_ENC_CLZ
+#define RCB_ENC_CLZ 0
+#endif
+constexpr bool ENC_CLZ = RCB_ENC_CLZ != 0;
+
 enum : int { TAB_SHARED = 0, TAB_LANE = 1, TAB_GLOBAL = 2 };
 // FM_GENCS: general total with the divide-free step (each table entry carries cs = floor(c * 2^64 / total),
 // rcb_core.cuh: fused_step_cs); TAB_SHARED only.  FM_GEN keeps the multiply-high reciprocal.
@@ -285,6 +294,11 @@ __device__ __forceinline__ void encode_body(const EncodeArgs& a, const CUtensorM
     // restart points of this chunk: rp_n written so far, the next one is due in front of symbol (rp_n+1)*restart_syms
     Restart* const rpts = a.restart ? a.restart + chunk * a.restart_per_chunk : nullptr;
     uint32_t rp_n = 0;
+    // a record holds range rounded down to a multiple of total_freq (what the fused loops carry; canonical, so
+    // that every kernel flavour -- and the checker -- writes the same bytes)
+    auto canon_range = [&](uint64_t r) -> uint64_t {
+        return (pow2 ? range_par_total<true>(r, div) : range_par_total<false>(r, div)) * (uint64_t)div.total;
+    };
 
     constexpr int SPW = 4 / sizeof(SYM);  // symbols per 32-bit word
     using Entries = typename std::conditional<CS, EncEntries4<SPW>, EncEntries<SPW>>::type;
@@ -408,12 +422,12 @@ __device__ __forceinline__ void encode_body(const EncodeArgs& a, const CUtensorM
                             uint32_t sh;
                             bool ok;
                             if constexpr (CS)
-                                ok = fused_step_cs(lo, rpt, en.e[b].x, en.e[b].y,
-                                                   ((uint64_t)en.e[b].w << 32) | en.e[b].z, nlo, rgp, nrpt, sh);
+                                ok = fused_step_cs<ENC_CLZ>(lo, rpt, en.e[b].x, en.e[b].y,
+                                                            ((uint64_t)en.e[b].w << 32) | en.e[b].z, nlo, rgp, nrpt, sh);
                             else if constexpr (M2)
-                                ok = fused_step_m2(lo, rpt, en.e[b].x, en.e[b].y, k2, nlo, rgp, nrpt, sh);
+                                ok = fused_step_m2<ENC_CLZ>(lo, rpt, en.e[b].x, en.e[b].y, k2, nlo, rgp, nrpt, sh);
                             else
-                                ok = fused_step<MODE>(lo, rpt, en.e[b].x, en.e[b].y, fp, nlo, rgp, nrpt, sh);
+                                ok = fused_step<MODE, ENC_CLZ>(lo, rpt, en.e[b].x, en.e[b].y, fp, nlo, rgp, nrpt, sh);
                             fs.put(em_hi, em_sh);
                             em_hi = hi32(nlo);
                             em_sh = sh;
@@ -527,7 +541,7 @@ __device__ __forceinline__ void encode_body(const EncodeArgs& a, const CUtensorM
                 for (; i < nvec; i++) {
                     prefetch_block(i);
                     if (rpts && i * PER == (uint64_t)(rp_n + 1u) * a.restart_syms)
-                        rpts[rp_n++] = Restart{lo, rg, sink.pos + (sink.nb >> 3), 0u};
+                        rpts[rp_n++] = Restart{lo, canon_range(rg), sink.pos + (sink.nb >> 3), 0u};
                     const uint4 nxt = (i + 1 < nvec) ? ldg_stream_v4(v + i + 1) : make_uint4(0, 0, 0, 0);
                     Entries eB = lookup(cur.y);
                     code(eA);
@@ -546,7 +560,7 @@ __device__ __forceinline__ void encode_body(const EncodeArgs& a, const CUtensorM
 #pragma unroll 1
     for (uint64_t i = done; i < cnt; i++) {
         if (rpts && i == (uint64_t)(rp_n + 1u) * a.restart_syms)
-            rpts[rp_n++] = Restart{lo, rg, sink.pos + (sink.nb >> 3), 0u};
+            rpts[rp_n++] = Restart{lo, canon_range(rg), sink.pos + (sink.nb >> 3), 0u};
         generic_symbol(entry((uint32_t)src[i]));
     }
     if (rpts)  // a ragged last chunk has fewer restart points: the rest are marked absent (range 0)

@@ -37,6 +37,17 @@ pub struct RcbStreamState {
     pub pad: u32,
 }
 
+/// `rcb_restart_point`: the Encoder's RangeCoder in front of a symbol of a chunk (src/range_coder.rs:7-12,
+/// range rounded down to a multiple of total_freq) and the bytes `Encoder::encode` has returned by then.
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct RcbRestartPoint {
+    pub lower_bound: u64,
+    pub range: u64,
+    pub code_bytes: u32,
+    pub reserved: u32,
+}
+
 pub const RCB_OK: c_int = 0;
 pub const RCB_ERR_ZERO_TOTAL: c_int = -3;
 pub const RCB_ERR_ZERO_FREQ_SYMBOL: c_int = -4;
@@ -46,6 +57,7 @@ pub const RCB_ERR_SYMBOL_OUT_OF_RANGE: c_int = -7;
 pub const RCB_ERR_OUT_CAPACITY: c_int = -8;
 pub const RCB_ERR_TRUNCATED_STREAM: c_int = -9;
 pub const RCB_ERR_NCCL: c_int = -13;
+pub const RCB_ERR_RESTART_POINT: c_int = -14;
 
 extern "C" {
     pub fn rcb_ctx_create(device: c_int, stream: *mut c_void, out: *mut *mut RcbCtx) -> c_int;
@@ -84,6 +96,35 @@ extern "C" {
         chunk: u64,
         m: *const RcbModel,
         out: *mut c_void,
+    ) -> c_int;
+
+    // restart points: the Encoder's state every restart_syms symbols of a chunk (several decoder lanes per chunk)
+    pub fn rcb_restart_points_per_chunk(chunk_syms: u64, restart_syms: u64) -> u64;
+    pub fn rcb_encode_host_restart(
+        ctx: *mut RcbCtx,
+        syms: *const c_void,
+        n: u64,
+        sym_bytes: c_int,
+        chunk: u64,
+        m: *const RcbModel,
+        out: *mut u8,
+        cap: u64,
+        offsets: *mut u64,
+        out_bytes: *mut u64,
+        restart_syms: u64,
+        restart: *mut RcbRestartPoint,
+    ) -> c_int;
+    pub fn rcb_decode_host_restart(
+        ctx: *mut RcbCtx,
+        stream: *const u8,
+        offsets: *const u64,
+        n: u64,
+        sym_bytes: c_int,
+        chunk: u64,
+        m: *const RcbModel,
+        out: *mut c_void,
+        restart_syms: u64,
+        restart: *const RcbRestartPoint,
     ) -> c_int;
 
     pub fn rcb_stream_state_init(st: *mut RcbStreamState);
@@ -191,6 +232,26 @@ extern "C" {
         sym_bytes: c_int,
         chunk: u64,
         m: *const RcbModel,
+        frame: *mut u8,
+        cap: u64,
+        frame_bytes: *mut u64,
+    ) -> c_int;
+    pub fn rcb_frame_bound_restart(
+        k: u32,
+        n_chunks: u64,
+        per_chunk: c_int,
+        payload: u64,
+        chunk_syms: u64,
+        restart_syms: u64,
+    ) -> u64;
+    pub fn rcb_frame_encode_host_restart(
+        ctx: *mut RcbCtx,
+        syms: *const c_void,
+        n: u64,
+        sym_bytes: c_int,
+        chunk: u64,
+        m: *const RcbModel,
+        restart_syms: u64,
         frame: *mut u8,
         cap: u64,
         frame_bytes: *mut u64,

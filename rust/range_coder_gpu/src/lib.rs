@@ -40,6 +40,19 @@ pub struct Encoded {
     pub stream: Vec<u8>,
     pub offsets: Vec<u64>,
     pub chunk_syms: u64,
+    /// Restart points (include/rcb200.h): the Encoder's state every `restart_syms` symbols of a chunk.  Side
+    /// information for `decode_chunks` (several GPU lanes per chunk); `stream` is unchanged by it.
+    pub restart_syms: u64,
+    pub restart: Vec<ffi::RcbRestartPoint>,
+}
+
+/// Restart points every quarter of a chunk when that is a whole number of 64-symbol units (0: none).
+pub fn default_restart_syms(chunk_syms: u64) -> u64 {
+    if chunk_syms % 256 == 0 {
+        chunk_syms / 4
+    } else {
+        0
+    }
 }
 
 impl Encoded {
@@ -118,7 +131,13 @@ impl Gpu {
             let mut stream = vec![0u8; cap as usize];
             let mut offsets = vec![0u64; n_chunks as usize + 1];
             let mut bytes = 0u64;
-            to_result(ffi::rcb_encode_host(
+            let mut restart_syms = default_restart_syms(chunk_syms);
+            let per = ffi::rcb_restart_points_per_chunk(chunk_syms, restart_syms);
+            if per == 0 {
+                restart_syms = 0;
+            }
+            let mut restart = vec![ffi::RcbRestartPoint::default(); (n_chunks * per) as usize];
+            to_result(ffi::rcb_encode_host_restart(
                 self.ctx,
                 symbols.as_ptr() as *const c_void,
                 n,
@@ -129,9 +148,11 @@ impl Gpu {
                 cap,
                 offsets.as_mut_ptr(),
                 &mut bytes,
+                restart_syms,
+                if restart.is_empty() { std::ptr::null_mut() } else { restart.as_mut_ptr() },
             ))?;
             stream.truncate(bytes as usize);
-            Ok(Encoded { stream, offsets, chunk_syms })
+            Ok(Encoded { stream, offsets, chunk_syms, restart_syms, restart })
         }
     }
     pub fn encode_chunks(&self, t: &Table<'_>, symbols: &[u8], chunk_syms: u64) -> Encoded {
@@ -146,7 +167,7 @@ impl Gpu {
         padded.resize((enc.stream.len() + 15) / 16 * 16 + 16, 0); // device reader fetches 16-byte pieces
         let mut out = vec![0u8; n_syms as usize];
         to_result(unsafe {
-            ffi::rcb_decode_host(
+            ffi::rcb_decode_host_restart(
                 self.ctx,
                 padded.as_ptr(),
                 enc.offsets.as_ptr(),
@@ -155,6 +176,8 @@ impl Gpu {
                 enc.chunk_syms,
                 t.m,
                 out.as_mut_ptr() as *mut c_void,
+                enc.restart_syms,
+                if enc.restart.is_empty() { std::ptr::null() } else { enc.restart.as_ptr() },
             )
         })?;
         Ok(out)
@@ -169,16 +192,19 @@ impl Gpu {
         let n_chunks = (n + chunk_syms - 1) / chunk_syms;
         unsafe {
             let payload = ffi::rcb_encode_bound(self.ctx, t.m, n, 1, chunk_syms);
-            let cap = ffi::rcb_frame_bound(t.k as u32, n_chunks, 0, payload);
+            // version-2 frame: restart points next to the offsets (several decoder lanes per chunk)
+            let restart_syms = default_restart_syms(chunk_syms);
+            let cap = ffi::rcb_frame_bound_restart(t.k as u32, n_chunks, 0, payload, chunk_syms, restart_syms);
             let mut frame = vec![0u8; cap as usize];
             let mut bytes = 0u64;
-            to_result(ffi::rcb_frame_encode_host(
+            to_result(ffi::rcb_frame_encode_host_restart(
                 self.ctx,
                 symbols.as_ptr() as *const c_void,
                 n,
                 1,
                 chunk_syms,
                 t.m,
+                restart_syms,
                 frame.as_mut_ptr(),
                 cap,
                 &mut bytes,
@@ -367,7 +393,7 @@ impl MultiGpu {
                 k,
                 g_n as c_int,
             ))?;
-            let mut enc = Encoded { stream: Vec::new(), offsets: vec![0u64], chunk_syms };
+            let mut enc = Encoded { stream: Vec::new(), offsets: vec![0u64], chunk_syms, restart_syms: 0, restart: Vec::new() };
             for (g, gpu) in self.gpus.iter().enumerate() {
                 let cnt = first[g + 1] - first[g];
                 let chunks = (cnt + chunk_syms - 1) / chunk_syms;

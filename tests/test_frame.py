@@ -130,6 +130,49 @@ def test_gpu_frame_per_chunk_models(ctx, oracle):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("K,chunk,n,rs,per_chunk", [(256, 65536, 5 * 65536 + 777, 16384, False),
+                                                    (256, 8192, 20 * 8192 + 5, 2048, True),
+                                                    (4096, 32768, 3 * 32768 + 100, 8192, False),
+                                                    (256, 65536, 40 * 65536, 8192, False)])
+def test_gpu_frame_with_restart_points(ctx, oracle, K, chunk, n, rs, per_chunk):
+    """Version-2 frames: the restart section (every record from the oracle's Encoder state) makes the GPU frame
+    byte-identical to the checker's; either side's frame decodes on the other; the 40-chunk case runs the sliced
+    host pipeline."""
+    import torch
+
+    if per_chunk:
+        thr = np.stack([oracle.zipf_thresholds(K, s) for s in (0.0, 1.1, 3.0)])
+        syms = oracle.generate(n, K, 0x5EED0002, thr, chunk_syms=chunk)
+        d = torch.from_numpy(syms).to(ctx.device)
+        model = ctx.model_from_counts(ctx.histogram(d, K, chunk_syms=chunk))
+        models = [oracle.model_from_symbols(syms[j * chunk:(j + 1) * chunk], K) for j in range((n + chunk - 1) // chunk)]
+    else:
+        syms = _data(oracle, n, K)
+        c, cum, total = oracle.model_from_symbols(syms, K)
+        model = ctx.model_from_tables(c, cum, total)
+        models = [(c, cum, total)]
+    frame = ctx.frame_encode(syms, chunk, model, restart_syms=rs)
+    info = ctx.frame_info(frame)
+    assert info.version == 2 and info.restart_syms == rs and info.frame_bytes == frame.size
+    ref = frame_ref.write_frame(syms, chunk, models, K, restart_syms=rs)
+    assert frame.tobytes() == ref.tobytes()
+    assert np.array_equal(ctx.frame_decode(ref), syms)
+    assert np.array_equal(frame_ref.decode_frame(frame), syms)
+    # the same symbols without restart points: a version-1 frame with the same payload
+    plain = ctx.frame_encode(syms, chunk, model)
+    f1, f2 = frame_ref.read_frame(plain), frame_ref.read_frame(frame)
+    assert ctx.frame_info(plain).version == 1 and np.array_equal(f1["stream"], f2["stream"])
+    assert np.array_equal(f1["offsets"], f2["offsets"])
+    # a damaged record is reported (RCB_ERR_RESTART_POINT), not silently decoded
+    bad = frame.copy()
+    bad[info.restart_off] ^= 0x40
+    from range_coder_rust_b200 import RcbError
+    with pytest.raises(RcbError) as e:
+        ctx.frame_decode(bad)
+    assert e.value.code == -14
+
+
+@pytest.mark.gpu
 def test_gpu_frame_empty_and_capacity(ctx, oracle):
     c = np.array([3, 1], dtype=np.uint32)
     cum = np.array([0, 3], dtype=np.uint32)
@@ -165,3 +208,4 @@ def test_file_front_end_round_trip(tmp_path, oracle, adaptive):
     assert np.array_equal(frame_ref.decode_frame(np.fromfile(frm, dtype=np.uint8)), data)
     out = subprocess.run(cmd + ["info", str(frm)], check=True, cwd=root, capture_output=True, text=True).stdout
     assert "300007 symbols" in out and ("per-chunk tables" in out) == adaptive
+    assert "RCB2 v2" in out and "restart points every 8192 symbols" in out  # the front end's default: chunk / 4
