@@ -49,7 +49,9 @@ def parse_args():
     p.add_argument("--mode", default="static", choices=["static", "adaptive"],
                    help="static: one global table (all-reduced counts); adaptive: one table per chunk, mixed entropy")
     p.add_argument("--seed", type=lambda s: int(s, 0), default=None)
-    p.add_argument("--e2e-steps", type=int, default=6)
+    p.add_argument("--e2e-steps", type=int, default=8)
+    p.add_argument("--e2e-depth", type=int, default=2,
+                   help="host-buffer calls of each kind (encode / decode) in flight in the end-to-end leg")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-parity", action="store_true")
@@ -522,74 +524,94 @@ def run_ours(a):
     # ---- end to end through the host-buffer C ABI (pinned host memory, copies inside the timed region)
     e2e = None
     if not a.no_e2e:
-        old_affinity = bind_near_gpu(local_rank)
-        h_syms = torch.empty(n_syms, dtype=d_syms.dtype, pin_memory=True)
-        h_syms.copy_(d_syms)
-        h_stream = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
-        h_back = torch.empty(n_syms, dtype=d_syms.dtype, pin_memory=True)
-        a_syms, a_stream, a_back = h_syms.numpy(), h_stream.numpy(), h_back.numpy()
-        if sym_bytes == 2:
-            a_syms, a_back = a_syms.view(np.uint16), a_back.view(np.uint16)
-
-        # Two contexts on this GPU, one host thread each ("one ctx per GPU per thread", include/rcb200.h):
-        # the encode of batch i+1 runs while batch i is decoded, so both directions of the link carry
-        # data at the same time (one call alone is dominated by one direction).  Every step still copies
-        # its input host->device and its results device->host inside the timed region; a step's decode
-        # starts when its own encode has returned (it needs that call's offsets and byte count).
         import queue
         import threading as th_
 
-        ctx2 = rcb.Context(local_rank, stream=torch.cuda.Stream(dev))
+        old_affinity = bind_near_gpu(local_rank)
+        h_syms = torch.empty(n_syms, dtype=d_syms.dtype, pin_memory=True)
+        h_syms.copy_(d_syms)
+        a_syms = h_syms.numpy()
+        if sym_bytes == 2:
+            a_syms = a_syms.view(np.uint16)
+
+        # "One ctx per GPU per thread" (include/rcb200.h): a.e2e_depth encoder threads and as many decoder threads,
+        # each with its own context, so that the encodes of later steps run while earlier steps are decoded and
+        # both directions of the link carry data all the time (one call alone keeps the bus ~65 % busy, two of
+        # each kind ~83 %; three were measured slower).  Every step still copies its input host->device and its
+        # results device->host inside its two calls; a step's decode starts when its own encode has returned (it
+        # needs that call's offsets and byte count).
+        depth = max(1, a.e2e_depth)
         c_, cum_, total_, _f = (counts, None, None, None) if adaptive else model.tables()
-        if adaptive:
-            model2 = ctx2.model_from_counts(counts)
-        else:
-            model2 = ctx2.model_from_tables(c_, cum_, total_)
-        # double-buffered code streams: batch i's stream is read by the decoder while batch i+1 is encoded
-        h_stream2 = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
-        streams = (a_stream, h_stream2.numpy())
-        # restart points travel with the code stream (host arrays, one per code-stream buffer)
+
+        def make_ctx():
+            cx = rcb.Context(local_rank, stream=torch.cuda.Stream(dev))
+            return cx, (cx.model_from_counts(counts) if adaptive else cx.model_from_tables(c_, cum_, total_))
+
+        encs = [(ctx, model)] + [make_ctx() for _ in range(depth - 1)]
+        decs = [make_ctx() for _ in range(depth)]
+        n_buf = 2 * depth  # code-stream buffers: free again when their step has been decoded
         rs_e2e = a.restart if d_restart is not None else 0
         rs_words = d_restart.numel() if d_restart is not None else 0
-        h_rs = [torch.zeros(max(1, rs_words), dtype=torch.int64, pin_memory=True).numpy().view(np.uint64) for _ in range(2)]
+        h_streams = [torch.empty(cap, dtype=torch.uint8, pin_memory=True) for _ in range(n_buf)]
+        h_rs = [torch.zeros(max(1, rs_words), dtype=torch.int64, pin_memory=True) for _ in range(n_buf)]
+        h_backs = [torch.empty(n_syms, dtype=d_syms.dtype, pin_memory=True) for _ in range(depth)]
+        streams = [t.numpy() for t in h_streams]
+        rs_np = [t.numpy().view(np.uint64) for t in h_rs]
+        backs = [t.numpy().view(np.uint16) if sym_bytes == 2 else t.numpy() for t in h_backs]
         result = {}
 
-        def enc_host(c_, m_, out_np, slot):
-            if rs_e2e:
-                buf, offs, nb, rs_np = c_.encode_host(a_syms, chunk, m_, out_np=out_np, restart_syms=rs_e2e,
-                                                      restart_np=h_rs[slot])
-                return buf, offs, nb, rs_np
-            buf, offs, nb = c_.encode_host(a_syms, chunk, m_, out_np=out_np)
-            return buf, offs, nb, None
+        def enc_host(cx, m_, slot):
+            r = cx.encode_host(a_syms, chunk, m_, out_np=streams[slot], restart_syms=rs_e2e,
+                               restart_np=rs_np[slot] if rs_e2e else None)
+            return r[1], r[2]  # offsets, bytes
 
-        def dec_host(c_, m_, buf, offs, nb, rs_np):
-            c_.decode_host(buf[:nb], offs, n_syms, chunk, m_, sym_bytes=sym_bytes, out_np=a_back,
-                           restart_syms=rs_e2e, restart_np=rs_np)
+        def dec_host(cx, m_, slot, offs, nb, out_np):
+            cx.decode_host(streams[slot][:nb], offs, n_syms, chunk, m_, sym_bytes=sym_bytes, out_np=out_np,
+                           restart_syms=rs_e2e, restart_np=rs_np[slot] if rs_e2e else None)
 
         def run_steps(k_steps):
-            q = queue.Queue()
-            free = th_.Semaphore(2)  # a code-stream buffer is free again when its batch has been decoded
+            q, free = queue.Queue(), queue.Queue()
+            for b_ in range(n_buf):
+                free.put(b_)
+            nxt, lock = [0], th_.Lock()
 
-            def decoder():
+            def decoder(j):
+                cx, m_ = decs[j]
                 with torch.cuda.device(dev):
                     while True:
                         item = q.get()
                         if item is None:
                             return
-                        buf, offs, nb, rs_np = item
-                        dec_host(ctx2, model2, buf, offs, nb, rs_np)
+                        slot, offs, nb = item
+                        dec_host(cx, m_, slot, offs, nb, backs[j])
                         result["nb"], result["offs"] = nb, offs
-                        free.release()
+                        free.put(slot)
 
-            t = th_.Thread(target=decoder)
-            t.start()
-            for i in range(k_steps):
-                free.acquire()
-                q.put(enc_host(ctx, model, streams[i & 1], i & 1))
-            q.put(None)
-            t.join()
+            def encoder(j):
+                cx, m_ = encs[j]
+                with torch.cuda.device(dev):
+                    while True:
+                        with lock:
+                            i = nxt[0]
+                            nxt[0] += 1
+                        if i >= k_steps:
+                            return
+                        slot = free.get()
+                        offs, nb = enc_host(cx, m_, slot)
+                        q.put((slot, offs, nb))
 
-        run_steps(2)  # warm-up: sizes the device scratch of both contexts
+            dts = [th_.Thread(target=decoder, args=(j,)) for j in range(depth)]
+            ets = [th_.Thread(target=encoder, args=(j,)) for j in range(depth)]
+            for t in dts + ets:
+                t.start()
+            for t in ets:
+                t.join()
+            for _ in dts:
+                q.put(None)
+            for t in dts:
+                t.join()
+
+        run_steps(n_buf)  # warm-up: sizes the device scratch of every context
         barrier()
         t0 = time.perf_counter()
         run_steps(a.e2e_steps)
@@ -597,11 +619,12 @@ def run_ours(a):
         dt = max_over_ranks(time.perf_counter() - t0)
         barrier()
         nb, offs = result["nb"], result["offs"]
-        assert np.array_equal(a_back, a_syms)
+        for b_ in backs:
+            assert np.array_equal(b_, a_syms)
         # the same two calls back to back on one context (no overlap between steps), for reference
         t1 = time.perf_counter()
-        _, offs1, nb1, rs1 = enc_host(ctx, model, a_stream, 0)
-        dec_host(ctx, model, a_stream, offs1, nb1, rs1)
+        offs1, nb1 = enc_host(ctx, model, 0)
+        dec_host(ctx, model, 0, offs1, nb1, backs[0])
         dt_serial = max_over_ranks(time.perf_counter() - t1)
         barrier()
         off_bytes = (n_chunks + 1) * 8 + rs_words * 8  # offsets + restart points
@@ -617,17 +640,19 @@ def run_ours(a):
                "bytes_are": "aggregate over all ranks, like `value`",
                "steps": a.e2e_steps, "ms_per_step": dt / a.e2e_steps * 1e3,
                "serial_ms_per_step": dt_serial * 1e3, "serial_value": world * n / dt_serial / 1e9,
-               "pipelining": "encode of step i+1 overlaps decode of step i (two contexts, two host threads); "
-                             "serial_* = the two calls back to back on one context",
+               "pipelining": f"{depth} encode and {depth} decode calls in flight ({2 * depth} contexts, one host thread "
+                             "each): later steps are encoded while earlier ones are decoded; serial_* = the two calls "
+                             "back to back on one context",
                "bus": bus, "bus_gbs": moved * a.e2e_steps / dt / 1e9,
                "bus_frac": moved * a.e2e_steps / dt / 1e9 / bus["duplex_gbs"],
                "api": ("rcb_encode_host_restart + rcb_decode_host_restart" if rs_e2e else
                        "rcb_encode_host + rcb_decode_host") + " (C ABI, pinned host buffers)"}
         if old_affinity:
             os.sched_setaffinity(0, old_affinity)
-        model2.close()
-        ctx2.close()
-        del h_syms, h_stream, h_back, h_stream2, h_rs
+        for cx, m_ in encs[1:] + decs:
+            m_.close()
+            cx.close()
+        del h_syms, h_streams, h_backs, h_rs, streams, rs_np, backs
 
     # ---- parity on EVERY rank at every N: a deterministic >= 1 % subset of this rank's chunks (every 64th,
     # starting at 5) re-encoded by the oracle under this rank's table and compared byte for byte

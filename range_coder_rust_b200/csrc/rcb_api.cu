@@ -29,6 +29,7 @@ static_assert((int)RCB_MODEL_REGULAR == (int)MODEL_REGULAR, "model flags");
 #define MAX_K_SHARED 4096u  // table + LUT must fit 227 KiB of shared memory
 #define MAX_K 65536u
 #define MAX_SLICES 16       // slices of one host batch in flight (rcb_encode_host / rcb_decode_host)
+#define DEC_TP_THREADS 640  // lanes per block of the throughput flavour of the fused decoder (rcb_decode.cuh)
 
 struct rcb_ctx {
     int device = 0;
@@ -300,14 +301,14 @@ extern "C" int rcb_ctx_get_timings(rcb_ctx* c, float* ms, int n) {
 // Lanes per block: the coder kernels keep one block per SM busy (the decoder's tables fill shared memory),
 // so the lanes are spread evenly over as few full waves of SM-count blocks as 512-thread blocks allow --
 // 16384 lanes: 128 threads, one wave; 65536 lanes: 448 threads, one wave (not 256 blocks of 256 = 1.7 waves).
-static int pick_threads(const rcb_ctx* c, int user, uint64_t n_chunks) {
+static int pick_threads(const rcb_ctx* c, int user, uint64_t n_chunks, uint64_t max_threads = 512) {
     if (user) return user;
     const uint64_t sms = (uint64_t)(c->sm_count > 0 ? c->sm_count : 148);
-    const uint64_t waves = (n_chunks + sms * 512 - 1) / (sms * 512);
+    const uint64_t waves = (n_chunks + sms * max_threads - 1) / (sms * max_threads);
     const uint64_t per_block = (n_chunks + waves * sms - 1) / (waves ? waves * sms : 1);
     uint64_t t = (per_block + 31) / 32 * 32;
     if (t < 128) t = 128;
-    if (t > 512) t = 512;
+    if (t > max_threads) t = max_threads;
     return (int)t;
 }
 
@@ -428,23 +429,33 @@ static int launch_hist(rcb_ctx* c, const void* d_syms, uint64_t n, uint32_t K, u
     const int threads = K <= 4096 ? 256 : 64;  // private copy of the K bins per warp
     const size_t smem = (size_t)(threads / 32) * K * sizeof(uint32_t);
     if (chunk_syms == 0 && sizeof(SYM) == 1 && K <= 256) {
-        // byte symbols: replicated bins (rcb_kernels.cuh), 3 blocks of 8 warps per SM
+        // byte symbols: replicated bins (rcb_kernels.cuh), 64 KiB of bins per block, 3 blocks per SM
         CK(c, cudaMemsetAsync(d_counts, 0, (size_t)K * sizeof(unsigned long long), c->stream));
-        const size_t smem8 = (size_t)(threads / 32) * K * HIST_REP * sizeof(uint32_t);
+        static int rep_env = -1;
+        if (rep_env < 0) {
+            const char* e = getenv("RCB_HIST_REP");
+            rep_env = e ? atoi(e) : 0;
+        }
+        const uint32_t rep = rep_env == 8 || rep_env == 16 || rep_env == 32 ? (uint32_t)rep_env : 16u;
+        const int thr8 = rep == 8 ? 256 : (rep == 16 ? 128 : 64);  // 8 / 4 / 2 warps share the 64 KiB
+        const size_t smem8 = (size_t)(thr8 / 32) * K * rep * sizeof(uint32_t);
         const uint64_t nvec = n / 16;
-        const uint64_t want = (nvec + threads * 8 - 1) / (threads * 8);
+        const uint64_t want = (nvec + thr8 * 8 - 1) / (thr8 * 8);
         const uint64_t maxb = (uint64_t)c->sm_count * 3;
         const int blocks = (int)(want < 1 ? 1 : (want > maxb ? maxb : want));
+        auto go = [&](auto kern) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8);
+            kern<<<blocks, thr8, smem8, c->stream>>>((const uint8_t*)d_syms, n, K, (unsigned long long*)d_counts,
+                                                     c->d_words + 2);
+        };
         if (K == 256) {
-            auto kern = hist_global_u8_kernel<true>;
-            CK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-            kern<<<blocks, threads, smem8, c->stream>>>((const uint8_t*)d_syms, n, K, (unsigned long long*)d_counts,
-                                                        c->d_words + 2);
+            if (rep == 8) go(hist_global_u8_kernel<true, 8, 2>);
+            else if (rep == 16) go(hist_global_u8_kernel<true, 16, 4>);
+            else go(hist_global_u8_kernel<true, 32, 8>);
         } else {
-            auto kern = hist_global_u8_kernel<false>;
-            CK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-            kern<<<blocks, threads, smem8, c->stream>>>((const uint8_t*)d_syms, n, K, (unsigned long long*)d_counts,
-                                                        c->d_words + 2);
+            if (rep == 8) go(hist_global_u8_kernel<false, 8, 2>);
+            else if (rep == 16) go(hist_global_u8_kernel<false, 16, 4>);
+            else go(hist_global_u8_kernel<false, 32, 8>);
         }
         CK_LAUNCH(c);
     } else if (chunk_syms == 0) {
@@ -986,6 +997,8 @@ static DecPlan plan_decode(const rcb_ctx* c, const rcb_model* m, uint64_t n_chun
             if (fat_ok) {
                 p.kind = 0;
                 p.fmode = p.pow2 ? (shift >= 24 ? FM_BIG : FM_POW2) : FM_GEN;
+                // the throughput flavour may run up to DEC_TP_THREADS lanes per block (20 warps per SM fit its registers)
+                if (p.tp) p.threads = pick_threads(c, c->dec_threads, n_chunks * parts, DEC_TP_THREADS);
                 // general totals >= 2^25: one table-wide reciprocal; smaller ones: per-candidate constants
                 p.m2 = p.fmode == FM_GEN && recip2_ok((uint32_t)total) && !getenv("RCB_NO_M2");
                 // FUSED kernel: candidates (16 bytes) + reciprocals of their frequencies (8 bytes) per bucket

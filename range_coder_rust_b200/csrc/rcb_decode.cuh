@@ -324,7 +324,7 @@ __device__ __noinline__ DecLaneState dec_exact(DecLaneState s, const uint2* tab,
 // dependency chain -- so the bucket estimate takes its one reciprocal AFTER the symbol is known (no second
 // table: -6 wavefronts per symbol) and output words leave 16 bytes at a time (-24 wavefronts per word).
 template <typename SYM, bool SHARED, bool POW2, bool CHECKED, int FMODE, bool TP = false>
-__global__ void __launch_bounds__(512, 1) decode_kernel(DecodeArgs a) {
+__global__ void __launch_bounds__(TP ? 640 : 512, 1) decode_kernel(DecodeArgs a) {
     constexpr bool FUSED = FMODE >= 0;
     constexpr bool WIN = FUSED;  // mirrored ring
     static_assert(!TP || FUSED, "TP belongs to the fused loops");

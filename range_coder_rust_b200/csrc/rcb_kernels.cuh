@@ -97,20 +97,24 @@ __global__ void __launch_bounds__(256) hist_global_kernel(const SYM* __restrict_
     if (oob) atomicOr(bad, 1u);
 }
 
-// Byte symbols (K <= 256): each warp keeps HIST_REP interleaved copies of its bins
-// (word = bin * HIST_REP + (lane % HIST_REP)), so the lanes that hit the same hot bin in one
-// instruction -- 6 of 32 for the top symbol of Zipf(1.1) -- spread over HIST_REP words and banks
-// instead of serialising on one shared-memory atomic.  Two 16-byte loads in flight per thread.
-constexpr uint32_t HIST_REP = 8;
-template <bool FULL>  // FULL: K == 256, no range check needed for a byte
+// Byte symbols (K <= 256): each warp keeps REP interleaved copies of its bins
+// (word = bin * REP + (lane % REP)), so the lanes that hit the same hot bin in one
+// instruction -- 6 of 32 for the top symbol of Zipf(1.1) -- spread over REP words and banks
+// instead of serialising on one shared-memory atomic.  The kernel is bound by the wavefronts of
+// those atomics: with REP copies, 32 / REP lanes share a bank group, and two of them collide
+// whenever their bins agree modulo 32 / REP (REP = 8: ~2.1 wavefronts per instruction, 16: ~1.5,
+// 32: one -- every lane owns a bank).  Fewer warps fit as REP grows (REP * K * 4 bytes per warp), so
+// NLOAD 16-byte loads per thread are in flight to keep HBM busy.
+constexpr uint32_t HIST_REP = 8;  // hist_chunks / default geometry
+template <bool FULL, uint32_t REP, int NLOAD>  // FULL: K == 256, no range check needed for a byte
 __global__ void __launch_bounds__(256) hist_global_u8_kernel(const uint8_t* __restrict__ syms, uint64_t n,
                                                              uint32_t K, unsigned long long* counts,
                                                              uint32_t* bad) {
-    extern __shared__ uint32_t s_hist[];  // [warps][K][HIST_REP]
+    extern __shared__ uint32_t s_hist[];  // [warps][K][REP]
     const uint32_t warps = blockDim.x >> 5, warp = threadIdx.x >> 5;
-    for (uint32_t i = threadIdx.x; i < warps * K * HIST_REP; i += blockDim.x) s_hist[i] = 0;
+    for (uint32_t i = threadIdx.x; i < warps * K * REP; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
-    uint32_t* h = s_hist + warp * K * HIST_REP + (threadIdx.x & (HIST_REP - 1));
+    uint32_t* h = s_hist + warp * K * REP + (threadIdx.x & (REP - 1));
     const uint64_t nvec = n / 16;
     const uint4* v = reinterpret_cast<const uint4*>(syms);
     uint32_t oob = 0;
@@ -118,24 +122,24 @@ __global__ void __launch_bounds__(256) hist_global_u8_kernel(const uint8_t* __re
 #pragma unroll
         for (int b = 0; b < 4; b++) {
             const uint32_t s = (w >> (8 * b)) & 0xFFu;
-            if (FULL || s < K) atomicAdd(&h[s * HIST_REP], 1u); else oob = 1;
+            if (FULL || s < K) atomicAdd(&h[s * REP], 1u); else oob = 1;
         }
     };
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + stride < nvec; i += 2 * stride) {
-        const uint4 q0 = ldg_stream_v4(v + i);
-        const uint4 q1 = ldg_stream_v4(v + i + stride);
-        count_word(q0.x);
-        count_word(q0.y);
-        count_word(q0.z);
-        count_word(q0.w);
-        count_word(q1.x);
-        count_word(q1.y);
-        count_word(q1.z);
-        count_word(q1.w);
+    for (; i + (NLOAD - 1) * stride < nvec; i += NLOAD * stride) {
+        uint4 q[NLOAD];
+#pragma unroll
+        for (int k = 0; k < NLOAD; k++) q[k] = ldg_stream_v4(v + i + k * stride);
+#pragma unroll
+        for (int k = 0; k < NLOAD; k++) {
+            count_word(q[k].x);
+            count_word(q[k].y);
+            count_word(q[k].z);
+            count_word(q[k].w);
+        }
     }
-    if (i < nvec) {
+    for (; i < nvec; i += stride) {
         const uint4 q0 = ldg_stream_v4(v + i);
         count_word(q0.x);
         count_word(q0.y);
@@ -145,7 +149,7 @@ __global__ void __launch_bounds__(256) hist_global_u8_kernel(const uint8_t* __re
     if (blockIdx.x == 0) {  // tail symbols (n not a multiple of the vector width)
         for (uint64_t j = nvec * 16 + threadIdx.x; j < n; j += blockDim.x) {
             const uint32_t s = syms[j];
-            if (FULL || s < K) atomicAdd(&h[s * HIST_REP], 1u); else oob = 1;
+            if (FULL || s < K) atomicAdd(&h[s * REP], 1u); else oob = 1;
         }
     }
     __syncthreads();
@@ -153,7 +157,7 @@ __global__ void __launch_bounds__(256) hist_global_u8_kernel(const uint8_t* __re
         unsigned long long t = 0;
         for (uint32_t w = 0; w < warps; w++)
 #pragma unroll
-            for (uint32_t r = 0; r < HIST_REP; r++) t += s_hist[(w * K + b) * HIST_REP + r];
+            for (uint32_t r = 0; r < REP; r++) t += s_hist[(w * K + b) * REP + r];
         if (t) atomicAdd(&counts[b], t);
     }
     if (oob) atomicOr(bad, 1u);
