@@ -246,8 +246,12 @@ struct Encoded {
     uint64_t restart_syms = 0;
     std::vector<rcb_restart_point> restart;
 };
-// restart points every quarter of a chunk when that is a whole number of 64-symbol units (0: none)
-inline uint64_t default_restart_syms(uint64_t chunk_syms) { return chunk_syms % 256 == 0 ? chunk_syms / 4 : 0; }
+// restart points: 16 parts per chunk for chunks of >= 32 Ki symbols, else 4, when the part is a whole number of
+// 64-symbol units (0: none)
+inline uint64_t default_restart_syms(uint64_t chunk_syms) {
+    if (chunk_syms >= 32768 && chunk_syms % 1024 == 0) return chunk_syms / 16;
+    return chunk_syms % 256 == 0 ? chunk_syms / 4 : 0;
+}
 template <class Sym>
 Encoded encode_chunks(Context& ctx, const ModelSnapshot& snap, const std::vector<Sym>& syms, uint64_t chunk_syms,
                       uint64_t restart_syms = ~0ull) {

@@ -26,7 +26,7 @@ def main(argv=None):
     c.add_argument("--adaptive", action="store_true", help="one frequency table per chunk")
     c.add_argument("--restart", type=int, default=-1,
                    help="restart points every N symbols of a chunk (several decoder lanes per chunk; multiple of 64); "
-                        "0 = none (version-1 frame), default: a quarter of the chunk when that is a multiple of 64")
+                        "0 = none (version-1 frame), default: chunk / 16 for chunks of >= 32 Ki symbols, else chunk / 4")
     c.add_argument("--device", type=int, default=0)
     d = sub.add_parser("decompress")
     d.add_argument("src")
@@ -45,7 +45,8 @@ def main(argv=None):
         dev = torch.from_numpy(syms).to(ctx.device)
         counts = ctx.histogram(dev, 256, chunk_syms=a.chunk if a.adaptive else 0)
         model = ctx.model_from_counts(counts)
-        restart = a.restart if a.restart >= 0 else (a.chunk // 4 if a.chunk % 256 == 0 else 0)
+        restart = a.restart if a.restart >= 0 else (a.chunk // 16 if a.chunk >= 32768 and a.chunk % 1024 == 0 else
+                                                    (a.chunk // 4 if a.chunk % 256 == 0 else 0))
         frame = ctx.frame_encode(syms, a.chunk, model, restart_syms=restart)
         frame.tofile(a.dst)
         print(f"{a.src}: {syms.size} -> {frame.size} bytes ({frame.size / syms.size:.4f}), "

@@ -1038,7 +1038,9 @@ static DecPlan plan_decode(const rcb_ctx* c, const rcb_model* m, uint64_t n_chun
     if (!p.checked && regular && (uint64_t)cmax * parts >= 32) {
         uint32_t CB = cmax * parts < 512u ? cmax : 512u / parts;  // chunks per block
         const uint64_t sms = (uint64_t)(c->sm_count > 0 ? c->sm_count : 148);
-        const uint64_t even = (n_chunks + sms - 1) / sms;  // one wave over all SMs when it fits
+        // whole waves of SM-count blocks: the chunks are spread evenly over as few waves as the cap allows
+        const uint64_t waves = (n_chunks + sms * CB - 1) / (sms * CB);
+        const uint64_t even = (n_chunks + waves * sms - 1) / (waves ? waves * sms : 1);
         if (even <= CB) CB = (uint32_t)(even ? even : 1);
         if (c->dec_threads && (uint32_t)c->dec_threads < CB * parts) CB = (uint32_t)c->dec_threads / parts;
         if (CB == 0) CB = 1;

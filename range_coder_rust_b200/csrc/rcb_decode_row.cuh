@@ -107,18 +107,30 @@ __global__ void __launch_bounds__(512, 1) decode_row_kernel(DecodeRowArgs a) {
                 }
                 s_luts[b] = (LUT_T)lft;
             }
-        } else if (threadIdx.x < lanes) {
-            // each lane walks its own row and its buckets together (both monotone).  (Dropping the
-            // zero-frequency symbols from the row was measured: the position -> symbol map costs more
-            // LUT buckets than the compaction saves in scans.)
-            const uint32_t* row = s_rows + threadIdx.x * row_words;
-            LUT_T* lut = s_luts + (size_t)threadIdx.x * nb;
+        } else if (threadIdx.x < lanes * parts) {
+            // the `parts` lanes of a chunk build its LUT together: each walks its share of the buckets and the
+            // row beside them (both monotone) from the symbol a binary search finds for its first bucket.
+            // (Dropping the zero-frequency symbols from the row was measured: the position -> symbol map costs
+            // more LUT buckets than the compaction saves in scans.)
+            const uint32_t my = threadIdx.x / parts, sub = threadIdx.x - my * parts;
+            const uint32_t* row = s_rows + my * row_words;
+            LUT_T* lut = s_luts + (size_t)my * nb;
             const uint64_t total = row[K];
             const uint64_t margin = total / nb / 8 + 1;
             const uint64_t step_q = total / nb, step_r = total % nb;  // floor(b*total/nb), incrementally
-            uint64_t q = 0, r = 0;
+            const uint32_t b_lo = (uint32_t)((uint64_t)nb * sub / parts), b_hi = (uint32_t)((uint64_t)nb * (sub + 1) / parts);
+            uint64_t q = (uint64_t)b_lo * total / nb, r = (uint64_t)b_lo * total % nb;
             uint32_t s = 0;
-            for (uint32_t b = 0; b < nb; b++) {
+            if (b_lo) {  // symbol whose interval contains the first bucket's point
+                const uint64_t v0 = q > margin ? q - margin : 0;
+                uint32_t lft = 0, rgt = K - 1;
+                while (lft < rgt) {
+                    const uint32_t mid = (lft + rgt) >> 1;
+                    if ((uint64_t)row[mid + 1] <= v0) lft = mid + 1; else rgt = mid;
+                }
+                s = lft;
+            }
+            for (uint32_t b = b_lo; b < b_hi; b++) {
                 const uint64_t v0 = q > margin ? q - margin : 0;
                 while (s < K - 1 && (uint64_t)row[s + 1] <= v0) s++;
                 lut[b] = (LUT_T)s;

@@ -46,9 +46,12 @@ pub struct Encoded {
     pub restart: Vec<ffi::RcbRestartPoint>,
 }
 
-/// Restart points every quarter of a chunk when that is a whole number of 64-symbol units (0: none).
+/// Restart points: 16 parts per chunk for chunks of >= 32 Ki symbols, else 4, when the part is a whole number
+/// of 64-symbol units (0: none).
 pub fn default_restart_syms(chunk_syms: u64) -> u64 {
-    if chunk_syms % 256 == 0 {
+    if chunk_syms >= 32768 && chunk_syms % 1024 == 0 {
+        chunk_syms / 16
+    } else if chunk_syms % 256 == 0 {
         chunk_syms / 4
     } else {
         0

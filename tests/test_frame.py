@@ -208,4 +208,4 @@ def test_file_front_end_round_trip(tmp_path, oracle, adaptive):
     assert np.array_equal(frame_ref.decode_frame(np.fromfile(frm, dtype=np.uint8)), data)
     out = subprocess.run(cmd + ["info", str(frm)], check=True, cwd=root, capture_output=True, text=True).stdout
     assert "300007 symbols" in out and ("per-chunk tables" in out) == adaptive
-    assert "RCB2 v2" in out and "restart points every 8192 symbols" in out  # the front end's default: chunk / 4
+    assert "RCB2 v2" in out and "restart points every 2048 symbols" in out  # the front end's default: chunk / 16
