@@ -495,13 +495,16 @@ def run_ours(a):
     alg_bytes = n + nbytes
     achieved = alg_bytes / (kavg[dom] * 1e-3) / 1e9
     tag = "static" if not adaptive and K <= 256 else ("adaptive" if adaptive else "k4096")
+    if d_restart is not None:
+        tag += "_restart"  # the tracked captures of the restart-point build (profiles/traffic.json, issue.json)
 
     def tracked(name):
         path = os.path.join(ROOT, "profiles", name)
         return json.load(open(path)) if os.path.exists(path) else {}
 
     tr = tracked("traffic.json").get(tag, {})
-    traffic = tr.get(dom) if n == 1 << 30 else None  # the capture is of the 1 GiB batch
+    # the captures are of the 1 GiB batch (restart points: 4 lanes per chunk)
+    traffic = tr.get(dom) if n == 1 << 30 else None
     issue = None
     cap_issue = tracked("issue.json").get(tag, {}).get(dom)
     if cap_issue:
