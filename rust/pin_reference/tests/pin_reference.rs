@@ -4,7 +4,8 @@
 //! (`tests/golden/make_golden.py`); the CPU oracle (`oracle/rc_oracle.c`) and the CUDA kernels are
 //! tested against the same file.  This test closes the loop: the reference's own `Encoder::encode` /
 //! `Encoder::finish` must produce exactly those bytes, and its `Decoder::decode` must return the
-//! symbols.  The frequency table below is a plain `PModel` over the vector's `c` / `cum` / `total`
+//! symbols; where a vector carries restart records (`restart`), the Encoder's `lower_bound`, `range` and
+//! code length in front of those symbols must be the recorded ones.  The frequency table below is a plain `PModel` over the vector's `c` / `cum` / `total`
 //! with the lookup rule of the reference's example model (examples/sample_impl.rs:27-45).
 use range_coder::{Decoder, Encoder, PModel};
 use serde_json::Value;
@@ -97,8 +98,27 @@ fn golden_vectors_match_the_reference_crate() {
         // the caller's loop of examples/sample_impl.rs:92-98
         let mut encoder = Encoder::new();
         let mut produced = 0u64;
-        for &s in &symbols {
+        // restart points (include/rcb200.h: rcb_restart_point): the Encoder's own state in front of every
+        // restart_syms-th symbol -- RangeCoder::lower_bound() / range() (src/range_coder.rs:28-35) through the
+        // public field Encoder::range_coder (src/encoder.rs:8), and peek_code().len() (src/encoder.rs:15-17)
+        let restart = v.get("restart");
+        let rs = restart.map(|r| r["restart_syms"].as_u64().unwrap() as usize).unwrap_or(0);
+        let mut seen = 0usize;
+        for (j, &s) in symbols.iter().enumerate() {
+            if rs != 0 && j != 0 && j % rs == 0 {
+                let rec = restart.unwrap()["records"][seen].as_array().unwrap();
+                let lower = u64::from_str_radix(rec[0].as_str().unwrap(), 16).unwrap();
+                let range = u64::from_str_radix(rec[1].as_str().unwrap(), 16).unwrap();
+                assert_eq!(encoder.range_coder.lower_bound(), lower, "{}: restart record {} lower_bound", name, seen);
+                assert_eq!(encoder.range_coder.range(), range, "{}: restart record {} range", name, seen);
+                assert_eq!(encoder.peek_code().len() as u64, rec[2].as_u64().unwrap(), "{}: restart record {} bytes", name, seen);
+                assert_eq!(produced, rec[2].as_u64().unwrap(), "{}: encode() return values add up", name);
+                seen += 1;
+            }
             produced += encoder.encode(&table, s) as u64;
+        }
+        if let Some(r) = restart {
+            assert_eq!(seen, r["records"].as_array().unwrap().len(), "{}: every restart record checked", name);
         }
         let code: VecDeque<u8> = encoder.finish();
         let code: Vec<u8> = code.into_iter().collect();

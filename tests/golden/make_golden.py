@@ -43,6 +43,21 @@ def vec(name, symbols, counts, note=""):
         "code_len": len(code),
         "code_sha256": hashlib.sha256(code).hexdigest(),
     }
+    if len(symbols) >= 128:
+        # restart points (include/rcb200.h): the Encoder in front of symbol j = restart_syms, 2*restart_syms, ...
+        # -- RangeCoder::lower_bound(), ::range() (src/range_coder.rs:28-35) and peek_code().len()
+        # (src/encoder.rs:15-17), straight from the transliterated Encoder; hex because they are u64
+        rs = 64 * -(-len(symbols) // (64 * 64))
+        enc = rc_pyref.Encoder()
+        recs = []
+        for j, sym in enumerate(symbols):
+            if j and j % rs == 0:
+                recs.append(["%016x" % enc.range_coder.lower_bound, "%016x" % enc.range_coder.range,
+                             len(enc.peek_code())])
+            enc.encode(t, int(sym))
+        assert bytes(enc.finish()) == bytes(code)
+        v["restart"] = {"restart_syms": rs, "records": recs,
+                        "note": "[lower_bound, range, code bytes so far] in front of symbol (r+1)*restart_syms"}
     if len(symbols) <= 64:
         v["symbols"] = [int(s) for s in symbols]
     elif len(set(symbols)) == 1:

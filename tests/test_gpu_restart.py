@@ -8,7 +8,7 @@ family, ragged last chunks included; damaged records must be reported, not silen
 import numpy as np
 import pytest
 
-from test_gpu_parity import S_CYCLE, assert_streams_equal, dev_to_np, to_dev
+from test_gpu_parity import S_CYCLE, VECTORS, assert_streams_equal, dev_to_np, to_dev, vector_inputs
 
 pytestmark = pytest.mark.gpu
 
@@ -82,6 +82,28 @@ def test_static_table_restart_points(ctx, oracle, n, chunk, rs):
     model = ctx.model_from_tables(c, cum, total)
     n_chunks = (n + chunk - 1) // chunk
     round_trip(ctx, oracle, syms, chunk, rs, model, (c, cum, total), picks=sorted({0, n_chunks // 2, n_chunks - 1}))
+
+
+@pytest.mark.parametrize("v", [v for v in VECTORS if "restart" in v], ids=[v["name"] for v in VECTORS if "restart" in v])
+def test_golden_restart_records_on_gpu(ctx, v):
+    """tests/golden/vectors.json: the records of one chunk = the whole vector against the committed fixture
+    (which rust/pin_reference checks against the unmodified crate), then both decoders."""
+    syms, c, cum, total = vector_inputs(v)
+    rs = v["restart"]["restart_syms"]
+    recs = v["restart"]["records"]
+    n = syms.size
+    model = ctx.model_from_tables(c, cum, total)
+    restart = ctx.restart_points(1, n, rs)
+    stream, offsets, nbytes = ctx.encode_chunks(to_dev(ctx, syms), n, model, restart_syms=rs, restart=restart)
+    assert nbytes == v["code_len"]
+    lo, rg, pos = records(restart, 1, len(recs))
+    for r, (ref_lo, ref_rg, ref_n) in enumerate(recs):
+        assert int(lo[0, r]) == int(ref_lo, 16), (v["name"], r)
+        assert int(rg[0, r]) == int(ref_rg, 16) // total * total, (v["name"], r)  # stored as a multiple of total_freq
+        assert int(pos[0, r]) == ref_n, (v["name"], r)
+    for kw in ({"restart_syms": rs, "restart": restart}, {}):
+        out = ctx.decode_chunks(stream, offsets, n, n, model, sym_bytes=syms.dtype.itemsize, **kw)
+        assert np.array_equal(dev_to_np(out, dtype=syms.dtype), syms)
 
 
 @pytest.mark.parametrize("kind", ["gen_2e30", "gen_prime", "pow2_2e20", "gen_u16", "gen_full_c", "irregular",
