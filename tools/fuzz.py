@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Randomised parity run on the GPU: random alphabets, tables (dense, sparse, power-of-two and odd
-totals), stream lengths and chunk sizes (odd, tiny, ragged), shared and per-chunk models -- every
-chunk's bytes against the oracle, and the decoded symbols against the input.  Not part of the test
+totals), stream lengths and chunk sizes (odd, tiny, ragged), shared and per-chunk models, with and without
+restart points -- every chunk's bytes (and restart records) against the oracle, and the decoded symbols against
+the input.  Not part of the test
 suite (minutes, not seconds); run it after touching a kernel:  python tools/fuzz.py --iters 200"""
 import argparse
 import os
@@ -92,6 +93,44 @@ def main():
         b = back.cpu().numpy()
         b = b.view(np.uint16) if sb == 2 else b
         assert np.array_equal(b, syms), f"decode mismatch: {tag}"
+        # restart points: same bytes, records == the oracle's Encoder state, several decoder lanes per chunk
+        units = chunk // 64
+        if units >= 2 and rng.random() < 0.6:
+            lo_u = -(-units // 64)  # at most 64 parts per chunk
+            rs = 64 * int(rng.integers(lo_u, max(lo_u, units // 2) + 1))
+            per = (chunk + rs - 1) // rs - 1
+            restart = ctx.restart_points(n_chunks, chunk, rs)
+            if restart is not None:
+                s2, o2, nb2 = ctx.encode_chunks(d, chunk, model, restart_syms=rs, restart=restart)
+                assert nb2 == nbytes and torch.equal(o2, offsets) and torch.equal(s2[:nb2], stream[:nbytes]), \
+                    f"restart encode changed the stream: {tag} rs={rs}"
+                rec = restart.cpu().numpy().view(np.uint64).reshape(n_chunks, per, 3)
+                for j in list(pick)[:6]:
+                    c, cum, total, _ = model.tables(j if per_chunk else 0)
+                    part = syms[j * chunk:(j + 1) * chunk]
+                    for r in sorted(set(rng.integers(0, per, size=min(per, 4)).tolist())):
+                        k = (r + 1) * rs
+                        if k >= part.size:
+                            assert not rec[j, r].any(), f"absent record not zero: {tag} rs={rs} chunk {j} rec {r}"
+                            continue
+                        lo, rg, nb_ = oracle.encode_state(part[:k], c, cum, int(total))
+                        assert (int(rec[j, r, 0]), int(rec[j, r, 1]), int(rec[j, r, 2]) & 0xFFFFFFFF) == \
+                            (lo, rg // int(total) * int(total), nb_), f"restart record: {tag} rs={rs} chunk {j} rec {r}"
+                st = torch.full((n_chunks,), 99, dtype=torch.int32, device=ctx.device)
+                back2 = ctx.decode_chunks(s2, o2, n, chunk, model, sym_bytes=sb, status=st, restart_syms=rs, restart=restart)
+                b2 = back2.cpu().numpy()
+                b2 = b2.view(np.uint16) if sb == 2 else b2
+                assert np.array_equal(b2, syms) and not st.any(), f"restart decode mismatch: {tag} rs={rs}"
+                tag += f" restart={rs}"
+                if big or rng.random() < 0.2:  # host entry points with restart points
+                    rs_np = np.zeros(n_chunks * per * 3, dtype=np.uint64)
+                    o, off2, nbh, _ = ctx.encode_host(syms, chunk, model, restart_syms=rs, restart_np=rs_np)
+                    assert nbh == nbytes and o[:nbh].tobytes() == h_stream.tobytes(), tag
+                    assert np.array_equal(rs_np.reshape(n_chunks, per, 3), rec), tag
+                    pad = np.zeros(nbh + 32, dtype=np.uint8)
+                    pad[:nbh] = o[:nbh]
+                    assert np.array_equal(ctx.decode_host(pad, off2, n, chunk, model, sym_bytes=sb, restart_syms=rs,
+                                                          restart_np=rs_np), syms), tag
         if big or rng.random() < 0.3:  # host entry points (pipeline + segments when big enough)
             o, off2, nb2 = ctx.encode_host(syms, chunk, model)
             assert nb2 == nbytes and np.array_equal(off2, h_off) and o[:nb2].tobytes() == h_stream.tobytes(), tag
