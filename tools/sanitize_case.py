@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Small end-to-end pass over every kernel family for compute-sanitizer (memcheck): tiny inputs, all paths --
-shared / per-chunk / general-total / K=4096 models, TMA input, the adaptive-per-symbol table, corrupt offsets,
+shared / per-chunk / general-total / K=4096 models, restart points (intact and damaged), TMA input, the adaptive-per-symbol table, corrupt offsets,
 host-buffer pipeline, container.  `compute-sanitizer --tool memcheck python tools/sanitize_case.py`"""
 import os
 import sys
@@ -11,6 +11,11 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import range_coder_rust_b200 as rcb  # noqa: E402
+
+
+def restart_syms(chunk):
+    """A restart spacing for the chunk (multiple of 64, several parts), 0 when the chunk is too short."""
+    return 64 * max(1, chunk // 64 // 5) if chunk >= 128 else 0
 
 
 def main():
@@ -41,11 +46,32 @@ def main():
                 stream, offsets, nbytes = ctx.encode_chunks(syms, chunk, model)
                 back = ctx.decode_chunks(stream, offsets, n, chunk, model, sym_bytes=sb)
                 assert torch.equal(back, syms), (K, name, tma)
+                rs = restart_syms(chunk)
+                if rs:  # restart points: several decoder lanes per chunk, then damaged records (status only)
+                    n_chunks = (n + chunk - 1) // chunk
+                    rp = ctx.restart_points(n_chunks, chunk, rs)
+                    s2, o2, nb2 = ctx.encode_chunks(syms, chunk, model, restart_syms=rs, restart=rp)
+                    assert nb2 == nbytes and torch.equal(s2[:nb2], stream[:nbytes]), (K, name, tma, "restart stream")
+                    assert torch.equal(ctx.decode_chunks(s2, o2, n, chunk, model, sym_bytes=sb, restart_syms=rs,
+                                                         restart=rp), syms), (K, name, tma, "restart")
+                    bad = rp.clone()
+                    bad[2::3] += 1 << 20  # code_bytes far past the chunk
+                    bad[0::7] ^= 0x5A5A5A5A5A
+                    try:
+                        ctx.decode_chunks(s2, o2, n, chunk, model, sym_bytes=sb, restart_syms=rs, restart=bad)
+                    except rcb.RcbError:
+                        pass
         os.environ.pop("RCB_ENC_TMA", None)
         # per-chunk tables
         pm = ctx.model_from_counts(ctx.histogram(syms, K, chunk_syms=chunk))
         stream, offsets, nbytes = ctx.encode_chunks(syms, chunk, pm)
         assert torch.equal(ctx.decode_chunks(stream, offsets, n, chunk, pm, sym_bytes=sb), syms)
+        rs = restart_syms(chunk)
+        if rs:
+            rp = ctx.restart_points((n + chunk - 1) // chunk, chunk, rs)
+            s2, o2, nb2 = ctx.encode_chunks(syms, chunk, pm, restart_syms=rs, restart=rp)
+            assert nb2 == nbytes and torch.equal(s2[:nb2], stream[:nbytes])
+            assert torch.equal(ctx.decode_chunks(s2, o2, n, chunk, pm, sym_bytes=sb, restart_syms=rs, restart=rp), syms)
         # corrupt offsets: contained, status only
         offs = offsets.clone()
         offs[1] = offs[2]
