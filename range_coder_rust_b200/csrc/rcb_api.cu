@@ -1183,6 +1183,22 @@ static int decode_issue(rcb_ctx* c, const uint8_t* d_stream, const uint64_t* d_o
     if ((chunk_syms * (uint64_t)sym_bytes) % 16 || (seg && (seg->first * (uint64_t)sym_bytes) % 16)) plan.tp = false;
     const uint64_t n_lanes = n_chunks * parts;
     const unsigned blocks = (unsigned)((n_lanes + plan.lanes - 1) / plan.lanes);  // row kernel: lanes % parts == 0
+    {
+        // start-up L2 prefetch per lane: 2 KiB when few lanes are resident, less when they are many, so that one
+        // wave of blocks prefetches at most 32 MiB (a quarter of L2); under 256 bytes the ring pieces' own
+        // 256-byte hints are the prefetch
+        const uint64_t wave = (uint64_t)c->sm_count * plan.lanes;  // lanes resident at one time (>= 1 block per SM)
+        const uint64_t resident = n_lanes < wave ? n_lanes : wave;
+        uint64_t bytes = resident ? ((uint64_t)32 << 20) / resident : 2048;
+        static int pf_env = -2;  // RCB_DEC_PF=<bytes>: override (measurements)
+        if (pf_env == -2) {
+            const char* e = getenv("RCB_DEC_PF");
+            pf_env = e ? atoi(e) : -1;
+        }
+        if (pf_env >= 0) bytes = (uint64_t)pf_env;
+        if (bytes > 2048) bytes = 2048;
+        a.pf_words = (uint32_t)(bytes / 256) * 64;
+    }
     if (plan.kind == 0) {
         if (sym_bytes == 1)
             launch_decode_variant<uint8_t>(c, m, a, plan, blocks);
@@ -1206,6 +1222,7 @@ static int decode_issue(rcb_ctx* c, const uint8_t* d_stream, const uint64_t* d_o
         ra.restart = a.restart;
         ra.restart_syms = a.restart_syms;
         ra.parts = a.parts;
+        ra.pf_words = a.pf_words;
         if (sym_bytes == 1) {
             if (plan.lut16) launch_decode_row<uint8_t, uint16_t>(c, ra, plan, blocks);
             else launch_decode_row<uint8_t, uint8_t>(c, ra, plan, blocks);

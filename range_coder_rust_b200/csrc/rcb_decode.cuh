@@ -60,6 +60,10 @@ struct DecodeArgs {
     const Restart* restart;  // [n_chunks][parts - 1]
     uint64_t restart_syms;
     uint32_t parts;          // 1: one lane per chunk (no restart points)
+    // start-up L2 prefetch per lane, in 32-bit words (multiple of 64 = 256 bytes; 0: none).  The host sizes it so
+    // that the lanes resident at one time prefetch no more than a fraction of L2 (2 KiB per lane for one lane
+    // per chunk; 262144 lanes of a few KB each would push 0.5 GB through a 126 MB L2 and read it twice)
+    uint32_t pf_words;
 };
 
 // Which part of which chunk a lane decodes, and from which state (restart points).
@@ -443,12 +447,13 @@ __global__ void __launch_bounds__(TP ? 640 : 512, 1) decode_kernel(DecodeArgs a)
             const uint64_t o = (uint64_t)pf_next * 4;
             if (offsets_ok && o < readable) {
                 const uint64_t left = readable - o;
-                prefetch_l2_bulk_dec(fill.pbase + o, (uint32_t)(left < PF_WORDS * 4 ? left : PF_WORDS * 4));
+                const uint32_t g = (upto_words - pf_next < PF_WORDS ? upto_words - pf_next : PF_WORDS) * 4;
+                prefetch_l2_bulk_dec(fill.pbase + o, (uint32_t)(left < g ? left : g));
             }
             pf_next += PF_WORDS;
         }
     };
-    prefetch_to(pf_next + 2 * PF_WORDS);
+    prefetch_to(pf_next + a.pf_words);
     fill.resync(rf);  // fill the ring from the read position, wait, load the current word
     DecSink<RingFetch> sink(rf);
 

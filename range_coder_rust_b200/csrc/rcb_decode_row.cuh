@@ -41,6 +41,7 @@ struct DecodeRowArgs {
     const Restart* restart;   // restart points (rcb_decode.cuh: DecodeArgs)
     uint64_t restart_syms;
     uint32_t parts;           // lanes per chunk; lanes_per_block is a multiple of it
+    uint32_t pf_words;        // start-up L2 prefetch per lane (rcb_decode.cuh: DecodeArgs)
 };
 
 // Literal renormalisation loops for a symbol that is already chosen (s.lo / s.rg hold lower' and
@@ -206,12 +207,13 @@ __global__ void __launch_bounds__(512, 1) decode_row_kernel(DecodeRowArgs a) {
             const uint64_t o = (uint64_t)pf_next * 4;
             if (offsets_ok && o < readable) {
                 const uint64_t left = readable - o;
-                prefetch_l2_bulk_dec(fill.pbase + o, (uint32_t)(left < PF_WORDS * 4 ? left : PF_WORDS * 4));
+                const uint32_t g = (upto_words - pf_next < PF_WORDS ? upto_words - pf_next : PF_WORDS) * 4;
+                prefetch_l2_bulk_dec(fill.pbase + o, (uint32_t)(left < g ? left : g));
             }
             pf_next += PF_WORDS;
         }
     };
-    prefetch_to(pf_next + 2 * PF_WORDS);
+    prefetch_to(pf_next + a.pf_words);
     fill.resync(rf);
     DecSink<RingFetch> sink(rf);
 
