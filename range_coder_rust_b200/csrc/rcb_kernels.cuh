@@ -1,6 +1,7 @@
 // rcb_kernels.cuh -- sm_100a kernels of the chunk-parallel range coder.
 //
-//   K1 hist_global_kernel / hist_chunks_kernel   examples/sample_impl.rs:58-60,78-80
+//   K1 hist_global_shared_kernel / hist_chunks_kernel   examples/sample_impl.rs:58-60,78-80
+//      (hist_global_kernel, hist_global_u8_kernel: the per-warp-copy forms, RCB_HIST_SHARED=0)
 //   K2 counts_to_tables_kernel / finalize_models_kernel  examples/sample_impl.rs:61-69
 //   K3 encode_kernel                              src/encoder.rs:24-46, src/range_coder.rs:53-135
 //   K4 scan_lengths_kernel + gather_kernel        (no reference analogue: one VecDeque there)
