@@ -501,16 +501,23 @@ static int launch_hist(rcb_ctx* c, const void* d_syms, uint64_t n, uint32_t K, u
         uint64_t n_chunks = (n + chunk_syms - 1) / chunk_syms;
         if (n_chunks == 0) return RCB_OK;
         if (n_chunks > 0x7FFFFFFFull) return RCB_ERR_UNSUPPORTED;
-        auto kern = hist_chunks_kernel<SYM>;
-        // one copy of the bins per block, REP interleaved words per bin; every chunk zeroes and merges its copy, so
-        // it stays small: 8 KiB for byte alphabets (REP = 8 at K = 256; REP = 32 measured 0.57 ms against 0.52),
-        // 32 KiB above (REP = 2 at K = 4096: 0.35 ms against 1.41 with a 16 KiB copy per warp)
+        // one copy of the bins per block, REP interleaved words per bin (up to 32: a bank per lane).  Every chunk
+        // zeroes and merges its copy, so the copy grows with the chunk: at most a word per 4 symbols, 8 to 32 KiB
+        // (K = 256: REP = 32 for 64 KiB chunks 0.29 ms per GiB, REP = 16 for 16 KiB chunks 0.39 ms; REP = 8 was
+        // 0.36 / 0.43, REP = 32 at 16 KiB 0.43; K = 4096: REP = 2, 0.35 ms)
+        uint64_t cap_words = chunk_syms / 4;
+        cap_words = cap_words < 2048 ? 2048 : (cap_words > 8192 ? 8192 : cap_words);
         uint32_t rep_log2 = 5;
-        while (rep_log2 > 0 && ((size_t)K << rep_log2) > (K <= 256 ? 2048u : 8192u)) rep_log2--;
-        const size_t smem_c = ((size_t)K << rep_log2) * sizeof(uint32_t);
-        CK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-        kern<<<(unsigned)n_chunks, 256, smem_c, c->stream>>>((const SYM*)d_syms, n, chunk_syms, K, rep_log2,
-                                                              (uint32_t*)d_counts, c->d_words + 2);
+        while (rep_log2 > 0 && ((uint64_t)K << rep_log2) > cap_words) rep_log2--;
+        const bool full = sizeof(SYM) == 1 ? K == 256 : K == 65536;
+        const size_t smem_c = ((size_t)(K + (full ? 0 : 1)) << rep_log2) * sizeof(uint32_t);
+        auto go = [&](auto kern) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
+            kern<<<(unsigned)n_chunks, 256, smem_c, c->stream>>>((const SYM*)d_syms, n, chunk_syms, K, rep_log2,
+                                                                  (uint32_t*)d_counts, c->d_words + 2);
+        };
+        if (full) go(hist_chunks_kernel<SYM, true>);
+        else go(hist_chunks_kernel<SYM, false>);
         CK_LAUNCH(c);
     }
     return RCB_OK;

@@ -238,39 +238,36 @@ __global__ void __launch_bounds__(512) hist_global_shared_kernel(const SYM* __re
 // One block per chunk: u32 counts[n_chunks][K].  The block's warps share one copy of the bins with REP interleaved
 // words per bin (word = bin * REP + lane % REP; REP = 8 at K = 256, the shared memory of a copy per warp): a chunk
 // of one dominant symbol (Zipf(5): 96 %) serialises 4 lanes per atomic instead of 32.  The host picks REP.
-template <typename SYM>
+// Branch-free like hist_global_shared_kernel (symbols >= K land in bin K; FULL: every value of SYM is < K): the
+// kernel is bound by instruction issue (15.8 warp instructions per symbol with a range-check branch per symbol).
+template <typename SYM, bool FULL>
 __global__ void __launch_bounds__(256) hist_chunks_kernel(const SYM* __restrict__ syms, uint64_t n,
                                                           uint64_t chunk_syms, uint32_t K, uint32_t rep_log2,
                                                           uint32_t* counts, uint32_t* bad) {
-    extern __shared__ uint32_t s_hist[];  // [K][REP]
+    extern __shared__ uint32_t s_hist[];  // [K (+ 1)][REP]
     const uint32_t REP = 1u << rep_log2;
+    const uint32_t nbins = FULL ? K : K + 1;
     const uint64_t chunk = blockIdx.x;
     const uint64_t first = chunk * chunk_syms;
     const uint64_t cnt = (n - first < chunk_syms) ? (n - first) : chunk_syms;
-    for (uint32_t i = threadIdx.x; i < (K << rep_log2); i += blockDim.x) s_hist[i] = 0;
+    for (uint32_t i = threadIdx.x; i < (nbins << rep_log2); i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
     uint32_t* h = s_hist + (threadIdx.x & (REP - 1));
     const SYM* p = syms + first;
-    uint32_t oob = 0;
     constexpr uint32_t PER = 16 / sizeof(SYM);
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(p) & 15u) == 0);
     uint64_t done = 0;
+    auto count_sym = [&](uint32_t s) { atomicAdd(&h[(FULL ? s : min(s, K)) << rep_log2], 1u); };
     if (vec_ok) {
         const uint64_t nvec = cnt / PER;
         const uint4* v = reinterpret_cast<const uint4*>(p);
         auto count_word = [&](uint32_t w) {
             if (sizeof(SYM) == 1) {
 #pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    const uint32_t s = (w >> (8 * b)) & 0xFFu;
-                    if (s < K) atomicAdd(&h[s << rep_log2], 1u); else oob = 1;
-                }
+                for (int b = 0; b < 4; b++) count_sym((w >> (8 * b)) & 0xFFu);
             } else {
 #pragma unroll
-                for (int b = 0; b < 2; b++) {
-                    const uint32_t s = (w >> (16 * b)) & 0xFFFFu;
-                    if (s < K) atomicAdd(&h[s << rep_log2], 1u); else oob = 1;
-                }
+                for (int b = 0; b < 2; b++) count_sym((w >> (16 * b)) & 0xFFFFu);
             }
         };
         constexpr int NLOAD = 4;  // 16-byte loads in flight per thread
@@ -296,17 +293,14 @@ __global__ void __launch_bounds__(256) hist_chunks_kernel(const SYM* __restrict_
         }
         done = nvec * PER;
     }
-    for (uint64_t i = done + threadIdx.x; i < cnt; i += blockDim.x) {
-        uint32_t s = p[i];
-        if (s < K) atomicAdd(&h[s << rep_log2], 1u); else oob = 1;
-    }
+    for (uint64_t i = done + threadIdx.x; i < cnt; i += blockDim.x) count_sym(p[i]);
     __syncthreads();
     for (uint32_t b = threadIdx.x; b < K; b += blockDim.x) {
         uint32_t t = 0;
         for (uint32_t r = 0; r < REP; r++) t += s_hist[(b << rep_log2) + ((r + b) & (REP - 1))];
         counts[chunk * K + b] = t;
     }
-    if (oob) atomicOr(bad, 1u);
+    if (!FULL && threadIdx.x < REP && s_hist[(K << rep_log2) + threadIdx.x]) atomicOr(bad, 1u);
 }
 
 // ============================================================ K2 model build
