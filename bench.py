@@ -60,14 +60,15 @@ def parse_args():
     p.add_argument("--dec-threads", type=int, default=0)
     p.add_argument("--restart", type=int, default=-1,
                    help="restart points every this many symbols of a chunk (several decoder lanes per chunk); "
-                        "0 = none, -1 = chunk / 16 (static byte table), / 8 (per-chunk tables), / 4 (u16 symbols)")
+                        "0 = none, -1 = chunk / 16 (static byte table), / 8 (per-chunk tables; / 16 from 128 Ki symbols), / 4 (u16 symbols)")
     a = p.parse_args()
     if a.alphabet > 256 and a.chunk == 65536:
         a.chunk = 32768  # 64 KiB chunks of u16 symbols
     if a.restart < 0:
         # lanes per chunk for the decoder: 16 for byte chunks of one static table (measured best: 19 warps per SM in
         # three even waves), 8 for per-chunk tables, 4 for the 4096-symbol alphabet (profiles/r02b_sweep.jsonl)
-        parts = 8 if a.mode == "adaptive" else (4 if a.alphabet > 256 else 16)
+        # (per-chunk tables at 256 KiB chunks: 16 lanes decode in 5.8 ms against 7.8 with 8, profiles/r02c_sweep.jsonl)
+        parts = (16 if a.chunk >= 131072 else 8) if a.mode == "adaptive" else (4 if a.alphabet > 256 else 16)
         a.restart = a.chunk // parts if a.chunk % (64 * parts) == 0 else (a.chunk // 4 if a.chunk % 256 == 0 else 0)
     if a.seed is None:
         a.seed = 0x5EED0002 if a.mode == "adaptive" else (0x5EED0003 if a.alphabet > 256 else 0x5EED0001)
